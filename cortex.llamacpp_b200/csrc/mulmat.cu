@@ -1,0 +1,142 @@
+// mulmat.cu -- MUL_MAT / MUL_MAT_ID dispatch.
+//
+// Replaces ggml_cuda_mul_mat (ggml-cuda.cu:1845-1906) and ggml_cuda_mul_mat_id (:1962-2098).
+// Semantics follow the CPU oracle (ggml_compute_forward_mul_mat, ggml-cpu.c:8708-8900): src1 rows are
+// quantised to the weight type's vec_dot_type (q8_0 for Q4_0/Q8_0, q8_K for K-quants, f16/bf16 for
+// 16-bit float weights) and every dst element is one dot product.
+//   quantised W, M <= GEMV_MAX_COLS : quantise (quant.cu) + streaming GEMV (gemv.cu)
+//   quantised W, M  > GEMV_MAX_COLS : quantise + tcgen05 int8 GEMM (gemm_i8.cu) when available, else GEMV in column chunks
+//   F32/F16/BF16 W                  : warp-per-row float kernel below (router, small test shapes)
+// MUL_MAT_ID: device-side expert routing -- no host sync on `ids` (the reference copies ids to the host and
+// loops experts there).
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);
+int launch_gemm_i8(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
+                   int64_t ncols, float *dst, size_t dst_col_stride, bool *handled);
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// float weights: dst[n, m, i2, i3] = sum_k W[k, n, i2/r2, i3/r3] * x[k, m, i2, i3]; one warp per (n, m, batch)
+// ---------------------------------------------------------------------------------------------------
+template <typename WT> __device__ __forceinline__ float w_to_float(WT v);
+template <> __device__ __forceinline__ float w_to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float w_to_float<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float w_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+// the CPU converts src1 to the weight's vec_dot_type before the dot
+template <typename WT> __device__ __forceinline__ float x_round(float v);
+template <> __device__ __forceinline__ float x_round<float>(float v) { return v; }
+template <> __device__ __forceinline__ float x_round<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float x_round<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <typename WT>
+__global__ void __launch_bounds__(128) mul_mat_float_kernel(b200_tensor w, b200_tensor x, b200_tensor d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int64_t N = d.ne[0], M = d.ne[1];
+    const int64_t total = N * M * d.ne[2] * d.ne[3];
+    if (gw >= total) return;
+    const int64_t n = gw % N, m = (gw / N) % M, i2 = (gw / (N * M)) % d.ne[2], i3 = gw / (N * M * d.ne[2]);
+    const int64_t w2 = i2 / (d.ne[2] / w.ne[2]), w3 = i3 / (d.ne[3] / w.ne[3]);
+    const char *wp = (const char *)w.data + n * w.nb[1] + w2 * w.nb[2] + w3 * w.nb[3];
+    const char *xp = (const char *)x.data + m * x.nb[1] + i2 * x.nb[2] + i3 * x.nb[3];
+    float acc = 0.0f;
+    for (int64_t k = lane; k < w.ne[0]; k += 32) {
+        const float wv = w_to_float<WT>(*(const WT *)(wp + k * w.nb[0]));
+        const float xv = x_round<WT>(*(const float *)(xp + k * x.nb[0]));
+        acc = fmaf(wv, xv, acc);
+    }
+    acc = warp_reduce_sum(acc);
+    if (lane == 0) *(float *)((char *)d.data + n * d.nb[0] + m * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]) = acc;
+}
+
+int mul_mat_float(b200_ctx *ctx, const b200_tensor &w, const b200_tensor &x, const b200_tensor &d) {
+    const int64_t total = tensor_nelements(d);
+    if (total == 0) return B200_OK;
+    const unsigned grid = (unsigned)((total + 3) / 4);
+    switch (w.type) {
+        case B200_TYPE_F32:  mul_mat_float_kernel<float><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
+        case B200_TYPE_F16:  mul_mat_float_kernel<__half><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
+        case B200_TYPE_BF16: mul_mat_float_kernel<__nv_bfloat16><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
+        default: return B200_ERR_UNSUPPORTED;
+    }
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+// one quantised matmul: W [N rows of K] x cols (already quantised into `act`) -> dst
+int mul_mat_q_cols(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int64_t ncols,
+                   float *dst, size_t dst_stride, bool w_const) {
+    if (ncols > 8) {
+        bool handled = false;
+        int rc = launch_gemm_i8(ctx, type, W, rb, N, K, act, ncols, dst, dst_stride, &handled);
+        if (rc) return rc;
+        if (handled) return B200_OK;
+    }
+    const size_t col_bytes = ActLayout::make(b200_act_mode_q8k(type), K).col_bytes;
+    // GEMV path; launch_gemv chunks columns by what fits in shared memory
+    for (int64_t c0 = 0; c0 < ncols; c0 += 64) {
+        const int nc = (int)(ncols - c0 < 64 ? ncols - c0 : 64);
+        int rc = launch_gemv(ctx, type, W, rb, N, K, act + (size_t)c0 * col_bytes, nc, dst + (size_t)c0 * dst_stride, dst_stride, w_const);
+        if (rc) return rc;
+    }
+    return B200_OK;
+}
+
+bool quant_mul_mat_shape_ok(const b200_tensor &w, const b200_tensor &x, const b200_tensor &d) {
+    if (!b200_type_is_quant(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    const int64_t K = w.ne[0];
+    if (K % b200_type_block_elems(w.type) != 0 || K % 32 != 0) return false;
+    if (x.ne[0] != K || x.nb[0] != 4 || d.nb[0] != 4) return false;
+    if (w.nb[0] != (uint64_t)b200_type_block_bytes(w.type)) return false;
+    if (w.nb[1] != b200_row_bytes(w.type, K)) return false;            // rows back to back (GGUF layout)
+    if ((x.nb[1] & 15) || ((uintptr_t)x.data & 15)) return false;     // float4 loads in the quantiser
+    if ((w.type == B200_TYPE_Q4_K || w.type == B200_TYPE_Q5_K) && (((uintptr_t)w.data & 15) || (w.nb[2] & 15) || (w.nb[3] & 15))) return false;
+    if (w.ne[2] == 0 || w.ne[3] == 0 || x.ne[2] % w.ne[2] || x.ne[3] % w.ne[3]) return false;
+    return true;
+}
+
+}  // namespace
+
+bool supports_mul_mat(const b200_op *op) {
+    const b200_tensor &w = op->src[0], &x = op->src[1], &d = op->dst;
+    if (x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    if (w.type == B200_TYPE_F32 || w.type == B200_TYPE_F16 || w.type == B200_TYPE_BF16) {
+        return w.ne[2] > 0 && w.ne[3] > 0 && d.ne[2] % w.ne[2] == 0 && d.ne[3] % w.ne[3] == 0;
+    }
+    return quant_mul_mat_shape_ok(w, x, d);
+}
+
+int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
+    const b200_tensor &w = op->src[0], &x = op->src[1], &d = op->dst;
+    if (!b200_type_is_quant(w.type)) return mul_mat_float(ctx, w, x, d);
+    if (!quant_mul_mat_shape_ok(w, x, d)) { b200_set_error("mul_mat: unsupported layout"); return B200_ERR_UNSUPPORTED; }
+    const int64_t K = w.ne[0], N = w.ne[1], M = x.ne[1];
+    const int q8k = b200_act_mode_q8k(w.type);
+    const ActLayout L = ActLayout::make(q8k, K);
+    const size_t rb = b200_row_bytes(w.type, K);
+    const bool w_const = (w.flags & B200_TENSOR_FLAG_WEIGHT) != 0;
+    // quantise every src1 column of every batch once
+    const int64_t nbatch = x.ne[2] * x.ne[3];
+    uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)(M * nbatch));
+    if (!act) return B200_ERR_ALLOC;
+    for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+        for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+            const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+            int rc = launch_quantize_act(ctx, q8k, xp, x.nb[1], K, M, act + (size_t)((i3 * x.ne[2] + i2) * M) * L.col_bytes);
+            if (rc) return rc;
+        }
+    for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+        for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+            const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+            const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+            float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+            int rc = mul_mat_q_cols(ctx, w.type, wp, rb, N, K, act + (size_t)((i3 * x.ne[2] + i2) * M) * L.col_bytes, M, dp,
+                                    d.nb[1] / 4, w_const);
+            if (rc) return rc;
+        }
+    return B200_OK;
+}

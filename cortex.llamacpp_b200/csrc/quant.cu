@@ -1,0 +1,169 @@
+// quant.cu -- activation quantisers.
+//
+// Replaces quantize_q8_1 (ggml-cuda/quantize.cu:4-38) with quantisers that reproduce the CPU oracle's
+// activation formats bit for bit, because parity is defined against the CPU backend:
+//   q8_K mode (K-quant weights): quantize_row_q8_K_ref, ggml-quants.c:2479-2513
+//       iscale = -127/max (max = signed value of the FIRST max-|x| element), q = min(127, RNE(iscale*x)),
+//       d = 1/iscale (f32), bsums per 16
+//   q8_0 mode (Q4_0/Q8_0 weights, quantised-K attention): quantize_row_q8_0 AVX2 path,
+//       ggml-cpu-quants.c:808-860:  d = amax/127 -> fp16, id = 127/amax, q = RNE(x*id)
+// Output goes to the split "activation scratch" layout described in common.cuh (ActLayout).
+#include "common.cuh"
+
+namespace {
+
+// one warp per 256 elements; lane owns 8 consecutive elements
+__global__ void __launch_bounds__(128) quantize_q8k_kernel(const float *__restrict__ x, size_t x_col_stride, int64_t K,
+                                                           int64_t ncols, uint8_t *__restrict__ out, ActLayout L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nblk = K / 256;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= nblk * ncols) return;
+    const int64_t col = gw / nblk, b = gw % nblk;
+    const float *xp = (const float *)((const char *)x + col * x_col_stride) + b * 256 + lane * 8;
+    uint8_t *oc = out + col * L.col_bytes;
+
+    float v[8];
+    {
+        const float4 a = *(const float4 *)xp, c = *(const float4 *)(xp + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    }
+    float amax = 0.0f, mx = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float a = fabsf(v[j]);
+        if (a > amax) { amax = a; mx = v[j]; }
+    }
+    int src = lane;   // first-occurrence tie break: equal |x| -> lower index wins (the reference scans in order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int   os = __shfl_xor_sync(0xffffffffu, src, o);
+        if (oa > amax || (oa == amax && os < src)) { amax = oa; mx = om; src = os; }
+    }
+    int8_t q[8];
+    int lsum = 0;
+    float d = 0.0f;
+    if (amax != 0.0f) {
+        const float iscale = __fdiv_rn(-127.0f, mx);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int t = __float2int_rn(__fmul_rn(iscale, v[j]));
+            t = t > 127 ? 127 : t;
+            q[j] = (int8_t)t;
+            lsum += t;
+        }
+        d = __fdiv_rn(1.0f, iscale);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) q[j] = 0;
+    }
+    *(uint2 *)(oc + b * 256 + lane * 8) = *(const uint2 *)q;
+    const int pair = lsum + __shfl_xor_sync(0xffffffffu, lsum, 1);
+    if ((lane & 1) == 0) ((int16_t *)(oc + L.off_sums))[b * 16 + (lane >> 1)] = (int16_t)pair;
+    if (lane == 0) ((float *)(oc + L.off_d))[b] = d;
+}
+
+// one warp per 256 elements = 8 blocks of 32; 4 lanes per block
+__global__ void __launch_bounds__(128) quantize_q80_kernel(const float *__restrict__ x, size_t x_col_stride, int64_t K,
+                                                           int64_t ncols, uint8_t *__restrict__ out, ActLayout L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nchunk = (K + 255) / 256;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= nchunk * ncols) return;
+    const int64_t col = gw / nchunk, c = gw % nchunk;
+    const int64_t e0 = c * 256 + lane * 8;
+    const bool valid = e0 < K;                 // K % 32 == 0 so a block is entirely valid or not
+    const float *xp = (const float *)((const char *)x + col * x_col_stride) + e0;
+    uint8_t *oc = out + col * L.col_bytes;
+
+    float v[8];
+    if (valid) {
+        const float4 a = *(const float4 *)xp, b = *(const float4 *)(xp + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0.0f;
+    }
+    float amax = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) amax = fmaxf(amax, fabsf(v[j]));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    const float d  = __fdiv_rn(amax, 127.0f);
+    const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+    int8_t q[8];
+    int lsum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int t = __float2int_rn(__fmul_rn(v[j], id));
+        q[j] = (int8_t)t;
+        lsum += t;
+    }
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+    if (!valid) return;
+    *(uint2 *)(oc + e0) = *(const uint2 *)q;
+    if ((lane & 3) == 0) {
+        const int64_t bi = e0 / 32;
+        ((float *)(oc + L.off_d))[bi] = __half2float(__float2half_rn(d));
+        ((int16_t *)(oc + L.off_sums))[bi] = (int16_t)lsum;
+    }
+}
+
+// scratch layout -> the reference's canonical block bytes (test hook only)
+__global__ void repack_q8k_kernel(const uint8_t *__restrict__ in, ActLayout L, int64_t ncols, uint8_t *__restrict__ blocks) {
+    const int64_t nblk = L.K / 256;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblk * ncols) return;
+    const int64_t col = i / nblk, b = i % nblk;
+    const uint8_t *ic = in + col * L.col_bytes;
+    uint8_t *o = blocks + i * 292;
+    *(float *)o = ((const float *)(ic + L.off_d))[b];
+    for (int j = 0; j < 256; j++) o[4 + j] = ic[b * 256 + j];
+    for (int j = 0; j < 16; j++) *(int16_t *)(o + 260 + 2 * j) = ((const int16_t *)(ic + L.off_sums))[b * 16 + j];
+}
+__global__ void repack_q80_kernel(const uint8_t *__restrict__ in, ActLayout L, int64_t ncols, uint8_t *__restrict__ blocks) {
+    const int64_t nblk = L.K / 32;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblk * ncols) return;
+    const int64_t col = i / nblk, b = i % nblk;
+    const uint8_t *ic = in + col * L.col_bytes;
+    uint8_t *o = blocks + i * 34;
+    *(__half *)o = __float2half_rn(((const float *)(ic + L.off_d))[b]);   // exact: value is already an fp16
+    for (int j = 0; j < 32; j++) o[2 + j] = ic[b * 32 + j];
+}
+
+}  // namespace
+
+int launch_quantize_act(b200_ctx *ctx, int q8k, const float *x, size_t x_col_stride, int64_t K, int64_t ncols, uint8_t *scratch) {
+    const ActLayout L = ActLayout::make(q8k, K);
+    const int64_t warps = (q8k ? K / 256 : (K + 255) / 256) * ncols;
+    if (warps == 0) return B200_OK;
+    const unsigned grid = (unsigned)((warps + 3) / 4);
+    if (q8k) quantize_q8k_kernel<<<grid, 128, 0, ctx->stream>>>(x, x_col_stride, K, ncols, scratch, L);
+    else     quantize_q80_kernel<<<grid, 128, 0, ctx->stream>>>(x, x_col_stride, K, ncols, scratch, L);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_quantize_act(b200_ctx *ctx, int32_t act_type, const float *x, void *blocks, int64_t K, int64_t rows) {
+    if (!ctx) return B200_ERR_FAILED;
+    const int q8k = act_type == B200_TYPE_Q8_K;
+    if (!q8k && act_type != B200_TYPE_Q8_0) { b200_set_error("quantize_act: type %d", act_type); return B200_ERR_UNSUPPORTED; }
+    if (K % (q8k ? 256 : 32) != 0) { b200_set_error("quantize_act: K=%lld", (long long)K); return B200_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const ActLayout L = ActLayout::make(q8k, K);
+    uint8_t *s = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)rows);
+    if (!s) return B200_ERR_ALLOC;
+    int rc = launch_quantize_act(ctx, q8k, x, (size_t)K * 4, K, rows, s);
+    if (rc) return rc;
+    const int64_t n = (K / (q8k ? 256 : 32)) * rows;
+    if (q8k) repack_q8k_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(s, L, rows, (uint8_t *)blocks);
+    else     repack_q80_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(s, L, rows, (uint8_t *)blocks);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}

@@ -1,0 +1,141 @@
+"""GPU parity tests (through the C ABI): activation quantisers and the decode GEMV against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import reflib as R
+from util import dev_bytes, rand_quant_rows, to_dev
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath_golden.npz"))
+
+
+def gpu_quantize(b200, ctx, ta, x):
+    rows, K = x.shape
+    xd = to_dev(x)
+    out = dev_bytes(rows * R.row_size(ta, K), 0)
+    b200.check(b200.lib().b200_quantize_act(ctx.h, ta, xd.data_ptr(), out.data_ptr(), K, rows), "quantize_act")
+    ctx.sync()
+    return out.cpu().numpy().reshape(rows, -1)
+
+
+@pytest.mark.parametrize("ta", [R.Q8_0, R.Q8_K])
+def test_act_quantiser_bit_exact_vs_golden(b200, ctx, ta):
+    got = gpu_quantize(b200, ctx, ta, G["act_x"])
+    want = G["act_" + R.TYPE_NAMES[ta]]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("ta", [R.Q8_0, R.Q8_K])
+def test_act_quantiser_bit_exact_vs_oracle_large(b200, ctx, ta):
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((7, 14336)) * rng.uniform(0.01, 30, (7, 1))).astype(np.float32)
+    x[3, 512:768] = 0
+    assert np.array_equal(gpu_quantize(b200, ctx, ta, x), R.orc_quantize_act(ta, x))
+
+
+def gpu_mul_mat(b200, ctx, t, W, x, N, K, flags=0):
+    M = x.shape[0]
+    pad = b200.lib().b200_alloc_size(t, (C.c_int64 * 4)(K, N, 1, 1), W.size)
+    Wd = dev_bytes(pad, 0)
+    Wd[:W.size] = to_dev(W)
+    xd = to_dev(x)
+    out = dev_bytes(M * N * 4, 0xFF)
+    import torch
+    torch.cuda.synchronize()
+    op = b200.make_op(b200.OP_MUL_MAT, b200.tensor(out.data_ptr(), b200.F32, [N, M]),
+                      [b200.tensor(Wd.data_ptr(), t, [K, N], flags=flags), b200.tensor(xd.data_ptr(), b200.F32, [K, M])])
+    assert b200.supports(op)
+    ctx.compute_op(op)
+    ctx.sync()
+    return out.cpu().numpy().view(np.float32).reshape(M, N)
+
+
+@pytest.mark.parametrize("K", [256, 1280])
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+def test_gemv_vs_golden_reference_output(b200, ctx, t, K):
+    name = "%s_%d" % (R.TYPE_NAMES[t], K)
+    got = gpu_mul_mat(b200, ctx, t, G["mm_W_" + name], G["mm_x_%d" % K], 12, K)
+    want = G["mm_out_" + name]
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+SHAPES = [(16, 256), (17, 512), (333, 2048), (1024, 4096), (600, 5632), (4096, 4096), (300, 14336), (64, 28672)]
+
+
+@pytest.mark.parametrize("N,K", SHAPES)
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+def test_block_sums_bit_exact(b200, ctx, t, N, K):
+    """per-block integer dot products of the CUDA pipeline == the oracle's, bit for bit"""
+    rng = np.random.default_rng(N * 31 + K + t)
+    N = min(N, 96)       # the oracle is scalar C; keep it to seconds
+    W = rand_quant_rows(t, N, K, rng)
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    nb = K // R.BLOCK[t][0]
+    Wd = dev_bytes(W.size + 256, 0)
+    Wd[:W.size] = to_dev(W)
+    xd = to_dev(x)
+    P = dev_bytes(N * nb * 4)
+    M = dev_bytes(N * nb * 4)
+    b200.check(b200.lib().b200_block_sums(ctx.h, t, Wd.data_ptr(), xd.data_ptr(), N, K, P.data_ptr(), M.data_ptr()), "block_sums")
+    ctx.sync()
+    Pg = P.cpu().numpy().view(np.int32).reshape(N, nb)
+    Mg = M.cpu().numpy().view(np.int32).reshape(N, nb)
+    act = R.orc_quantize_act(R.act_type(t), x)[0]
+    rb = R.row_size(t, K)
+    for n in range(N):
+        p, m = R.orc_block_sums(t, W.reshape(N, rb)[n], act, K)
+        assert np.array_equal(p, Pg[n]), "P differs row %d" % n
+        assert np.array_equal(m, Mg[n]), "M differs row %d" % n
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("N,K", SHAPES)
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+def test_gemv_vs_oracle(b200, ctx, t, N, K, M):
+    if M > 1 and (N, K) not in [(17, 512), (1024, 4096), (300, 14336)]:
+        pytest.skip("multi-column cases on a subset of shapes")
+    rng = np.random.default_rng(N + K + t + M)
+    W = rand_quant_rows(t, N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    got = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    rows = np.unique(np.concatenate([np.arange(min(N, 24)), rng.integers(0, N, 24), [N - 1]]))
+    rb = R.row_size(t, K)
+    Wsub = W.reshape(N, rb)[rows].reshape(-1)
+    want = R.orc_mul_mat(t, Wsub, x, len(rows), K)
+    scale = max(np.abs(want).max(), 1e-6)
+    assert np.abs(got[:, rows] - want).max() <= 3e-6 * scale
+    assert np.isfinite(got).all()
+
+
+def test_gemv_deterministic(b200, ctx):
+    rng = np.random.default_rng(9)
+    N, K, t = 4096, 14336, R.Q4_K
+    W = rand_quant_rows(t, N, K, rng)
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    a = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    b = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("wt", ["f32", "f16"])
+def test_float_weight_matmul(b200, ctx, wt):
+    rng = np.random.default_rng(2)
+    N, K, M = 8, 4096, 3
+    w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    if wt == "f16":
+        wb, t = w.astype(np.float16), R.F16
+    else:
+        wb, t = w, R.F32
+    Wd, xd = to_dev(wb.view(np.uint8).reshape(-1)), to_dev(x)
+    out = dev_bytes(M * N * 4)
+    op = b200.make_op(b200.OP_MUL_MAT, b200.tensor(out.data_ptr(), b200.F32, [N, M]),
+                      [b200.tensor(Wd.data_ptr(), t, [K, N]), b200.tensor(xd.data_ptr(), b200.F32, [K, M])])
+    ctx.compute_op(op)
+    ctx.sync()
+    got = out.cpu().numpy().view(np.float32).reshape(M, N)
+    want = R.orc_mul_mat(t, wb.view(np.uint8).reshape(-1), x, N, K)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
