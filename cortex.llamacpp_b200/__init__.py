@@ -93,6 +93,7 @@ def lib():
         "b200_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "b200_quantize_act": (C.c_int, [vp, i32, vp, vp, i64, i64]),
         "b200_block_sums": (C.c_int, [vp, i32, vp, vp, i64, i64, vp, vp]),
+        "b200_debug_set_prof": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here == the .so does not export what the header declares

@@ -119,6 +119,8 @@ int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     return B200_OK;
 }
 
+int b200_debug_set_prof(b200_ctx *ctx, void *buf) { ctx->prof_buf = buf; return B200_OK; }
+
 // ---- memory ----
 void *b200_malloc(int device, size_t size) {
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;

@@ -128,6 +128,7 @@ struct b200_ctx {
     int           opt_pdl         = 0;
     GraphCache *  graph_cache = nullptr;
     bool          capturing = false;
+    void *        prof_buf = nullptr;   // debug: per-CTA timestamps (b200_debug_set_prof)
 
     void *get_scratch(int slot, size_t size);   // grows (sync + realloc) when too small; nullptr on OOM
 };

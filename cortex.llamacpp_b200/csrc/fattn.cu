@@ -1,0 +1,488 @@
+// fattn.cu -- FLASH_ATTN_EXT over f16 / q8_0 / q4_0 KV caches (decode and batched), split-KV.
+//
+// Replaces ggml_cuda_flash_attn_ext (fattn.cu:244-319), flash_attn_vec_ext_f32 (fattn-vec-f32.cuh:4-282), the
+// combine kernel (fattn-common.cuh:609-650) and the "dequantise the whole cache to f16 first" path of the
+// reference's mma kernel (fattn-common.cuh:720-746).  Semantics follow the CPU oracle
+// (ggml_compute_forward_flash_attn_ext_f16, ggml-cpu.c:12221-12434):
+//   * f16 K      : Q rows are rounded to f16, K.Q products are exact, accumulated in f32
+//   * q8_0/q4_0 K: Q rows are quantised to q8_0 exactly like quantize_row_q8_0 (RNE, d=amax/127 as f16); the
+//                  per-32 integer dots are EXACT (integers carried in f16 through the tensor core, |sum| < 2^24)
+//                  and scaled by d_k*d_q in f32 like ggml_vec_dot_q8_0_q8_0 / q4_0_q8_0
+//   * online softmax in f32, -inf mask cells contribute nothing, ALiBi slope and logit softcap as the CPU
+//   * V: f16 as is; q8_0/q4_0 dequantised on the fly (d*q); P.V accumulated in f32 (the CPU uses an f16
+//     accumulator for f16 V -- ours is strictly more accurate; the difference is bounded in the tests)
+// Design: one CTA = one KV head x one tile of 16 query rows (GQA heads of the same KV head and/or several
+// query columns share every K/V byte) x one KV split.  The 4 warps of a CTA take alternating 32-position KV
+// tiles; K/V tiles are staged in shared memory (cp.async for f16, convert-on-load for quantised), fed to
+// mma.sync.m16n8k16 via ldmatrix.  32-position tiles whose mask is -inf for every query of the CTA are
+// skipped before any K/V byte is requested (unified multi-slot KV cache).  Splits are merged by a small
+// combine kernel (log-sum-exp).  A tcgen05 variant for long prefill is future work.
+#include "common.cuh"
+
+namespace {
+
+enum { KV_F16 = 0, KV_Q8_0 = 1, KV_Q4_0 = 2 };
+constexpr int BK = 32;          // kv positions per warp tile
+constexpr int NWARP = 4;
+
+struct FaParams {
+    const char *q; uint64_t q_nb1, q_nb2, q_nb3;
+    const char *k; uint64_t k_nb1, k_nb2, k_nb3;
+    const char *v; uint64_t v_nb1, v_nb2, v_nb3;
+    const char *mask; uint64_t m_nb1;
+    float *dst;
+    float *part;                 // [tile][split][16][D + 2]
+    int n_q, n_kv, H, Hkv, gq, HG, QC, n_headtiles, n_coltiles, n_splits, kv_per_split;
+    float scale, softcap, max_bias, m0, m1;
+    int n_head_log2;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const void *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const void *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void *s, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *(const uint32_t *)&h;
+}
+
+// stage one 32 x D tile of K or V into shared memory as f16 [32][D+8]; quantised types are converted on load.
+// RAWINT: keep the integer quants (K path: scales go to `sc`), else dequantise d*q (V path).
+template <int D, int T, bool RAWINT>
+__device__ __forceinline__ void stage_tile(__half *s, float *sc, const char *g, uint64_t nb1, int kv0, int lane) {
+    constexpr int LD = D + 8;
+    if (T == KV_F16) {
+        constexpr int CH = D / 8;                      // 16-byte chunks per row
+        for (int c = lane; c < BK * CH; c += 32) {
+            const int r = c / CH, cc = c % CH;
+            cp_async16(s + r * LD + cc * 8, g + (uint64_t)(kv0 + r) * nb1 + cc * 16);
+        }
+    } else {
+        // one lane per kv row: rows are 8-byte aligned (q8_0: 34*D/32, q4_0: 18*D/32 bytes with D = 128)
+        constexpr int RB = (T == KV_Q8_0 ? 34 : 18) * (D / 32);
+        const uint2 *src = (const uint2 *)(g + (uint64_t)(kv0 + lane) * nb1);
+        uint2 raw[RB / 8];
+#pragma unroll
+        for (int i = 0; i < RB / 8; i++) raw[i] = src[i];
+        const uint8_t *rb = (const uint8_t *)raw;
+        __half *row = s + lane * LD;
+#pragma unroll
+        for (int b = 0; b < D / 32; b++) {
+            const uint8_t *blk = rb + b * (T == KV_Q8_0 ? 34 : 18);
+            const float d = __half2float(*(const __half *)blk);
+            if (RAWINT) sc[lane * (D / 32) + b] = d;
+            const float m = RAWINT ? 1.0f : d;
+            if (T == KV_Q8_0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float a = (float)(int8_t)blk[2 + j], c = (float)(int8_t)blk[3 + j];
+                    *(uint32_t *)(row + b * 32 + j) = pack_h2(__fmul_rn(a, m), __fmul_rn(c, m));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const int q0 = blk[2 + j], q1 = blk[3 + j];
+                    *(uint32_t *)(row + b * 32 + j)      = pack_h2(__fmul_rn((float)((q0 & 15) - 8), m), __fmul_rn((float)((q1 & 15) - 8), m));
+                    *(uint32_t *)(row + b * 32 + 16 + j) = pack_h2(__fmul_rn((float)((q0 >> 4) - 8), m), __fmul_rn((float)((q1 >> 4) - 8), m));
+                }
+            }
+        }
+    }
+}
+
+template <int D, int KT, int VT>
+__global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) {
+    constexpr int LD = D + 8;
+    constexpr int NKS = D / 16;                  // k-steps of the QK product
+    constexpr int NDT = D / 8;                   // n-tiles of the PV product
+    constexpr int NB = D / 32;                   // 32-element blocks per row
+    constexpr bool KQ = KT != KV_F16;
+    extern __shared__ __align__(128) uint8_t fsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp staging: K tile, V tile, K scales
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + BK * NB * 4;
+    __half *sK = (__half *)(fsm + warp * WARP_BYTES);
+    __half *sV = sK + BK * LD;
+    float *sKs = (float *)(sV + BK * LD);
+
+    const int split = blockIdx.x;
+    int tile = blockIdx.y;
+    const int ct = tile % p.n_coltiles; tile /= p.n_coltiles;
+    const int ht = tile % p.n_headtiles;
+    const int hk = tile / p.n_headtiles;
+    const int c0 = ct * p.QC;
+
+    // rows owned by this lane in the mma layouts: r_lo = lane/4, r_hi = r_lo + 8
+    int rcol[2], rhead[2]; bool rvalid[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int r = (lane >> 2) + 8 * i;
+        const int hin = ht * p.HG + r % p.HG;
+        rcol[i] = c0 + r / p.HG;
+        rhead[i] = hk * p.gq + hin;
+        rvalid[i] = (r / p.HG) < p.QC && rcol[i] < p.n_q && hin < p.gq;
+    }
+
+    // ---- Q fragments (A operand), converted like the CPU converts Q for K's vec_dot_type -------------------
+    uint32_t qa[NKS][4];
+    float dq[2][NB];                      // q8_0 scales of my two rows (quantised K only)
+    {
+        float qv[2][NKS][4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float *qp = (const float *)(p.q + (uint64_t)rcol[i] * p.q_nb1 + (uint64_t)rhead[i] * p.q_nb2);
+#pragma unroll
+            for (int ks = 0; ks < NKS; ks++) {
+                const int kb = ks * 16 + (lane & 3) * 2;
+                if (rvalid[i]) {
+                    const float2 a = *(const float2 *)(qp + kb), b = *(const float2 *)(qp + kb + 8);
+                    qv[i][ks][0] = a.x; qv[i][ks][1] = a.y; qv[i][ks][2] = b.x; qv[i][ks][3] = b.y;
+                } else {
+                    qv[i][ks][0] = qv[i][ks][1] = qv[i][ks][2] = qv[i][ks][3] = 0.0f;
+                }
+            }
+            if (KQ) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    float amax = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) amax = fmaxf(amax, fmaxf(fabsf(qv[i][2 * b][e]), fabsf(qv[i][2 * b + 1][e])));
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                    const float d = __fdiv_rn(amax, 127.0f);
+                    const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+                    dq[i][b] = __half2float(__float2half_rn(d));
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        qv[i][2 * b][e] = (float)__float2int_rn(__fmul_rn(qv[i][2 * b][e], id));
+                        qv[i][2 * b + 1][e] = (float)__float2int_rn(__fmul_rn(qv[i][2 * b + 1][e], id));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < NKS; ks++) {
+            qa[ks][0] = pack_h2(qv[0][ks][0], qv[0][ks][1]);
+            qa[ks][1] = pack_h2(qv[1][ks][0], qv[1][ks][1]);
+            qa[ks][2] = pack_h2(qv[0][ks][2], qv[0][ks][3]);
+            qa[ks][3] = pack_h2(qv[1][ks][2], qv[1][ks][3]);
+        }
+    }
+
+    float slope[2] = {1.0f, 1.0f};
+    if (p.max_bias > 0.0f) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int h = rhead[i];
+            slope[i] = h < p.n_head_log2 ? powf(p.m0, (float)(h + 1)) : powf(p.m1, (float)(2 * (h - p.n_head_log2) + 1));
+        }
+    }
+
+    float o[NDT][4];
+#pragma unroll
+    for (int t = 0; t < NDT; t++) o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.0f;
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.0f, 0.0f};
+
+    const char *kbase = p.k + (uint64_t)hk * p.k_nb2;
+    const char *vbase = p.v + (uint64_t)hk * p.v_nb2;
+    const int kv_begin = split * p.kv_per_split;
+    const int kv_end = min(p.n_kv, kv_begin + p.kv_per_split);
+
+    for (int kv0 = kv_begin + warp * BK; kv0 < kv_end; kv0 += NWARP * BK) {
+        // ---- skip tiles that are fully masked for every query column of this CTA -------------------------
+        if (p.mask) {
+            bool any = false;
+            for (int c = 0; c < p.QC; c++) {
+                const int col = c0 + c;
+                if (col < p.n_q) {
+                    const __half mv = *(const __half *)(p.mask + (uint64_t)col * p.m_nb1 + (uint64_t)(kv0 + lane) * 2);
+                    any |= !(__hisinf(mv) && __half2float(mv) < 0.0f);
+                }
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+        }
+        __syncwarp();
+        stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane);
+        stage_tile<D, VT, false>(sV, nullptr, vbase, p.v_nb1, kv0, lane);
+        if (KT == KV_F16 || VT == KV_F16) cp_async_wait_all();
+        __syncwarp();
+
+        // ---- S = Q K^T  (16 x 32) ---------------------------------------------------------------------
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < NKS; ks += 2) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(b0, b1, b2, b3, sK + (nt * 8 + (lane & 7)) * LD + ks * 16 + (lane >> 3) * 8);
+                if (KQ) {
+                    float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    mma16816(t, qa[ks], b0, b1);
+                    mma16816(t, qa[ks + 1], b2, b3);
+                    const int b = ks >> 1;
+                    const int kvc = nt * 8 + (lane & 3) * 2;
+                    const float dk0 = sKs[kvc * NB + b], dk1 = sKs[(kvc + 1) * NB + b];
+                    s[nt][0] += t[0] * (dk0 * dq[0][b]); s[nt][1] += t[1] * (dk1 * dq[0][b]);
+                    s[nt][2] += t[2] * (dk0 * dq[1][b]); s[nt][3] += t[3] * (dk1 * dq[1][b]);
+                } else {
+                    mma16816(s[nt], qa[ks], b0, b1);
+                    mma16816(s[nt], qa[ks + 1], b2, b3);
+                }
+            }
+        }
+        // ---- scale, softcap, mask, online softmax ---------------------------------------------------------
+        float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int kvc = kv0 + nt * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                float v0 = s[nt][2 * i] * p.scale, v1 = s[nt][2 * i + 1] * p.scale;
+                if (p.softcap != 0.0f) { v0 = p.softcap * tanhf(v0); v1 = p.softcap * tanhf(v1); }
+                if (p.mask && rvalid[i]) {
+                    const __half2 mv = *(const __half2 *)(p.mask + (uint64_t)rcol[i] * p.m_nb1 + (uint64_t)kvc * 2);
+                    v0 += slope[i] * __low2float(mv);
+                    v1 += slope[i] * __high2float(mv);
+                }
+                s[nt][2 * i] = v0; s[nt][2 * i + 1] = v1;
+                tmax[i] = fmaxf(tmax[i], fmaxf(v0, v1));
+            }
+        }
+        float corr[2], muse[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            tmax[i] = fmaxf(tmax[i], __shfl_xor_sync(0xffffffffu, tmax[i], 1));
+            tmax[i] = fmaxf(tmax[i], __shfl_xor_sync(0xffffffffu, tmax[i], 2));
+            const float mnew = fmaxf(mrow[i], tmax[i]);
+            muse[i] = mnew == -INFINITY ? 0.0f : mnew;
+            corr[i] = mrow[i] == -INFINITY ? 0.0f : expf(mrow[i] - muse[i]);
+            mrow[i] = mnew;
+            lrow[i] *= corr[i];
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float p0 = expf(s[nt][2 * i] - muse[i]), p1 = expf(s[nt][2 * i + 1] - muse[i]);
+                s[nt][2 * i] = p0; s[nt][2 * i + 1] = p1;
+                lrow[i] += p0 + p1;
+            }
+#pragma unroll
+        for (int t = 0; t < NDT; t++) { o[t][0] *= corr[0]; o[t][1] *= corr[0]; o[t][2] *= corr[1]; o[t][3] *= corr[1]; }
+        // ---- O += P V --------------------------------------------------------------------------------------
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            uint32_t pa[4];
+            pa[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            pa[3] = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int dt = 0; dt < NDT; dt += 2) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(b0, b1, b2, b3, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + dt * 8 + (lane >> 4) * 8);
+                mma16816(o[dt], pa, b0, b1);
+                mma16816(o[dt + 1], pa, b2, b3);
+            }
+        }
+    }
+
+    // ---- merge the 4 warps of the CTA (fixed warp order), then write the result or the split partial ----------
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        lrow[i] += __shfl_xor_sync(0xffffffffu, lrow[i], 1);
+        lrow[i] += __shfl_xor_sync(0xffffffffu, lrow[i], 2);
+    }
+    __syncthreads();                      // staging buffers are dead from here on
+    float *cm = (float *)fsm;             // [NWARP][16] max
+    float *cl = cm + NWARP * 16;          // [NWARP][16] sum
+    float *co = cl + NWARP * 16;          // [NWARP][16][D]
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int r = (lane >> 2) + 8 * i;
+        if ((lane & 3) == 0) { cm[warp * 16 + r] = mrow[i]; cl[warp * 16 + r] = lrow[i]; }
+#pragma unroll
+        for (int t = 0; t < NDT; t++) {
+            const int d = t * 8 + (lane & 3) * 2;
+            *(float2 *)(co + (warp * 16 + r) * D + d) = make_float2(o[t][2 * i], o[t][2 * i + 1]);
+        }
+    }
+    __syncthreads();
+    const int tile_id = blockIdx.y;
+    for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
+        const int r = e / D, d = e % D;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) M = fmaxf(M, cm[w * 16 + r]);
+        float val = 0.0f, L = 0.0f;
+        if (M != -INFINITY) {
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) {
+                const float mw = cm[w * 16 + r];
+                const float f = mw == -INFINITY ? 0.0f : expf(mw - M);
+                val += co[(w * 16 + r) * D + d] * f;
+                L += cl[w * 16 + r] * f;
+            }
+        }
+        const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+        const bool valid = (r / p.HG) < p.QC && col < p.n_q && hin < p.gq;
+        if (p.n_splits == 1) {
+            if (valid) p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = val / L;
+        } else {
+            float *pp = p.part + (((uint64_t)tile_id * p.n_splits + split) * 16 + r) * (D + 2);
+            pp[d] = val;
+            if (d == 0) { pp[D] = M; pp[D + 1] = L; }
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) fattn_combine_kernel(const FaParams p) {
+    int tile = blockIdx.x;
+    const int tile_id = tile;
+    const int ct = tile % p.n_coltiles; tile /= p.n_coltiles;
+    const int ht = tile % p.n_headtiles;
+    const int hk = tile / p.n_headtiles;
+    const int c0 = ct * p.QC;
+    for (int e = threadIdx.x; e < 16 * D; e += blockDim.x) {
+        const int r = e / D, d = e % D;
+        const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+        const bool valid = (r / p.HG) < p.QC && col < p.n_q && hin < p.gq;
+        if (!valid) continue;
+        const float *base = p.part + ((uint64_t)tile_id * p.n_splits * 16 + r) * (D + 2);
+        float M = -INFINITY;
+        for (int s = 0; s < p.n_splits; s++) M = fmaxf(M, base[(uint64_t)s * 16 * (D + 2) + D]);
+        float val = 0.0f, L = 0.0f;
+        for (int s = 0; s < p.n_splits; s++) {
+            const float *pp = base + (uint64_t)s * 16 * (D + 2);
+            const float ms = pp[D];
+            const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+            val += pp[d] * f;
+            L += pp[D + 1] * f;
+        }
+        p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = val / L;
+    }
+}
+
+int kv_kind(int type) { return type == B200_TYPE_F16 ? KV_F16 : type == B200_TYPE_Q8_0 ? KV_Q8_0 : type == B200_TYPE_Q4_0 ? KV_Q4_0 : -1; }
+
+template <int D, int KT, int VT>
+int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
+    constexpr int LD = D + 8;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + BK * (D / 32) * 4;
+    constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D) * 4;
+    constexpr int SMEM = NWARP * WARP_BYTES > COMBINE_BYTES ? NWARP * WARP_BYTES : COMBINE_BYTES;
+    auto kern = fattn_kernel<D, KT, VT>;
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set[ctx->device & 15] = true;
+    }
+    kern<<<dim3((unsigned)p.n_splits, (unsigned)n_tiles), NWARP * 32, SMEM, ctx->stream>>>(p);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (p.n_splits > 1) {
+        fattn_combine_kernel<D><<<(unsigned)n_tiles, 128, 0, ctx->stream>>>(p);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return B200_OK;
+}
+
+template <int D>
+int launch_fa_types(b200_ctx *ctx, const FaParams &p, int n_tiles, int kt, int vt) {
+    if (kt == KV_F16 && vt == KV_F16) return launch_fa<D, KV_F16, KV_F16>(ctx, p, n_tiles);
+    if (D == 128) {
+        if constexpr (D == 128) {
+            if (kt == KV_Q8_0 && vt == KV_Q8_0) return launch_fa<128, KV_Q8_0, KV_Q8_0>(ctx, p, n_tiles);
+            if (kt == KV_Q4_0 && vt == KV_Q4_0) return launch_fa<128, KV_Q4_0, KV_Q4_0>(ctx, p, n_tiles);
+        }
+    }
+    b200_set_error("flash_attn: K/V type combination not built");
+    return B200_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+bool supports_flash_attn_ext(const b200_op *op) {
+    const b200_tensor &q = op->src[0], &k = op->src[1], &v = op->src[2], &m = op->src[3], &d = op->dst;
+    if (q.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    const int64_t D = q.ne[0];
+    if (D != 64 && D != 128) return false;
+    if (k.ne[0] != D || v.ne[0] != D) return false;
+    const int kt = kv_kind(k.type), vt = kv_kind(v.type);
+    if (kt < 0 || vt < 0 || kt != vt) return false;
+    if (kt != KV_F16 && D != 128) return false;
+    if (q.ne[3] != 1 || k.ne[3] != 1 || v.ne[3] != 1) return false;
+    const int64_t H = q.ne[2], Hkv = k.ne[2], n_kv = k.ne[1];
+    if (Hkv == 0 || H % Hkv || v.ne[2] != Hkv || v.ne[1] != n_kv) return false;
+    if (n_kv % BK != 0 || n_kv == 0) return false;
+    if (q.nb[0] != 4 || (q.nb[1] & 7) || (q.nb[2] & 7) || ((uintptr_t)q.data & 7)) return false;
+    const uint64_t rowb = b200_row_bytes(k.type, D);
+    if (k.nb[0] != (uint64_t)b200_type_block_bytes(k.type) || v.nb[0] != k.nb[0]) return false;
+    const uint64_t al = kt == KV_F16 ? 15 : 7;
+    if ((k.nb[1] & al) || (k.nb[2] & al) || (v.nb[1] & al) || (v.nb[2] & al) || ((uintptr_t)k.data & al) || ((uintptr_t)v.data & al)) return false;
+    if (k.nb[1] < rowb || v.nb[1] < rowb) return false;
+    if (!tensor_is_contiguous(d)) return false;
+    if (op->n_src > 3 && m.data) {
+        if (m.type != B200_TYPE_F16 || m.ne[0] != n_kv || m.ne[1] < q.ne[1] || m.nb[0] != 2 || (m.nb[1] & 3) || ((uintptr_t)m.data & 3)) return false;
+    }
+    return true;
+}
+
+int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
+    const b200_tensor &q = op->src[0], &k = op->src[1], &v = op->src[2], &m = op->src[3], &d = op->dst;
+    FaParams p = {};
+    const int D = (int)q.ne[0];
+    p.q = (const char *)q.data; p.q_nb1 = q.nb[1]; p.q_nb2 = q.nb[2]; p.q_nb3 = q.nb[3];
+    p.k = (const char *)k.data; p.k_nb1 = k.nb[1]; p.k_nb2 = k.nb[2]; p.k_nb3 = k.nb[3];
+    p.v = (const char *)v.data; p.v_nb1 = v.nb[1]; p.v_nb2 = v.nb[2]; p.v_nb3 = v.nb[3];
+    const bool has_mask = op->n_src > 3 && m.data != nullptr;
+    p.mask = has_mask ? (const char *)m.data : nullptr; p.m_nb1 = has_mask ? m.nb[1] : 0;
+    p.dst = (float *)d.data;
+    p.n_q = (int)q.ne[1]; p.n_kv = (int)k.ne[1]; p.H = (int)q.ne[2]; p.Hkv = (int)k.ne[2];
+    p.gq = p.H / p.Hkv;
+    p.HG = p.gq < 16 ? p.gq : 16;
+    p.QC = 16 / p.HG;
+    p.n_headtiles = (p.gq + p.HG - 1) / p.HG;
+    p.n_coltiles = (p.n_q + p.QC - 1) / p.QC;
+    memcpy(&p.scale, &op->params[0], 4);
+    memcpy(&p.max_bias, &op->params[1], 4);
+    memcpy(&p.softcap, &op->params[2], 4);
+    if (p.softcap != 0.0f) p.scale /= p.softcap;
+    p.n_head_log2 = 1 << (int)floorf(log2f((float)p.H));
+    p.m0 = powf(2.0f, -(p.max_bias) / p.n_head_log2);
+    p.m1 = powf(2.0f, -(p.max_bias / 2.0f) / p.n_head_log2);
+    const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;
+    if (n_tiles == 0 || p.n_q == 0) return B200_OK;
+    // split the KV range so the grid covers the machine ~2-3x; each split is a multiple of NWARP*BK positions
+    const int unit = NWARP * BK;
+    const int max_splits = (p.n_kv + unit - 1) / unit;
+    int ns = (3 * ctx->sm_count + n_tiles - 1) / n_tiles;
+    if (ns > max_splits) ns = max_splits;
+    if (ns < 1) ns = 1;
+    p.kv_per_split = ((p.n_kv + ns - 1) / ns + unit - 1) / unit * unit;
+    ns = (p.n_kv + p.kv_per_split - 1) / p.kv_per_split;
+    p.n_splits = ns;
+    if (ns > 1) {
+        p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)n_tiles * ns * 16 * (D + 2) * 4);
+        if (!p.part) return B200_ERR_ALLOC;
+    }
+    const int kt = kv_kind(k.type), vt = kv_kind(v.type);
+    if (D == 128) return launch_fa_types<128>(ctx, p, n_tiles, kt, vt);
+    if (D == 64) return launch_fa_types<64>(ctx, p, n_tiles, kt, vt);
+    b200_set_error("flash_attn: D=%d", D);
+    return B200_ERR_UNSUPPORTED;
+}

@@ -10,6 +10,11 @@
 // Replaces vec_dot_q*_q8_1 (ggml-cuda/vecdotq.cuh:527-787): no q8_1, 128-bit shared loads where the
 // format allows, exact-integer min/offset handling through the activation block sums.
 //
+// Split in two halves so the kernel can keep the activation registers of an item live while it walks
+// several weight rows (bs1) or keep the decoded weights live while it walks several columns (bs2..4):
+//     load_act<TYPE>(A, col, it)            -> ActRegs<TYPE>
+//     item_dot<TYPE,DBG>(rowp, it, K, act)  -> float contribution of this item to (row, col)
+//
 // The file is host/device portable (B200_HD) so tests/host_emul can run the very same decode code on
 // the CPU against the oracle.
 #pragma once
@@ -63,6 +68,13 @@ B200_HD U4 ld128(const void *p) {
 #endif
 }
 B200_HD uint32_t ld32(const void *p) { return *(const uint32_t *)p; }
+B200_HD float u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { uint32_t u; float f; } cv; cv.u = u; return cv.f;
+#endif
+}
 
 // ---- shared-memory view of the quantised activations ------------------------------------------------
 // qs are stored per item with 16 bytes of padding (bank-conflict-free 128-bit loads at lane stride),
@@ -84,6 +96,7 @@ template <> struct Traits<T_Q4_0> { static constexpr int ITEM = 128, BLOCK = 32,
 template <> struct Traits<T_Q8_0> { static constexpr int ITEM = 128, BLOCK = 32,  BYTES = 34,  Q8K = 0; };
 
 template <int TYPE> B200_HD constexpr int act_item_stride() { return Traits<TYPE>::ITEM + 16; }
+template <int TYPE> B200_HD int num_items(int K) { return (K + Traits<TYPE>::ITEM - 1) / Traits<TYPE>::ITEM; }
 
 // six-bit (scale, min) of sub-block j from the 12 packed bytes (get_scale_min_k4, ggml-quants.c:631-639)
 B200_HD void scale_min_k4(uint32_t w0, uint32_t w1, uint32_t w2, int j, int &sc, int &mn) {
@@ -98,21 +111,51 @@ B200_HD void scale_min_k4(uint32_t w0, uint32_t w1, uint32_t w2, int j, int &sc,
     }
 }
 
-// Result of one item against one column: value to add to the row accumulator, plus (debug) the exact
-// integer pieces and which weight block they belong to.
+// debug sink: exact integer pieces per weight block of the current row (block-sum test hook)
 struct DbgSink {
-    int32_t *P, *M;     // per-block accumulators of the current row (atomic adds on device)
+    int32_t *P, *M;
 };
-
 #ifdef __CUDA_ARCH__
 #define B200_DBG_ADD(ptr, v) atomicAdd((int *)(ptr), (int)(v))
 #else
 #define B200_DBG_ADD(ptr, v) (*(ptr) += (v))
 #endif
 
+// ---- activation registers of one item ---------------------------------------------------------------
+template <int TYPE> struct ActRegs {        // 128-element items (Q6_K, Q4_0, Q8_0)
+    U4 a[8];          // 128 int8
+    U4 s;             // Q6_K: 8 bsums (int16) ; Q4_0: s.x,s.y = 4 block sums (int16) ; Q8_0: unused
+    U4 d;             // Q6_K: d.x = block scale (f32 bits) ; Q4_0/Q8_0: 4 block scales (f32 bits)
+};
+template <> struct ActRegs<T_Q4_K> { U4 a[4]; uint32_t s01, s23; float da; };
+template <> struct ActRegs<T_Q5_K> { U4 a[4]; uint32_t s01, s23; float da; };
+
+template <int TYPE> B200_HD void load_act(const ActView &A, int c, int it, ActRegs<TYPE> &r) {
+    const int8_t *ap = A.q + (size_t)c * A.q_stride + (size_t)it * act_item_stride<TYPE>();
+    if constexpr (TYPE == T_Q4_K || TYPE == T_Q5_K) {
+        r.a[0] = ld128(ap); r.a[1] = ld128(ap + 16); r.a[2] = ld128(ap + 32); r.a[3] = ld128(ap + 48);
+        const int16_t *sp = A.s + (size_t)c * A.s_stride + (size_t)it * 4;
+        r.s01 = ld32(sp); r.s23 = ld32(sp + 2);
+        r.da = A.d[(size_t)c * A.d_stride + (it >> 2)];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.a[i] = ld128(ap + 16 * i);
+        if constexpr (TYPE == T_Q6_K) {
+            r.s = ld128(A.s + (size_t)c * A.s_stride + (size_t)it * 8);
+            r.d.x = ld32(A.d + (size_t)c * A.d_stride + (it >> 1));
+        } else {
+            if constexpr (TYPE == T_Q4_0) {
+                const int16_t *sp = A.s + (size_t)c * A.s_stride + (size_t)it * 4;
+                r.s.x = ld32(sp); r.s.y = ld32(sp + 2);
+            }
+            r.d = ld128(A.d + (size_t)c * A.d_stride + (size_t)it * 4);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- Q4_K / Q5_K
-template <int TYPE, int NC, bool DBG>
-B200_HD void dot_item_q45k(const uint8_t *rowp, int it, const ActView &A, float *acc, DbgSink dbg) {
+template <int TYPE, bool DBG>
+B200_HD float item_dot_q45k(const uint8_t *rowp, int it, const ActRegs<TYPE> &r, DbgSink dbg) {
     constexpr int BYTES = Traits<TYPE>::BYTES;
     const uint8_t *b = rowp + (size_t)(it >> 2) * BYTES;
     const int g = it & 3;
@@ -136,36 +179,22 @@ B200_HD void dot_item_q45k(const uint8_t *rowp, int it, const ActView &A, float 
             hi[i] |= ((hw[i] >> (2 * g + 1)) & 0x01010101u) << 4;
         }
     }
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-        const int8_t *ap = A.q + (size_t)c * A.q_stride + (size_t)it * act_item_stride<TYPE>();
-        const U4 a0 = ld128(ap), a1 = ld128(ap + 16), a2 = ld128(ap + 32), a3 = ld128(ap + 48);
-        int sA = 0, sB = 0;
-        sA = dp4a_ss(lo[0], a0.x, sA); sA = dp4a_ss(lo[1], a0.y, sA); sA = dp4a_ss(lo[2], a0.z, sA); sA = dp4a_ss(lo[3], a0.w, sA);
-        sA = dp4a_ss(lo[4], a1.x, sA); sA = dp4a_ss(lo[5], a1.y, sA); sA = dp4a_ss(lo[6], a1.z, sA); sA = dp4a_ss(lo[7], a1.w, sA);
-        sB = dp4a_ss(hi[0], a2.x, sB); sB = dp4a_ss(hi[1], a2.y, sB); sB = dp4a_ss(hi[2], a2.z, sB); sB = dp4a_ss(hi[3], a2.w, sB);
-        sB = dp4a_ss(hi[4], a3.x, sB); sB = dp4a_ss(hi[5], a3.y, sB); sB = dp4a_ss(hi[6], a3.z, sB); sB = dp4a_ss(hi[7], a3.w, sB);
-        const int P = sc0 * sA + sc1 * sB;
-        const int16_t *sp = A.s + (size_t)c * A.s_stride + (size_t)it * 4;
-        const uint32_t s01 = ld32(sp), s23 = ld32(sp + 2);
-        const int M = m0 * ((int)(int16_t)(s01 & 0xffff) + (int)(int16_t)(s01 >> 16)) +
-                      m1 * ((int)(int16_t)(s23 & 0xffff) + (int)(int16_t)(s23 >> 16));
-        const float da = A.d[(size_t)c * A.d_stride + (it >> 2)];
-        acc[c] += (d * da) * (float)P - (dmin * da) * (float)M;
-        if (DBG && c == 0) { B200_DBG_ADD(dbg.P + (it >> 2), P); B200_DBG_ADD(dbg.M + (it >> 2), M); }
-    }
+    int sA = 0, sB = 0, sA2 = 0, sB2 = 0;     // two chains each for ILP; integer adds are exact in any order
+    sA  = dp4a_ss(lo[0], r.a[0].x, sA);  sA2 = dp4a_ss(lo[1], r.a[0].y, sA2); sA  = dp4a_ss(lo[2], r.a[0].z, sA);  sA2 = dp4a_ss(lo[3], r.a[0].w, sA2);
+    sA  = dp4a_ss(lo[4], r.a[1].x, sA);  sA2 = dp4a_ss(lo[5], r.a[1].y, sA2); sA  = dp4a_ss(lo[6], r.a[1].z, sA);  sA2 = dp4a_ss(lo[7], r.a[1].w, sA2);
+    sB  = dp4a_ss(hi[0], r.a[2].x, sB);  sB2 = dp4a_ss(hi[1], r.a[2].y, sB2); sB  = dp4a_ss(hi[2], r.a[2].z, sB);  sB2 = dp4a_ss(hi[3], r.a[2].w, sB2);
+    sB  = dp4a_ss(hi[4], r.a[3].x, sB);  sB2 = dp4a_ss(hi[5], r.a[3].y, sB2); sB  = dp4a_ss(hi[6], r.a[3].z, sB);  sB2 = dp4a_ss(hi[7], r.a[3].w, sB2);
+    const int P = sc0 * (sA + sA2) + sc1 * (sB + sB2);
+    const int M = m0 * ((int)(int16_t)(r.s01 & 0xffff) + (int)(int16_t)(r.s01 >> 16)) +
+                  m1 * ((int)(int16_t)(r.s23 & 0xffff) + (int)(int16_t)(r.s23 >> 16));
+    if (DBG) { B200_DBG_ADD(dbg.P + (it >> 2), P); B200_DBG_ADD(dbg.M + (it >> 2), M); }
+    return (d * r.da) * (float)P - (dmin * r.da) * (float)M;
 }
 
 // ---------------------------------------------------------------------------------------------- 2-byte aligned streams
-// word k (32 bits at byte offset 4k) of a stream that starts at the 2-byte aligned address p
-B200_HD uint32_t word_at(const uint8_t *p, int k) {
-    const uintptr_t a = (uintptr_t)p + 4 * (uintptr_t)k;
-    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
-    return (a & 2) ? align2_word(w[0], w[1], 2) : w[0];
-}
 B200_HD uint32_t half_at(const uint8_t *p) { return *(const uint16_t *)p; }
 
-// loads n words starting at the 2-byte aligned p with n+1 aligned 32-bit loads
+// loads N words starting at the 2-byte aligned p with N+1 aligned 32-bit loads
 template <int N> B200_HD void load_words(const uint8_t *p, uint32_t *out) {
     const uintptr_t a = (uintptr_t)p;
     const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
@@ -180,8 +209,8 @@ template <int N> B200_HD void load_words(const uint8_t *p, uint32_t *out) {
 }
 
 // ---------------------------------------------------------------------------------------------- Q6_K
-template <int NC, bool DBG>
-B200_HD void dot_item_q6k(const uint8_t *rowp, int it, const ActView &A, float *acc, DbgSink dbg) {
+template <bool DBG>
+B200_HD float item_dot_q6k(const uint8_t *rowp, int it, const ActRegs<T_Q6_K> &r, DbgSink dbg) {
     const uint8_t *b = rowp + (size_t)(it >> 1) * 210;
     const int h = it & 1;
     uint32_t L[16], H[8], S[2];
@@ -189,50 +218,46 @@ B200_HD void dot_item_q6k(const uint8_t *rowp, int it, const ActView &A, float *
     load_words<8>(b + 128 + 32 * h, H);
     load_words<2>(b + 192 + 8 * h, S);
     const float d = h2f_bits(half_at(b + 208));
-    // 6-bit quants (unsigned, 0..63) of the 8 scale groups: group sg = 2t + (i>>2), word i of quadrant t
-    uint32_t q[32];
+    const uint32_t bsw[4] = {r.s.x, r.s.y, r.s.z, r.s.w};
+    int P = 0;
+    // scale group sg = 2t + (i>>2) covers word i (0..7) of quadrant t; 6-bit quants kept unsigned (0..63), the
+    // -32 offset is applied through the activation bsums: sum (q-32)*a = sum q*a - 32*bsum
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        q[i]      = (L[i] & 0x0f0f0f0fu)            | ((H[i] << 4) & 0x30303030u);
-        q[8 + i]  = (L[8 + i] & 0x0f0f0f0fu)        | ((H[i] << 2) & 0x30303030u);
-        q[16 + i] = ((L[i] >> 4) & 0x0f0f0f0fu)     | (H[i] & 0x30303030u);
-        q[24 + i] = ((L[8 + i] >> 4) & 0x0f0f0f0fu) | ((H[i] >> 2) & 0x30303030u);
-    }
+    for (int sg = 0; sg < 8; sg++) {
+        const int t = sg >> 1;
+        const U4 a = r.a[sg];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        int s = 0;
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        const int8_t *ap = A.q + (size_t)c * A.q_stride + (size_t)it * act_item_stride<T_Q6_K>();
-        const int16_t *sp = A.s + (size_t)c * A.s_stride + (size_t)it * 8;
-        const U4 bs0 = ld128(sp);
-        const uint32_t bsw[4] = {bs0.x, bs0.y, bs0.z, bs0.w};
-        int P = 0;
-#pragma unroll
-        for (int sg = 0; sg < 8; sg++) {
-            const U4 a = ld128(ap + 16 * sg);
-            int s = 0;
-            s = dp4a_ss(q[4 * sg + 0], a.x, s); s = dp4a_ss(q[4 * sg + 1], a.y, s);
-            s = dp4a_ss(q[4 * sg + 2], a.z, s); s = dp4a_ss(q[4 * sg + 3], a.w, s);
-            const int bsum = (int)(int16_t)((sg & 1) ? (bsw[sg >> 1] >> 16) : (bsw[sg >> 1] & 0xffff));
-            const int scale = (int)(int8_t)((S[sg >> 2] >> (8 * (sg & 3))) & 0xff);
-            P += scale * (s - 32 * bsum);
+        for (int k = 0; k < 4; k++) {
+            const int i = (sg & 1) * 4 + k;
+            uint32_t q;
+            if (t == 0)      q = (L[i] & 0x0f0f0f0fu)            | ((H[i] << 4) & 0x30303030u);
+            else if (t == 1) q = (L[8 + i] & 0x0f0f0f0fu)        | ((H[i] << 2) & 0x30303030u);
+            else if (t == 2) q = ((L[i] >> 4) & 0x0f0f0f0fu)     | (H[i] & 0x30303030u);
+            else             q = ((L[8 + i] >> 4) & 0x0f0f0f0fu) | ((H[i] >> 2) & 0x30303030u);
+            s = dp4a_ss(q, aw[k], s);
         }
-        const float da = A.d[(size_t)c * A.d_stride + (it >> 1)];
-        acc[c] += (d * da) * (float)P;
-        if (DBG && c == 0) B200_DBG_ADD(dbg.P + (it >> 1), P);
+        const int bsum = (int)(int16_t)((sg & 1) ? (bsw[sg >> 1] >> 16) : (bsw[sg >> 1] & 0xffff));
+        const int scale = (int)(int8_t)((S[sg >> 2] >> (8 * (sg & 3))) & 0xff);
+        P += scale * (s - 32 * bsum);
     }
+    if (DBG) B200_DBG_ADD(dbg.P + (it >> 1), P);
+    return (d * u2f(r.d.x)) * (float)P;
 }
 
 // ---------------------------------------------------------------------------------------------- Q4_0 / Q8_0
 // item = up to 4 consecutive 32-element blocks; nvalid = number of blocks of this item inside K
-template <int NC, bool DBG>
-B200_HD void dot_item_q40(const uint8_t *rowp, int it, int nvalid, const ActView &A, float *acc, DbgSink dbg) {
+template <bool DBG>
+B200_HD float item_dot_q40(const uint8_t *rowp, int it, int nvalid, const ActRegs<T_Q4_0> &r, DbgSink dbg) {
     const uint8_t *p = rowp + (size_t)it * 72;
     uint32_t W[18];
     load_words<18>(p, W);    // stream of 72 bytes; block bi: half d at 18bi, qs at 18bi+2
+    const uint32_t dav[4] = {r.d.x, r.d.y, r.d.z, r.d.w};
+    float acc = 0.0f;
 #pragma unroll
     for (int bi = 0; bi < 4; bi++) {
         if (bi < nvalid) {
-            // bytes 18bi .. 18bi+17 ; word index (18bi)>>2, sub = (18bi)&2
-            constexpr int dummy = 0; (void)dummy;
             const int o = 18 * bi;
             const uint32_t dbits = (o & 2) ? (W[o >> 2] >> 16) : (W[o >> 2] & 0xffff);
             uint32_t qw[4];
@@ -241,31 +266,29 @@ B200_HD void dot_item_q40(const uint8_t *rowp, int it, int nvalid, const ActView
                 const int t = o + 2 + 4 * k;
                 qw[k] = (t & 2) ? align2_word(W[t >> 2], W[(t >> 2) + 1 < 18 ? (t >> 2) + 1 : 17], 2) : W[t >> 2];
             }
-            const float dw = h2f_bits(dbits);
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const int8_t *ap = A.q + (size_t)c * A.q_stride + (size_t)it * act_item_stride<T_Q4_0>() + 32 * bi;
-                const U4 a0 = ld128(ap), a1 = ld128(ap + 16);
-                int s = 0;
-                s = dp4a_ss(qw[0] & 0x0f0f0f0fu, a0.x, s); s = dp4a_ss(qw[1] & 0x0f0f0f0fu, a0.y, s);
-                s = dp4a_ss(qw[2] & 0x0f0f0f0fu, a0.z, s); s = dp4a_ss(qw[3] & 0x0f0f0f0fu, a0.w, s);
-                s = dp4a_ss((qw[0] >> 4) & 0x0f0f0f0fu, a1.x, s); s = dp4a_ss((qw[1] >> 4) & 0x0f0f0f0fu, a1.y, s);
-                s = dp4a_ss((qw[2] >> 4) & 0x0f0f0f0fu, a1.z, s); s = dp4a_ss((qw[3] >> 4) & 0x0f0f0f0fu, a1.w, s);
-                const int bsum = (int)A.s[(size_t)c * A.s_stride + (size_t)it * 4 + bi];
-                const int P = s - 8 * bsum;
-                const float da = A.d[(size_t)c * A.d_stride + (size_t)it * 4 + bi];
-                acc[c] += (dw * da) * (float)P;
-                if (DBG && c == 0) B200_DBG_ADD(dbg.P + it * 4 + bi, P);
-            }
+            const U4 a0 = r.a[2 * bi], a1 = r.a[2 * bi + 1];
+            int s = 0, s2 = 0;
+            s  = dp4a_ss(qw[0] & 0x0f0f0f0fu, a0.x, s);  s2 = dp4a_ss(qw[1] & 0x0f0f0f0fu, a0.y, s2);
+            s  = dp4a_ss(qw[2] & 0x0f0f0f0fu, a0.z, s);  s2 = dp4a_ss(qw[3] & 0x0f0f0f0fu, a0.w, s2);
+            s  = dp4a_ss((qw[0] >> 4) & 0x0f0f0f0fu, a1.x, s);  s2 = dp4a_ss((qw[1] >> 4) & 0x0f0f0f0fu, a1.y, s2);
+            s  = dp4a_ss((qw[2] >> 4) & 0x0f0f0f0fu, a1.z, s);  s2 = dp4a_ss((qw[3] >> 4) & 0x0f0f0f0fu, a1.w, s2);
+            const uint32_t sw = bi < 2 ? r.s.x : r.s.y;
+            const int bsum = (int)(int16_t)((bi & 1) ? (sw >> 16) : (sw & 0xffff));
+            const int P = s + s2 - 8 * bsum;
+            acc += (h2f_bits(dbits) * u2f(dav[bi])) * (float)P;
+            if (DBG) B200_DBG_ADD(dbg.P + it * 4 + bi, P);
         }
     }
+    return acc;
 }
 
-template <int NC, bool DBG>
-B200_HD void dot_item_q80(const uint8_t *rowp, int it, int nvalid, const ActView &A, float *acc, DbgSink dbg) {
+template <bool DBG>
+B200_HD float item_dot_q80(const uint8_t *rowp, int it, int nvalid, const ActRegs<T_Q8_0> &r, DbgSink dbg) {
     const uint8_t *p = rowp + (size_t)it * 136;
     uint32_t W[34];
     load_words<34>(p, W);    // block bi: half d at 34bi, int8 qs at 34bi+2
+    const uint32_t dav[4] = {r.d.x, r.d.y, r.d.z, r.d.w};
+    float acc = 0.0f;
 #pragma unroll
     for (int bi = 0; bi < 4; bi++) {
         if (bi < nvalid) {
@@ -277,34 +300,27 @@ B200_HD void dot_item_q80(const uint8_t *rowp, int it, int nvalid, const ActView
                 const int t = o + 2 + 4 * k;
                 qw[k] = (t & 2) ? align2_word(W[t >> 2], W[(t >> 2) + 1 < 34 ? (t >> 2) + 1 : 33], 2) : W[t >> 2];
             }
-            const float dw = h2f_bits(dbits);
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const int8_t *ap = A.q + (size_t)c * A.q_stride + (size_t)it * act_item_stride<T_Q8_0>() + 32 * bi;
-                const U4 a0 = ld128(ap), a1 = ld128(ap + 16);
-                int s = 0;
-                s = dp4a_ss(qw[0], a0.x, s); s = dp4a_ss(qw[1], a0.y, s); s = dp4a_ss(qw[2], a0.z, s); s = dp4a_ss(qw[3], a0.w, s);
-                s = dp4a_ss(qw[4], a1.x, s); s = dp4a_ss(qw[5], a1.y, s); s = dp4a_ss(qw[6], a1.z, s); s = dp4a_ss(qw[7], a1.w, s);
-                const float da = A.d[(size_t)c * A.d_stride + (size_t)it * 4 + bi];
-                acc[c] += (dw * da) * (float)s;
-                if (DBG && c == 0) B200_DBG_ADD(dbg.P + it * 4 + bi, s);
-            }
+            const U4 a0 = r.a[2 * bi], a1 = r.a[2 * bi + 1];
+            int s = 0, s2 = 0;
+            s  = dp4a_ss(qw[0], a0.x, s); s2 = dp4a_ss(qw[1], a0.y, s2); s  = dp4a_ss(qw[2], a0.z, s); s2 = dp4a_ss(qw[3], a0.w, s2);
+            s  = dp4a_ss(qw[4], a1.x, s); s2 = dp4a_ss(qw[5], a1.y, s2); s  = dp4a_ss(qw[6], a1.z, s); s2 = dp4a_ss(qw[7], a1.w, s2);
+            acc += (h2f_bits(dbits) * u2f(dav[bi])) * (float)(s + s2);
+            if (DBG) B200_DBG_ADD(dbg.P + it * 4 + bi, s + s2);
         }
     }
+    return acc;
 }
 
 // ---------------------------------------------------------------------------------------------- dispatch
-template <int TYPE> B200_HD int num_items(int K) { return (K + Traits<TYPE>::ITEM - 1) / Traits<TYPE>::ITEM; }
-
-template <int TYPE, int NC, bool DBG>
-B200_HD void dot_item(const uint8_t *rowp, int it, int K, const ActView &A, float *acc, DbgSink dbg) {
-    if (TYPE == T_Q4_K || TYPE == T_Q5_K) dot_item_q45k<TYPE, NC, DBG>(rowp, it, A, acc, dbg);
-    else if (TYPE == T_Q6_K) dot_item_q6k<NC, DBG>(rowp, it, A, acc, dbg);
+template <int TYPE, bool DBG>
+B200_HD float item_dot(const uint8_t *rowp, int it, int K, const ActRegs<TYPE> &r, DbgSink dbg) {
+    if constexpr (TYPE == T_Q4_K || TYPE == T_Q5_K) return item_dot_q45k<TYPE, DBG>(rowp, it, r, dbg);
+    else if constexpr (TYPE == T_Q6_K) return item_dot_q6k<DBG>(rowp, it, r, dbg);
     else {
         const int left = K / 32 - it * 4;
         const int nvalid = left < 4 ? left : 4;
-        if (TYPE == T_Q4_0) dot_item_q40<NC, DBG>(rowp, it, nvalid, A, acc, dbg);
-        else dot_item_q80<NC, DBG>(rowp, it, nvalid, A, acc, dbg);
+        if constexpr (TYPE == T_Q4_0) return item_dot_q40<DBG>(rowp, it, nvalid, r, dbg);
+        else return item_dot_q80<DBG>(rowp, it, nvalid, r, dbg);
     }
 }
 

@@ -13,6 +13,9 @@
 #include <cuda_bf16.h>
 
 int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);
+int launch_gemv_f32(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const float *x, size_t x_stride_bytes,
+                    int ncols, float *dst, size_t dst_col_stride, bool w_const, int fuse_mode, const float *x2, float eps,
+                    const float *residual);
 int launch_gemm_i8(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
                    int64_t ncols, float *dst, size_t dst_col_stride, bool *handled);
 
@@ -119,8 +122,21 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     const ActLayout L = ActLayout::make(q8k, K);
     const size_t rb = b200_row_bytes(w.type, K);
     const bool w_const = (w.flags & B200_TENSOR_FLAG_WEIGHT) != 0;
-    // quantise every src1 column of every batch once
     const int64_t nbatch = x.ne[2] * x.ne[3];
+    if (M <= 8) {
+        // decode path: one fused launch per (batch) matmul -- activation quantisation happens in the GEMV prologue
+        for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+                const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+                const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+                const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+                float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+                int rc = launch_gemv_f32(ctx, w.type, wp, rb, N, K, xp, x.nb[1], (int)M, dp, d.nb[1] / 4, w_const, 0, nullptr, 0.0f, nullptr);
+                if (rc) return rc;
+            }
+        return B200_OK;
+    }
+    // quantise every src1 column of every batch once
     uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)(M * nbatch));
     if (!act) return B200_ERR_ALLOC;
     for (int64_t i3 = 0; i3 < x.ne[3]; i3++)

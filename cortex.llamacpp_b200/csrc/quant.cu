@@ -9,6 +9,7 @@
 //       ggml-cpu-quants.c:808-860:  d = amax/127 -> fp16, id = 127/amax, q = RNE(x*id)
 // Output goes to the split "activation scratch" layout described in common.cuh (ActLayout).
 #include "common.cuh"
+#include "quant_warp.cuh"
 
 namespace {
 
@@ -28,39 +29,9 @@ __global__ void __launch_bounds__(128) quantize_q8k_kernel(const float *__restri
         const float4 a = *(const float4 *)xp, c = *(const float4 *)(xp + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
     }
-    float amax = 0.0f, mx = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const float a = fabsf(v[j]);
-        if (a > amax) { amax = a; mx = v[j]; }
-    }
-    int src = lane;   // first-occurrence tie break: equal |x| -> lower index wins (the reference scans in order)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int   os = __shfl_xor_sync(0xffffffffu, src, o);
-        if (oa > amax || (oa == amax && os < src)) { amax = oa; mx = om; src = os; }
-    }
-    int8_t q[8];
-    int lsum = 0;
-    float d = 0.0f;
-    if (amax != 0.0f) {
-        const float iscale = __fdiv_rn(-127.0f, mx);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int t = __float2int_rn(__fmul_rn(iscale, v[j]));
-            t = t > 127 ? 127 : t;
-            q[j] = (int8_t)t;
-            lsum += t;
-        }
-        d = __fdiv_rn(1.0f, iscale);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = 0;
-    }
-    *(uint2 *)(oc + b * 256 + lane * 8) = *(const uint2 *)q;
-    const int pair = lsum + __shfl_xor_sync(0xffffffffu, lsum, 1);
+    uint2 qp; float d; int pair;
+    warp_quant_q8k(v, lane, qp, d, pair);
+    *(uint2 *)(oc + b * 256 + lane * 8) = qp;
     if ((lane & 1) == 0) ((int16_t *)(oc + L.off_sums))[b * 16 + (lane >> 1)] = (int16_t)pair;
     if (lane == 0) ((float *)(oc + L.off_d))[b] = d;
 }
@@ -86,28 +57,13 @@ __global__ void __launch_bounds__(128) quantize_q80_kernel(const float *__restri
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = 0.0f;
     }
-    float amax = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 8; j++) amax = fmaxf(amax, fabsf(v[j]));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-    const float d  = __fdiv_rn(amax, 127.0f);
-    const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
-    int8_t q[8];
-    int lsum = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int t = __float2int_rn(__fmul_rn(v[j], id));
-        q[j] = (int8_t)t;
-        lsum += t;
-    }
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+    uint2 qp; float d16; int lsum;
+    warp_quant_q80(v, qp, d16, lsum);
     if (!valid) return;
-    *(uint2 *)(oc + e0) = *(const uint2 *)q;
+    *(uint2 *)(oc + e0) = qp;
     if ((lane & 3) == 0) {
         const int64_t bi = e0 / 32;
-        ((float *)(oc + L.off_d))[bi] = __half2float(__float2half_rn(d));
+        ((float *)(oc + L.off_d))[bi] = d16;
         ((int16_t *)(oc + L.off_sums))[bi] = (int16_t)lsum;
     }
 }

@@ -141,6 +141,9 @@ B200_API int         b200_quantize_act(b200_ctx *ctx, int32_t act_type, const fl
 B200_API int         b200_block_sums(b200_ctx *ctx, int32_t type, const void *W, const float *x, int64_t N, int64_t K,
                                      int32_t *P, int32_t *M);
 
+/* debug: device buffer of [sm_count][16] u64 receiving %globaltimer stamps from the GEMV kernel (NULL = off) */
+B200_API int         b200_debug_set_prof(b200_ctx *ctx, void *device_buf);
+
 #ifdef __cplusplus
 }
 #endif

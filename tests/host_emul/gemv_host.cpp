@@ -26,7 +26,10 @@ static void run(const uint8_t *W, size_t rb, int N, int K, const uint8_t *act, f
     std::vector<int8_t> aq((size_t)nitems * ASTR + 64, 0);
     for (int e = 0; e < K; e++) aq[(size_t)(e / ITEM) * ASTR + e % ITEM] = (int8_t)act[e];
     ActView A;
-    A.q = aq.data(); A.d = (const float *)(act + L.off_d); A.s = (const int16_t *)(act + L.off_sums);
+    const size_t nd = K / (Q8K ? 256 : 32), ns = K / (Q8K ? 16 : 32);
+    std::vector<float> ad(nd + 8, 0.0f); std::vector<int16_t> as(ns + 16, 0);
+    memcpy(ad.data(), act + L.off_d, nd * 4); memcpy(as.data(), act + L.off_sums, ns * 2);
+    A.q = aq.data(); A.d = ad.data(); A.s = as.data();
     A.q_stride = A.d_stride = A.s_stride = 0;
     const int nblk = K / Traits<TYPE>::BLOCK;
     // emulate a shared-memory stage: row copied to an address with the requested 2-byte phase
@@ -38,7 +41,11 @@ static void run(const uint8_t *W, size_t rb, int N, int K, const uint8_t *act, f
         memcpy(rowp, W + (size_t)n * rb, rb);
         float acc[1] = {0.0f};
         DbgSink dbg; dbg.P = P + (size_t)n * nblk; dbg.M = M + (size_t)n * nblk;
-        for (int it = 0; it < nitems; it++) dot_item<TYPE, 1, true>(rowp, it, K, A, acc, dbg);
+        for (int it = 0; it < nitems; it++) {
+            ActRegs<TYPE> ar;
+            load_act<TYPE>(A, 0, it, ar);
+            acc[0] += item_dot<TYPE, true>(rowp, it, K, ar, dbg);
+        }
         dst[n] = acc[0];
     }
 }

@@ -139,3 +139,15 @@ def test_float_weight_matmul(b200, ctx, wt):
     got = out.cpu().numpy().view(np.float32).reshape(M, N)
     want = R.orc_mul_mat(t, wb.view(np.uint8).reshape(-1), x, N, K)
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+def test_batched_columns_prequantised_path(b200, ctx, t):
+    """M > 8 goes through the stand-alone quantiser + the pre-quantised activation path"""
+    rng = np.random.default_rng(77 + t)
+    N, K, M = 96, 2048, 19
+    W = rand_quant_rows(t, N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    got = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    want = R.orc_mul_mat(t, W, x, N, K)
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
