@@ -335,7 +335,10 @@ int64_t op_batch_size(const ggml_tensor *op) {
         default: return ggml_nrows(op);
     }
 }
-bool dev_offload_op(ggml_backend_dev_t, const ggml_tensor *op) { return op_batch_size(op) >= 32; }   // as ggml-cuda.cu:3264-3285
+bool dev_offload_op(ggml_backend_dev_t, const ggml_tensor *op) {
+    static const bool off = getenv("GGML_B200_NO_OFFLOAD") != nullptr;   // keep -ngl 0 runs purely on the CPU backend (parity baselines)
+    return !off && op_batch_size(op) >= 32;
+}   // as ggml-cuda.cu:3264-3285
 
 ggml_backend_event_t dev_event_new(ggml_backend_dev_t dev) {
     b200_event *e = b200_event_create(((device_ctx *)dev->context)->device);

@@ -9,8 +9,9 @@
 //                  per-32 integer dots are EXACT (integers carried in f16 through the tensor core, |sum| < 2^24)
 //                  and scaled by d_k*d_q in f32 like ggml_vec_dot_q8_0_q8_0 / q4_0_q8_0
 //   * online softmax in f32, -inf mask cells contribute nothing, ALiBi slope and logit softcap as the CPU
-//   * V: f16 as is; q8_0/q4_0 dequantised on the fly (d*q); P.V accumulated in f32 (the CPU uses an f16
-//     accumulator for f16 V -- ours is strictly more accurate; the difference is bounded in the tests)
+//   * V: f16 as is; q8_0/q4_0 kept as exact integers with their scales folded into P (p*d_v in f32); the softmax
+//     weights are fed to the tensor core as an f16 hi+lo pair (22 significant bits), so P.V is f32-accurate like the
+//     CPU's f32 path for quantised V (the CPU's f16 accumulator for f16 V is LESS accurate than this; see tests)
 // Design: one CTA = one KV head x one tile of 16 query rows (GQA heads of the same KV head and/or several
 // query columns share every K/V byte) x one KV split.  The 4 warps of a CTA take alternating 32-position KV
 // tiles; K/V tiles are staged in shared memory (cp.async for f16, convert-on-load for quantised), fed to
@@ -111,10 +112,12 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
     extern __shared__ __align__(128) uint8_t fsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per-warp staging: K tile, V tile, K scales
-    constexpr int WARP_BYTES = 2 * BK * LD * 2 + BK * NB * 4;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * NB * 4;
     __half *sK = (__half *)(fsm + warp * WARP_BYTES);
     __half *sV = sK + BK * LD;
     float *sKs = (float *)(sV + BK * LD);
+    float *sVs = sKs + BK * NB;
+    constexpr bool VQ = VT != KV_F16;
 
     const int split = blockIdx.x;
     int tile = blockIdx.y;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
         }
         __syncwarp();
         stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane);
-        stage_tile<D, VT, false>(sV, nullptr, vbase, p.v_nb1, kv0, lane);
+        stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane);
         if (KT == KV_F16 || VT == KV_F16) cp_async_wait_all();
         __syncwarp();
 
@@ -281,20 +284,41 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
             }
 #pragma unroll
         for (int t = 0; t < NDT; t++) { o[t][0] *= corr[0]; o[t][1] *= corr[0]; o[t][2] *= corr[1]; o[t][3] *= corr[1]; }
-        // ---- O += P V --------------------------------------------------------------------------------------
+        // ---- O += P V : P as f16 hi+lo (22 bits); quantised V stays integer, its scale is folded into P per dim block ----
 #pragma unroll
         for (int kk = 0; kk < 2; kk++) {
-            uint32_t pa[4];
-            pa[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
-            pa[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
-            pa[2] = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            pa[3] = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+            const float pv[8] = {s[2 * kk][0], s[2 * kk][1], s[2 * kk][2], s[2 * kk][3], s[2 * kk + 1][0], s[2 * kk + 1][1], s[2 * kk + 1][2], s[2 * kk + 1][3]};
+            const int kvA = kk * 16 + (lane & 3) * 2;       // kv index (within the tile) of pv[0], pv[2]; +1 for pv[1], pv[3]; +8 for pv[4..7]
 #pragma unroll
-            for (int dt = 0; dt < NDT; dt += 2) {
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4_t(b0, b1, b2, b3, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + dt * 8 + (lane >> 4) * 8);
-                mma16816(o[dt], pa, b0, b1);
-                mma16816(o[dt + 1], pa, b2, b3);
+            for (int b = 0; b < (VQ ? NB : 1); b++) {
+                float w[8];
+                if (VQ) {
+                    const float dA0 = sVs[kvA * NB + b], dA1 = sVs[(kvA + 1) * NB + b], dB0 = sVs[(kvA + 8) * NB + b], dB1 = sVs[(kvA + 9) * NB + b];
+                    w[0] = pv[0] * dA0; w[1] = pv[1] * dA1; w[2] = pv[2] * dA0; w[3] = pv[3] * dA1;
+                    w[4] = pv[4] * dB0; w[5] = pv[5] * dB1; w[6] = pv[6] * dB0; w[7] = pv[7] * dB1;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) w[e] = pv[e];
+                }
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const __half2 hi = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+                    const float2 hf = __half22float2(hi);
+                    ph[e] = *(const uint32_t *)&hi;
+                    pl[e] = pack_h2(w[2 * e] - hf.x, w[2 * e + 1] - hf.y);
+                }
+                constexpr int DT0 = 0;
+                const int dt_begin = VQ ? b * 4 : DT0, dt_end = VQ ? b * 4 + 4 : NDT;
+#pragma unroll
+                for (int dt = dt_begin; dt < dt_end; dt += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(b0, b1, b2, b3, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + dt * 8 + (lane >> 4) * 8);
+                    mma16816(o[dt], ph, b0, b1);
+                    mma16816(o[dt], pl, b0, b1);
+                    mma16816(o[dt + 1], ph, b2, b3);
+                    mma16816(o[dt + 1], pl, b2, b3);
+                }
             }
         }
     }
@@ -381,7 +405,7 @@ int kv_kind(int type) { return type == B200_TYPE_F16 ? KV_F16 : type == B200_TYP
 template <int D, int KT, int VT>
 int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     constexpr int LD = D + 8;
-    constexpr int WARP_BYTES = 2 * BK * LD * 2 + BK * (D / 32) * 4;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4;
     constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D) * 4;
     constexpr int SMEM = NWARP * WARP_BYTES > COMBINE_BYTES ? NWARP * WARP_BYTES : COMBINE_BYTES;
     auto kern = fattn_kernel<D, KT, VT>;
