@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- Llama-3-8B Q4_K_M batch-1 decode on B200 through the ggml-b200 C ABI (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one decoded token: one pass of the whole hot path (32 layers of rms_norm -> Q4_K/Q6_K GEMV x7 -> rope ->
+KV store -> flash_attn_ext -> ..., then the 128256-row output GEMV) over a 512-token context.
+
+  value     tok/s with every input resident in HBM (CUDA events on the library's stream, CUDA-graph replay)
+  e2e       tok/s through the reference-facing call with HOST buffers: per step the pinned host->device copies of the
+            token embedding, position and KQ mask, b200_graph_compute, and the device->host read of the logits
+  e2e_llama (extra) the same workload through the UNMODIFIED llama.cpp runtime (llama_decode) with libggml-b200.so
+            loaded as its backend plugin -- what cortex.llamacpp's LlamaServerContext calls
+  roofline  the Q4_K decode GEMV (dominant kernel): algorithmic bytes / CUDA-event time over all Q4_K matmuls of a step
+  cpu_baseline / --impl reference: the reference's own ggml CPU backend (oracle/_ref, built from /root/reference) on the
+            same GGUF shapes, all host threads, bounded sample of decode steps.
+
+N > 1 (torchrun): every rank runs an independent replica of the model on its own GPU (slot data parallelism,
+SURVEY.md 8e: no collective on the data path); value = tokens of all ranks / max-over-ranks time.  scaling = weak.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+HARNESS = os.path.join(REF_DIR, "logits_dump")
+BACKEND_SO = os.path.join(ROOT, "cortex.llamacpp_b200", "libggml-b200.so")
+MODEL, FTYPE, KV, DEPTH = "llama3-8b", "q4_k_m", "f16", 512
+METRIC = "Llama-3-8B Q4_K_M decode tok/s (bs1)"
+WORKLOAD = "Llama-3-8B Q4_K_M (random-init GGUF blocks) bs1 decode, f16 KV, flash_attn, context depth %d" % DEPTH
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_harness(ngl, n_prompt, n_gen, warm, threads, gguf, timeout=900):
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "cortex.llamacpp_b200") + ":" + REF_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env["LOGITS_DUMP_WARMUP"] = str(warm)
+    if ngl > 0:
+        env["GGML_BACKEND_PATH"] = BACKEND_SO
+        env.setdefault("GGML_B200_GRAPHS", "1")
+    else:
+        env.pop("GGML_BACKEND_PATH", None)
+    out = subprocess.run([HARNESS, gguf, "-", str(ngl), str(n_prompt), str(n_gen), KV, "1", str(threads)], env=env,
+                         capture_output=True, text=True, timeout=timeout)
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("harness failed (rc %d): %s" % (out.returncode, out.stderr[-800:]))
+
+
+def ensure_gguf():
+    path = "/tmp/b200_bench_%s_%s.gguf" % (MODEL, FTYPE)
+    if not os.path.exists(path):
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_gguf.py"), "--model", MODEL, "--ftype", FTYPE, "--out", path + ".tmp"],
+                              stderr=subprocess.DEVNULL)
+        os.replace(path + ".tmp", path)
+    return path
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(a):
+    """the reference's own CPU backend (unmodified llama.cpp sources compiled by oracle/Makefile) on the host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    line = {"impl": "reference", "metric": METRIC, "unit": "tok/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 x int4..6 block dots (q8_K/q8_0 activations), f32 accumulate",
+            "data": "synthetic", "config": {"workload": WORKLOAD}}
+    if not os.path.exists(HARNESS):
+        line["unavailable"] = "oracle/_ref was not built (run __graft_entry__.build() where /root/reference exists)"
+        print(json.dumps(line))
+        return
+    threads = host_threads()
+    gguf = ensure_gguf()
+    steps = min(a.steps, 16)                 # bounded sample: <= 16 decode steps after a DEPTH-token prompt
+    r = run_harness(0, DEPTH, steps, min(a.warmup, 2), threads, gguf)
+    v = r["decode_tok_s"]
+    line.update({"value": v, "ms_per_step": 1000.0 / v, "steps": steps,
+                 "cpu_baseline": {"value": v, "unit": "tok/s", "cores": threads, "kind": "reference",
+                                  "sample": "%d decode steps after a %d-token prompt, llama_decode on the ggml CPU backend (AVX2 build)" % (steps, DEPTH)},
+                 "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (the reported line is then INVALID for the metric)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / e2e_llama legs (profiling runs)")
+    ap.add_argument("--graphs", type=int, default=1)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_llama_graph, load_package
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    b200 = load_package()
+    lg = load_llama_graph()
+    L = b200.lib()
+    ctx = b200.Context(local)
+    W = max(a.warmup, 3)
+    K = a.steps
+    n_ctx = 1024
+    g = lg.LlamaGraph(b200, model=MODEL, ftype=FTYPE, kv=KV, n_ctx=n_ctx, layers=a.layers, device=local, max_tokens=1)
+    g.fill_cache(DEPTH)
+    kv_head, n_kv = DEPTH, (DEPTH + 1 + 255) // 256 * 256
+    rng = np.random.default_rng(rank)
+    emb, pos, mask = g.set_inputs_host(1, kv_head, n_kv, rng)
+    # pinned host staging (what the scheduler's host buffer type provides) + device inputs
+    h_emb = torch.from_numpy(emb.reshape(-1)).pin_memory()
+    h_pos = torch.from_numpy(pos).pin_memory()
+    h_mask = torch.from_numpy(mask.reshape(-1)).pin_memory()
+    h_logits = torch.empty(g.V, dtype=torch.float32).pin_memory()
+    g.inp_embd[:g.E] = h_emb.cuda(local)
+    g.pos[:1] = h_pos.cuda(local)
+    g.mask_f32[:h_mask.numel()] = h_mask.cuda(local)
+    torch.cuda.synchronize()
+    ops = g.build(1, kv_head, n_kv)
+    ops_arr = (b200.Op * len(ops))(*ops)
+    ctx.set_option("cuda_graphs", a.graphs)
+
+    def step():
+        b200.check(L.b200_graph_compute(ctx.h, ops_arr, len(ops)), "graph_compute")
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    e0, e1 = L.b200_event_create(local), L.b200_event_create(local)
+
+    # ---------------------------------------------------------------- value: inputs resident in HBM
+    n_before = ctx.launches()
+    step(); ctx.sync()
+    launches_eager = ctx.launches() - n_before              # kernels of one step (graph replay launches the same nodes)
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.b200_event_record(ctx.h, e0)
+    for _ in range(K):
+        step()
+    L.b200_event_record(ctx.h, e1)
+    L.b200_event_synchronize(e1)
+    barrier()
+    ms = L.b200_event_elapsed_ms(e0, e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * K / (ms / 1e3)
+
+    # ---------------------------------------------------------------- e2e: host buffers, copies inside the timed region
+    def e2e_step():
+        b200.check(L.b200_memcpy_h2d_async(ctx.h, g.inp_embd.data_ptr(), h_emb.data_ptr(), g.E * 4), "h2d")
+        b200.check(L.b200_memcpy_h2d_async(ctx.h, g.pos.data_ptr(), h_pos.data_ptr(), 4), "h2d")
+        b200.check(L.b200_memcpy_h2d_async(ctx.h, g.mask_f32.data_ptr(), h_mask.data_ptr(), h_mask.numel() * 4), "h2d")
+        step()
+        b200.check(L.b200_memcpy_d2h_async(ctx.h, h_logits.data_ptr(), g.logits.data_ptr(), g.V * 4), "d2h")
+        ctx.sync()                                           # the sampler reads the logits on the host every step
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.summary()
+    e2e = {"value": world * K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": g.E * 4 + 4 + h_mask.numel() * 4, "d2h_bytes_per_step": g.V * 4,
+           "path": "b200_memcpy_h2d_async x3 -> b200_graph_compute -> b200_memcpy_d2h_async -> b200_synchronize (C ABI, pinned host buffers)"}
+    assert np.isfinite(h_logits.numpy()).all(), "non-finite logits"
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (Q4_K decode GEMV)
+    peak, peak_src = measured_peaks()
+    ctx.set_option("cuda_graphs", 0)
+    q4k = [o for o in ops if o.op == b200.OP_MUL_MAT and o.src[0].type == b200.Q4_K]
+    alg = sum(o.src[0].ne[1] * lg.row_size(b200.Q4_K, o.src[0].ne[0]) + 4 * o.src[0].ne[0] + 4 * o.src[0].ne[1] for o in q4k)
+    q4k_arr = (b200.Op * len(q4k))(*q4k)
+    ctx.set_option("fusion", 0)
+    for _ in range(3):
+        b200.check(L.b200_graph_compute(ctx.h, q4k_arr, len(q4k)), "q4k")
+    ctx.sync()
+    reps = 5
+    L.b200_event_record(ctx.h, e0)
+    for _ in range(reps):
+        b200.check(L.b200_graph_compute(ctx.h, q4k_arr, len(q4k)), "q4k")
+    L.b200_event_record(ctx.h, e1)
+    L.b200_event_synchronize(e1)
+    k_ms = L.b200_event_elapsed_ms(e0, e1) / reps
+    ctx.set_option("fusion", 1)
+    achieved = alg / (k_ms / 1e3) / 1e9
+    sb = g.step_bytes(1, n_kv)
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_K> (decode GEMV, %d launches/step, eager back-to-back)" % len(q4k),
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch_avg": alg / len(q4k), "avg_launch_us": 1e3 * k_ms / len(q4k),
+                "whole_step": {"algorithmic_bytes": sb["total"], "achieved_gbs": sb["total"] * (K / (ms / 1e3)) / 1e9,
+                               "frac": sb["total"] * (K / (ms / 1e3)) / 1e9 / peak, "breakdown": sb}}
+
+    line = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 x int4..6 block dots (q8_K/q8_0 activations), f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2: %.2f GB of weights streamed per step vs 126 MB L2" % (g.weight_bytes / 1e9),
+                       "n_kv": n_kv, "cuda_graphs": a.graphs, "replicas": world,
+                       "layers": g.L if a.layers else "all (%d)" % g.L},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_eager) * K, "roofline": roofline}
+    if a.layers:
+        line["INVALID"] = "--layers override: not the named model"
+
+    # ---------------------------------------------------------------- CPU baseline + llama.cpp-level e2e (rank 0, N=1)
+    if rank == 0 and world == 1 and not a.no_cpu and not a.layers and os.path.exists(HARNESS):
+        try:
+            gguf = ensure_gguf()
+            threads = host_threads()
+            if os.path.exists(BACKEND_SO):
+                r = run_harness(99, DEPTH, K, W, 4, gguf)
+                line["e2e_llama"] = {"value": r["decode_tok_s"], "unit": "tok/s", "prefill_tok_s": r["prefill_tok_s"],
+                                     "path": "llama_decode (unmodified llama.cpp runtime) -> ggml_backend_sched -> libggml-b200.so graph_compute; logits read on host every step"}
+            r = run_harness(0, DEPTH, 8, 1, threads, gguf)
+            line["cpu_baseline"] = {"value": r["decode_tok_s"], "unit": "tok/s", "cores": threads, "kind": "reference",
+                                    "sample": "8 decode steps after a %d-token prompt, llama_decode on the reference ggml CPU backend" % DEPTH}
+        except Exception as ex:           # the baseline is a report, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": host_threads(), "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

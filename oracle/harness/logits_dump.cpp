@@ -3,6 +3,8 @@
 // logit row, so the CPU backend and the B200 backend can be compared on identical inputs (teacher forcing).
 //   logits_dump MODEL OUT.bin NGL N_PROMPT N_GEN [kv_type f16|q8_0|q4_0] [n_parallel] [threads]
 // Output: int32 n_rows, int32 n_vocab, then n_rows*n_vocab f32.  Also prints per-phase timings.
+// OUT.bin == "-" is bench mode (bench.py e2e / --impl reference legs): nothing is stored, the prompt only asks for the
+// logits of its last token, and env LOGITS_DUMP_WARMUP=W runs W untimed decode steps before the n_gen timed ones.
 #include "llama.h"
 #include "ggml.h"
 #include "ggml-backend.h"
@@ -38,6 +40,8 @@ int main(int argc, char **argv) {
     const char *kv = argc > 6 ? argv[6] : "f16";
     const int n_par = argc > 7 ? atoi(argv[7]) : 1;
     const int threads = argc > 8 ? atoi(argv[8]) : 8;
+    const bool bench = !strcmp(out_path, "-");
+    const int n_warm = bench && getenv("LOGITS_DUMP_WARMUP") ? atoi(getenv("LOGITS_DUMP_WARMUP")) : 0;
     ggml_backend_load_all();
     llama_backend_init();
     llama_model_params mp = llama_model_default_params();
@@ -45,7 +49,7 @@ int main(int argc, char **argv) {
     llama_model *model = llama_model_load_from_file(model_path, mp);
     if (!model) return 1;
     llama_context_params cp = llama_context_default_params();
-    cp.n_ctx = (n_prompt + n_gen + 8) * n_par;
+    cp.n_ctx = (n_prompt + n_warm + n_gen + 8) * n_par;
     cp.n_batch = 2048; cp.n_ubatch = 2048;                 // cortex defaults (C/src/llama_engine.cc:617-618)
     cp.n_seq_max = n_par;
     cp.flash_attn = true;
@@ -66,28 +70,36 @@ int main(int argc, char **argv) {
     for (int p = 0; p < n_par; p++)
         for (int i = 0; i < n_prompt; i++) {
             const int j = batch.n_tokens++;
-            batch.token[j] = next(); batch.pos[j] = i; batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = 1;
+            batch.token[j] = next(); batch.pos[j] = i; batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = !bench || i == n_prompt - 1;
         }
     double t0 = now_ms();
     if (llama_decode(ctx, batch) != 0) { fprintf(stderr, "prefill decode failed\n"); return 1; }
     llama_synchronize(ctx);
     const double t_prefill = now_ms() - t0;
-    for (int j = 0; j < batch.n_tokens; j++) { const float *l = llama_get_logits_ith(ctx, j); all.insert(all.end(), l, l + V); rows++; }
+    if (!bench) for (int j = 0; j < batch.n_tokens; j++) { const float *l = llama_get_logits_ith(ctx, j); all.insert(all.end(), l, l + V); rows++; }
     // ---- decode: one token per slot per step, teacher forced ----
     t0 = now_ms();
-    for (int g = 0; g < n_gen; g++) {
+    float sink = 0.0f;
+    for (int g = -n_warm; g < n_gen; g++) {
+        if (g == 0) { llama_synchronize(ctx); t0 = now_ms(); }
         batch.n_tokens = 0;
         for (int p = 0; p < n_par; p++) {
             const int j = batch.n_tokens++;
-            batch.token[j] = next(); batch.pos[j] = n_prompt + g; batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = 1;
+            batch.token[j] = next(); batch.pos[j] = n_prompt + n_warm + g; batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = 1;
         }
         if (llama_decode(ctx, batch) != 0) { fprintf(stderr, "decode failed at %d\n", g); return 1; }
-        for (int j = 0; j < batch.n_tokens; j++) { const float *l = llama_get_logits_ith(ctx, j); all.insert(all.end(), l, l + V); rows++; }
+        // reading the logits is what the sampler does every step: it forces the device->host copy + synchronize
+        for (int j = 0; j < batch.n_tokens; j++) {
+            const float *l = llama_get_logits_ith(ctx, j);
+            if (bench) sink += l[0] + l[V - 1]; else { all.insert(all.end(), l, l + V); rows++; }
+        }
     }
     llama_synchronize(ctx);
     const double t_decode = now_ms() - t0;
-    FILE *f = fopen(out_path, "wb");
-    fwrite(&rows, 4, 1, f); fwrite(&V, 4, 1, f); fwrite(all.data(), 4, all.size(), f); fclose(f);
+    if (!bench) {
+        FILE *f = fopen(out_path, "wb");
+        fwrite(&rows, 4, 1, f); fwrite(&V, 4, 1, f); fwrite(all.data(), 4, all.size(), f); fclose(f);
+    } else if (sink != sink) fprintf(stderr, "nan in logits\n");
     printf("{\"ngl\": %d, \"n_parallel\": %d, \"n_prompt\": %d, \"n_gen\": %d, \"kv\": \"%s\", \"prefill_ms\": %.3f, \"prefill_tok_s\": %.1f, \"decode_ms\": %.3f, \"decode_tok_s\": %.1f}\n",
            ngl, n_par, n_prompt, n_gen, kv, t_prefill, 1000.0 * n_prompt * n_par / t_prefill, t_decode, n_gen > 0 ? 1000.0 * n_gen * n_par / t_decode : 0.0);
     llama_batch_free(batch); llama_free(ctx); llama_model_free(model);
