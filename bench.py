@@ -146,6 +146,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (the reported line is then INVALID for the metric)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / e2e_llama legs (profiling runs)")
     ap.add_argument("--graphs", type=int, default=1)
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("GGML_B200_PDL", "1")))
+    ap.add_argument("--fusion", type=int, default=2)
+    ap.add_argument("--l2pf", type=int, default=1)
     a = ap.parse_args()
     if a.impl == "reference":
         return reference_arm(a)
@@ -182,6 +185,9 @@ def main():
     ops = g.build(1, kv_head, n_kv)
     ops_arr = (b200.Op * len(ops))(*ops)
     ctx.set_option("cuda_graphs", a.graphs)
+    ctx.set_option("pdl", a.pdl)
+    ctx.set_option("fusion", a.fusion)
+    ctx.set_option("l2_prefetch", a.l2pf)
 
     def step():
         b200.check(L.b200_graph_compute(ctx.h, ops_arr, len(ops)), "graph_compute")
@@ -258,10 +264,10 @@ def main():
     L.b200_event_record(ctx.h, e1)
     L.b200_event_synchronize(e1)
     k_ms = L.b200_event_elapsed_ms(e0, e1) / reps
-    ctx.set_option("fusion", 1)
+    ctx.set_option("fusion", a.fusion)
     achieved = alg / (k_ms / 1e3) / 1e9
     sb = g.step_bytes(1, n_kv)
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_K> (decode GEMV, %d launches/step, eager back-to-back)" % len(q4k),
+    roofline = {"bound": "hbm", "kernel": "b200_gemv_kernel<Q4_K> (decode GEMV, %d launches/step, eager back-to-back)" % len(q4k),
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch_avg": alg / len(q4k), "avg_launch_us": 1e3 * k_ms / len(q4k),
                 "whole_step": {"algorithmic_bytes": sb["total"], "achieved_gbs": sb["total"] * (K / (ms / 1e3)) / 1e9,
@@ -271,7 +277,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 x int4..6 block dots (q8_K/q8_0 activations), f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2: %.2f GB of weights streamed per step vs 126 MB L2" % (g.weight_bytes / 1e9),
-                       "n_kv": n_kv, "cuda_graphs": a.graphs, "replicas": world,
+                       "n_kv": n_kv, "cuda_graphs": a.graphs, "pdl": a.pdl, "fusion": a.fusion, "l2_prefetch": a.l2pf, "replicas": world,
                        "layers": g.L if a.layers else "all (%d)" % g.L},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_eager) * K, "roofline": roofline}
     if a.layers:

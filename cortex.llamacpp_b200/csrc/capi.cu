@@ -95,7 +95,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     graph_cache_free(ctx);
-    for (int i = 0; i < 4; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < SCRATCH_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -115,6 +115,7 @@ int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
     else if (k == "fusion") ctx->opt_fusion = value;
     else if (k == "pdl") ctx->opt_pdl = value;
+    else if (k == "l2_prefetch") ctx->opt_l2_prefetch = value;
     else { b200_set_error("unknown option %s", key); return B200_ERR_UNSUPPORTED; }
     return B200_OK;
 }

@@ -119,13 +119,14 @@ struct b200_ctx {
     int           sm_count = 148;
     size_t        smem_optin = 227 * 1024;
     // growable device scratch (activation quantisation, split-KV partials, MoE routing tables)
-    void *        scratch[4]      = {nullptr, nullptr, nullptr, nullptr};
-    size_t        scratch_size[4] = {0, 0, 0, 0};
+    void *        scratch[5]      = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t        scratch_size[5] = {0, 0, 0, 0, 0};
     int64_t       launches = 0;
     // options
     int           opt_cuda_graphs = 0;
-    int           opt_fusion      = 1;
+    int           opt_fusion      = 2;      // 0 off, 1 two-op fusions, 2 + llama layer fusions for decode ubatches
     int           opt_pdl         = 0;
+    int           opt_l2_prefetch = 1;
     GraphCache *  graph_cache = nullptr;
     bool          capturing = false;
     void *        prof_buf = nullptr;   // debug: per-CTA timestamps (b200_debug_set_prof)
@@ -133,7 +134,7 @@ struct b200_ctx {
     void *get_scratch(int slot, size_t size);   // grows (sync + realloc) when too small; nullptr on OOM
 };
 
-enum { SCRATCH_ACT = 0, SCRATCH_FATTN = 1, SCRATCH_MOE = 2, SCRATCH_MISC = 3 };
+enum { SCRATCH_ACT = 0, SCRATCH_FATTN = 1, SCRATCH_MOE = 2, SCRATCH_MISC = 3, SCRATCH_FUSE = 4, SCRATCH_COUNT = 5 };
 
 // op entry points (each in its own .cu); all asynchronous on ctx->stream
 int op_mul_mat(b200_ctx *ctx, const b200_op *op);
@@ -144,6 +145,20 @@ bool supports_mul_mat(const b200_op *op);
 bool supports_mul_mat_id(const b200_op *op);
 bool supports_flash_attn_ext(const b200_op *op);
 bool supports_glue(const b200_op *op);
+
+// fused ROPE(q) + ROPE(k) + KV-store of k and v for a decode ubatch (glue.cu); q/k/v are contiguous [D, heads, T] f32
+struct RopeStoreDesc {
+    const float *q, *k, *v;
+    const int32_t *pos;
+    const float *freq_factors;          // optional [D/2]
+    float *q_out; uint64_t q_out_nb1, q_out_nb2;     // roped q, byte strides of head and token
+    void *k_dst, *v_dst;                // cache rows of token 0 of this ubatch (layout [T][Hkv][D] in the cache type)
+    void *const *k_dst_ind, *const *v_dst_ind;       // when non-NULL the destinations are read from device memory (CUDA-graph replay)
+    int D, H, Hkv, T, kv_type;
+    int32_t rope_params[16];
+    int use_pdl;
+};
+int launch_rope_store(b200_ctx *ctx, const RopeStoreDesc &d);
 
 // quantise f32 activations [K, ncols] (column byte stride nb1) into the scratch layout above
 int launch_quantize_act(b200_ctx *ctx, int q8k, const float *x, size_t x_col_stride_bytes, int64_t K, int64_t ncols,

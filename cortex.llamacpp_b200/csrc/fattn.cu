@@ -25,6 +25,7 @@ namespace {
 enum { KV_F16 = 0, KV_Q8_0 = 1, KV_Q4_0 = 2 };
 constexpr int BK = 32;          // kv positions per warp tile
 constexpr int NWARP = 4;
+constexpr float PV_SCALE = 256.0f, PV_UNSCALE = 1.0f / 256.0f;
 
 struct FaParams {
     const char *q; uint64_t q_nb1, q_nb2, q_nb3;
@@ -36,6 +37,7 @@ struct FaParams {
     int n_q, n_kv, H, Hkv, gq, HG, QC, n_headtiles, n_coltiles, n_splits, kv_per_split;
     float scale, softcap, max_bias, m0, m1;
     int n_head_log2;
+    int use_pdl;
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const void *p) {
@@ -103,7 +105,7 @@ __device__ __forceinline__ void stage_tile(__half *s, float *sc, const char *g, 
 }
 
 template <int D, int KT, int VT>
-__global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) {
+__global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParams p) {
     constexpr int LD = D + 8;
     constexpr int NKS = D / 16;                  // k-steps of the QK product
     constexpr int NDT = D / 8;                   // n-tiles of the PV product
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
     constexpr bool KQ = KT != KV_F16;
     extern __shared__ __align__(128) uint8_t fsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
     // per-warp staging: K tile, V tile, K scales
     constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * NB * 4;
     __half *sK = (__half *)(fsm + warp * WARP_BYTES);
@@ -300,6 +303,10 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
 #pragma unroll
                     for (int e = 0; e < 8; e++) w[e] = pv[e];
                 }
+                // exact power-of-two pre-scale: keeps the f16 hi/lo pair out of the f16 subnormal range for small
+                // softmax weights (w ~ 1e-4 would otherwise lose its low half); undone when the accumulators are stored
+#pragma unroll
+                for (int e = 0; e < 8; e++) w[e] *= PV_SCALE;
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
 #pragma unroll
         for (int t = 0; t < NDT; t++) {
             const int d = t * 8 + (lane & 3) * 2;
-            *(float2 *)(co + (warp * 16 + r) * D + d) = make_float2(o[t][2 * i], o[t][2 * i + 1]);
+            *(float2 *)(co + (warp * 16 + r) * D + d) = make_float2(o[t][2 * i] * PV_UNSCALE, o[t][2 * i + 1] * PV_UNSCALE);
         }
     }
     __syncthreads();
@@ -372,32 +379,47 @@ __global__ void __launch_bounds__(NWARP * 32, 2) fattn_kernel(const FaParams p) 
     }
 }
 
+// merge of the KV splits: one WARP per (tile, query row); lanes first reduce the per-split (max, sum) pairs, then each lane
+// owns D/32 output dims and walks the splits with independent loads (log-sum-exp merge, fixed split order => deterministic)
 template <int D>
-__global__ void __launch_bounds__(128) fattn_combine_kernel(const FaParams p) {
-    int tile = blockIdx.x;
-    const int tile_id = tile;
+__global__ void __launch_bounds__(128) b200_fattn_combine_kernel(const FaParams p, int n_tiles) {
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int tile_id = wid >> 4, r = wid & 15;
+    if (tile_id >= n_tiles) return;
+    int tile = tile_id;
     const int ct = tile % p.n_coltiles; tile /= p.n_coltiles;
     const int ht = tile % p.n_headtiles;
     const int hk = tile / p.n_headtiles;
-    const int c0 = ct * p.QC;
-    for (int e = threadIdx.x; e < 16 * D; e += blockDim.x) {
-        const int r = e / D, d = e % D;
-        const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
-        const bool valid = (r / p.HG) < p.QC && col < p.n_q && hin < p.gq;
-        if (!valid) continue;
-        const float *base = p.part + ((uint64_t)tile_id * p.n_splits * 16 + r) * (D + 2);
-        float M = -INFINITY;
-        for (int s = 0; s < p.n_splits; s++) M = fmaxf(M, base[(uint64_t)s * 16 * (D + 2) + D]);
-        float val = 0.0f, L = 0.0f;
-        for (int s = 0; s < p.n_splits; s++) {
-            const float *pp = base + (uint64_t)s * 16 * (D + 2);
-            const float ms = pp[D];
-            const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
-            val += pp[d] * f;
-            L += pp[D + 1] * f;
-        }
-        p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = val / L;
+    const int hin = ht * p.HG + r % p.HG, col = ct * p.QC + r / p.HG;
+    if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) return;
+    const float *base = p.part + ((uint64_t)tile_id * p.n_splits * 16 + r) * (D + 2);
+    const uint64_t sstride = (uint64_t)16 * (D + 2);
+    float M = -INFINITY;
+    for (int s = lane; s < p.n_splits; s += 32) M = fmaxf(M, base[s * sstride + D]);
+    M = warp_reduce_max(M);
+    float L = 0.0f;
+    for (int s = lane; s < p.n_splits; s += 32) {
+        const float ms = base[s * sstride + D];
+        L += ms == -INFINITY ? 0.0f : base[s * sstride + D + 1] * expf(ms - M);
     }
+    // fixed-order sum over lanes (xor tree is order-independent of scheduling)
+    L = warp_reduce_sum(L);
+    constexpr int PER = D / 32;
+    float acc[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) acc[j] = 0.0f;
+    for (int s = 0; s < p.n_splits; s++) {
+        const float *pp = base + s * sstride;
+        const float ms = pp[D];
+        const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+#pragma unroll
+        for (int j = 0; j < PER; j++) acc[j] += pp[lane + 32 * j] * f;
+    }
+    float *o = p.dst + ((uint64_t)col * p.H + hk * p.gq + hin) * D;
+#pragma unroll
+    for (int j = 0; j < PER; j++) o[lane + 32 * j] = acc[j] / L;
 }
 
 int kv_kind(int type) { return type == B200_TYPE_F16 ? KV_F16 : type == B200_TYPE_Q8_0 ? KV_Q8_0 : type == B200_TYPE_Q4_0 ? KV_Q4_0 : -1; }
@@ -408,19 +430,30 @@ int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4;
     constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D) * 4;
     constexpr int SMEM = NWARP * WARP_BYTES > COMBINE_BYTES ? NWARP * WARP_BYTES : COMBINE_BYTES;
-    auto kern = fattn_kernel<D, KT, VT>;
+    auto kern = b200_fattn_kernel<D, KT, VT>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set[ctx->device & 15] = true;
     }
-    kern<<<dim3((unsigned)p.n_splits, (unsigned)n_tiles), NWARP * 32, SMEM, ctx->stream>>>(p);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.n_splits, (unsigned)n_tiles);
+    cfg.blockDim = dim3(NWARP * 32);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = ctx->stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.use_pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ctx->launches++;
-    CUDA_TRY(cudaGetLastError());
     if (p.n_splits > 1) {
-        fattn_combine_kernel<D><<<(unsigned)n_tiles, 128, 0, ctx->stream>>>(p);
+        cfg.gridDim = dim3((unsigned)((n_tiles * 16 + 3) / 4));
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_combine_kernel<D>, p, n_tiles));
         ctx->launches++;
-        CUDA_TRY(cudaGetLastError());
     }
     return B200_OK;
 }
@@ -487,6 +520,7 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     memcpy(&p.softcap, &op->params[2], 4);
     if (p.softcap != 0.0f) p.scale /= p.softcap;
     p.n_head_log2 = 1 << (int)floorf(log2f((float)p.H));
+    p.use_pdl = ctx->opt_pdl;
     p.m0 = powf(2.0f, -(p.max_bias) / p.n_head_log2);
     p.m1 = powf(2.0f, -(p.max_bias / 2.0f) / p.n_head_log2);
     const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;

@@ -1,0 +1,33 @@
+// gemv.h -- host-side interface of the decode GEMV (gemv.cu), shared with mulmat.cu and graph.cu
+#pragma once
+#include "common.cuh"
+
+constexpr int GEMV_MAX_SEG = 3;
+enum { ACT_PREQ = 0, ACT_F32 = 1, ACT_F32_NORM = 2, ACT_F32_SWIGLU = 3 };
+
+// one weight matrix of a launch ("segment"): dst[:, col] = W . act[:, col] (+ residual)
+struct GemvSegDesc {
+    int            type;
+    const uint8_t *W;
+    size_t         rb;               // bytes per row
+    int64_t        N;                // rows
+    float *        dst;
+    size_t         dst_stride;       // elements between columns
+    const float *  residual;         // optional, laid out like dst
+    const int32_t *expert_id;        // MUL_MAT_ID: device pointer to the expert index
+    size_t         expert_stride;    // bytes between expert matrices
+    int32_t *      dbgP, *dbgM;      // block-sum test hook
+};
+// where the activations come from
+struct GemvActDesc {
+    int            mode;             // ACT_*
+    const uint8_t *act;              // ACT_PREQ: pre-quantised scratch (ActLayout)
+    const float *  x;                // f32 source, column stride x_stride bytes
+    size_t         x_stride;
+    const float *  x2;               // ACT_F32_NORM: norm weight [K]; ACT_F32_SWIGLU: `up` (strided like x)
+    float          eps;
+};
+
+int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, int ncols, bool w_const,
+                const void *pf_ptr, size_t pf_bytes);
+int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);

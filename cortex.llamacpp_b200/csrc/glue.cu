@@ -44,7 +44,7 @@ __device__ __forceinline__ float block_reduce_max_f(float v, float *sh) {
 // ---------------------------------------------------------------------------------------------- rms_norm (+mul)
 // ggml_compute_forward_rms_norm_f32: sum(x*x) in double, mean=(float)(sum/n), scale=1/sqrtf(mean+eps), y=x*scale
 template <bool MUL>
-__global__ void __launch_bounds__(256) rms_norm_kernel(b200_tensor x, b200_tensor w, b200_tensor y, float eps) {
+__global__ void __launch_bounds__(256) b200_rms_norm_kernel(b200_tensor x, b200_tensor w, b200_tensor y, float eps) {
     __shared__ double sh[8];
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % x.ne[1], i2 = (row / x.ne[1]) % x.ne[2], i3 = row / (x.ne[1] * x.ne[2]);
@@ -71,7 +71,7 @@ template <int OP> __device__ __forceinline__ float bin(float a, float b) {
     return OP == BIN_ADD ? __fadd_rn(a, b) : OP == BIN_SUB ? __fsub_rn(a, b) : OP == BIN_MUL ? __fmul_rn(a, b) : __fdiv_rn(a, b);
 }
 template <int OP>
-__global__ void __launch_bounds__(256) bin_bcast_kernel(b200_tensor a, b200_tensor b, b200_tensor d, int64_t total) {
+__global__ void __launch_bounds__(256) b200_bin_bcast_kernel(b200_tensor a, b200_tensor b, b200_tensor d, int64_t total) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const Idx4 i = unravel(e, d.ne);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) bin_bcast_kernel(b200_tensor a, b200_tens
 }
 // fast path: everything contiguous, b is either the same shape or one row broadcast over all rows; n % 4 == 0
 template <int OP>
-__global__ void __launch_bounds__(256) bin_fast_kernel(const float4 *a, const float4 *b, float4 *d, int64_t n4, int64_t brow4) {
+__global__ void __launch_bounds__(256) b200_bin_fast_kernel(const float4 *a, const float4 *b, float4 *d, int64_t n4, int64_t brow4) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n4) return;
     const float4 av = a[e], bv = b[brow4 ? e % brow4 : e];
@@ -104,7 +104,7 @@ template <int OP> __device__ __forceinline__ float unary(float x, float p) {
     }
 }
 template <int OP>
-__global__ void __launch_bounds__(256) unary_kernel(const float *x, const float *u, float *y, int64_t n, float p) {
+__global__ void __launch_bounds__(256) b200_unary_kernel(const float *x, const float *u, float *y, int64_t n, float p) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (OP == UN_SWIGLU) y[e] = __fmul_rn(unary<UN_SILU>(x[e], 0.0f), u[e]);
@@ -120,7 +120,7 @@ struct RopeParams {
     float theta_scale, corr0, corr1;
 };
 template <typename T>
-__global__ void __launch_bounds__(128) rope_kernel(b200_tensor x, b200_tensor pos, b200_tensor ff, b200_tensor y, RopeParams rp, int has_ff) {
+__global__ void __launch_bounds__(128) b200_rope_kernel(b200_tensor x, b200_tensor pos, b200_tensor ff, b200_tensor y, RopeParams rp, int has_ff) {
     // grid: (ne2 tokens, ne1 heads, ne3); threads over pairs
     const int64_t i2 = blockIdx.x, i1 = blockIdx.y, i3 = blockIdx.z;
     const char *xp = (const char *)x.data + i1 * x.nb[1] + i2 * x.nb[2] + i3 * x.nb[3];
@@ -166,7 +166,7 @@ template <> __device__ __forceinline__ int32_t cvt<int32_t, int32_t>(int32_t v) 
 
 // flat-index copy: element e of src (src's logical order) -> element e of dst (dst's logical order)
 template <typename TS, typename TD>
-__global__ void __launch_bounds__(256) cpy_kernel(b200_tensor s, b200_tensor d, int64_t total) {
+__global__ void __launch_bounds__(256) b200_cpy_kernel(b200_tensor s, b200_tensor d, int64_t total) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const Idx4 a = unravel(e, s.ne), b = unravel(e, d.ne);
@@ -187,7 +187,7 @@ __device__ __forceinline__ const char *blk_ptr(const b200_tensor &t, int64_t blk
 
 // f32 -> q8_0 / q4_0, one thread per 32-element block (quantize_row_q8_0 AVX2 semantics / quantize_row_q4_0_ref)
 template <int DT>
-__global__ void __launch_bounds__(128) cpy_f32_q_kernel(b200_tensor s, b200_tensor d, int64_t nblocks) {
+__global__ void __launch_bounds__(128) b200_cpy_f32_q_kernel(b200_tensor s, b200_tensor d, int64_t nblocks) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const float *xp = (const float *)blk_ptr(s, b, 32);
@@ -266,7 +266,7 @@ __device__ float dequant_elem(int type, const uint8_t *row, int64_t e) {
     return 0.0f;
 }
 
-__global__ void __launch_bounds__(256) cpy_q_f32_kernel(b200_tensor s, b200_tensor d, int64_t total) {
+__global__ void __launch_bounds__(256) b200_cpy_q_f32_kernel(b200_tensor s, b200_tensor d, int64_t total) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const Idx4 a = unravel(e, s.ne), b = unravel(e, d.ne);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) cpy_q_f32_kernel(b200_tensor s, b200_tens
 }
 
 // get_rows: dst[:, i10, i11, i12] = src0[:, idx[i10,i11,i12], i11, i12]
-__global__ void __launch_bounds__(256) get_rows_kernel(b200_tensor s, b200_tensor idx, b200_tensor d, int64_t total) {
+__global__ void __launch_bounds__(256) b200_get_rows_kernel(b200_tensor s, b200_tensor idx, b200_tensor d, int64_t total) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const Idx4 i = unravel(e, d.ne);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) get_rows_kernel(b200_tensor s, b200_tenso
 // ---------------------------------------------------------------------------------------------- soft_max
 // ggml_compute_forward_soft_max_f32 (ggml-cpu.c:10224-10320): w = x*scale + slope*mask; max; exp(w-max) summed in double
 template <typename MT>
-__global__ void __launch_bounds__(256) soft_max_kernel(b200_tensor x, b200_tensor mask, b200_tensor y, float scale, float max_bias, int has_mask) {
+__global__ void __launch_bounds__(256) b200_soft_max_kernel(b200_tensor x, b200_tensor mask, b200_tensor y, float scale, float max_bias, int has_mask) {
     __shared__ double shd[8];
     __shared__ float shf[8];
     const int64_t row = blockIdx.x;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) soft_max_kernel(b200_tensor x, b200_tenso
 
 // ---------------------------------------------------------------------------------------------- argsort / sum_rows
 // bitonic sort of one row (ncols <= 1024) in shared memory; ties keep the lower index first like a stable CPU sort
-__global__ void argsort_kernel(b200_tensor x, b200_tensor y, int ncols_pad, int desc) {
+__global__ void b200_argsort_kernel(b200_tensor x, b200_tensor y, int ncols_pad, int desc) {
     extern __shared__ int sidx[];
     const int64_t row = blockIdx.x;
     const int64_t ne00 = x.ne[0];
@@ -352,7 +352,7 @@ __global__ void argsort_kernel(b200_tensor x, b200_tensor y, int ncols_pad, int 
     if (t < ne00) ((int32_t *)((char *)y.data + row * y.nb[1]))[t] = sidx[t];
 }
 
-__global__ void __launch_bounds__(256) sum_rows_kernel(b200_tensor x, b200_tensor y) {
+__global__ void __launch_bounds__(256) b200_sum_rows_kernel(b200_tensor x, b200_tensor y) {
     __shared__ double sh[8];
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % x.ne[1], i2 = (row / x.ne[1]) % x.ne[2], i3 = row / (x.ne[1] * x.ne[2]);
@@ -386,14 +386,14 @@ template <int OP> int launch_bin(b200_ctx *ctx, const b200_op *op) {
         if (same_shape(a, b)) brow4 = 0;
         else if (b.ne[0] == a.ne[0] && b.ne[1] == 1 && b.ne[2] == 1 && b.ne[3] == 1) brow4 = b.ne[0] / 4;
         if (brow4 >= 0) {
-            bin_fast_kernel<OP><<<nblk(total / 4, 256), 256, 0, ctx->stream>>>((const float4 *)a.data, (const float4 *)b.data,
+            b200_bin_fast_kernel<OP><<<nblk(total / 4, 256), 256, 0, ctx->stream>>>((const float4 *)a.data, (const float4 *)b.data,
                                                                               (float4 *)d.data, total / 4, brow4);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;
         }
     }
-    bin_bcast_kernel<OP><<<nblk(total, 256), 256, 0, ctx->stream>>>(a, b, d, total);
+    b200_bin_bcast_kernel<OP><<<nblk(total, 256), 256, 0, ctx->stream>>>(a, b, d, total);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
@@ -402,7 +402,7 @@ template <int OP> int launch_bin(b200_ctx *ctx, const b200_op *op) {
 template <int OP> int launch_unary(b200_ctx *ctx, const b200_op *op, float p) {
     const int64_t n = tensor_nelements(op->dst);
     if (n == 0) return B200_OK;
-    unary_kernel<OP><<<nblk(n, 256), 256, 0, ctx->stream>>>((const float *)op->src[0].data,
+    b200_unary_kernel<OP><<<nblk(n, 256), 256, 0, ctx->stream>>>((const float *)op->src[0].data,
                                                             OP == UN_SWIGLU ? (const float *)op->src[1].data : nullptr,
                                                             (float *)op->dst.data, n, p);
     ctx->launches++;
@@ -423,7 +423,7 @@ int launch_cpy(b200_ctx *ctx, const b200_tensor &s, const b200_tensor &d) {
     const int64_t total = tensor_nelements(s);
     if (total == 0) return B200_OK;
     const int st = s.type, dt = d.type;
-#define CPY_CASE(TS, TD) cpy_kernel<TS, TD><<<nblk(total, 256), 256, 0, ctx->stream>>>(s, d, total)
+#define CPY_CASE(TS, TD) b200_cpy_kernel<TS, TD><<<nblk(total, 256), 256, 0, ctx->stream>>>(s, d, total)
     if (st == B200_TYPE_F32 && dt == B200_TYPE_F32) CPY_CASE(float, float);
     else if (st == B200_TYPE_F32 && dt == B200_TYPE_F16) CPY_CASE(float, __half);
     else if (st == B200_TYPE_F32 && dt == B200_TYPE_BF16) CPY_CASE(float, __nv_bfloat16);
@@ -431,9 +431,9 @@ int launch_cpy(b200_ctx *ctx, const b200_tensor &s, const b200_tensor &d) {
     else if (st == B200_TYPE_F16 && dt == B200_TYPE_F32) CPY_CASE(__half, float);
     else if (st == B200_TYPE_BF16 && dt == B200_TYPE_F32) CPY_CASE(__nv_bfloat16, float);
     else if (st == B200_TYPE_I32 && dt == B200_TYPE_I32) CPY_CASE(int32_t, int32_t);
-    else if (st == B200_TYPE_F32 && dt == B200_TYPE_Q8_0) cpy_f32_q_kernel<B200_TYPE_Q8_0><<<nblk(total / 32, 128), 128, 0, ctx->stream>>>(s, d, total / 32);
-    else if (st == B200_TYPE_F32 && dt == B200_TYPE_Q4_0) cpy_f32_q_kernel<B200_TYPE_Q4_0><<<nblk(total / 32, 128), 128, 0, ctx->stream>>>(s, d, total / 32);
-    else if (b200_type_is_quant(st) && dt == B200_TYPE_F32) cpy_q_f32_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(s, d, total);
+    else if (st == B200_TYPE_F32 && dt == B200_TYPE_Q8_0) b200_cpy_f32_q_kernel<B200_TYPE_Q8_0><<<nblk(total / 32, 128), 128, 0, ctx->stream>>>(s, d, total / 32);
+    else if (st == B200_TYPE_F32 && dt == B200_TYPE_Q4_0) b200_cpy_f32_q_kernel<B200_TYPE_Q4_0><<<nblk(total / 32, 128), 128, 0, ctx->stream>>>(s, d, total / 32);
+    else if (b200_type_is_quant(st) && dt == B200_TYPE_F32) b200_cpy_q_f32_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(s, d, total);
     else { b200_set_error("cpy %d -> %d", st, dt); return B200_ERR_UNSUPPORTED; }
 #undef CPY_CASE
     ctx->launches++;
@@ -441,7 +441,127 @@ int launch_cpy(b200_ctx *ctx, const b200_tensor &s, const b200_tensor &d) {
     return B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- fused rope + KV store (decode)
+// One launch replaces ROPE(q), ROPE(k), CPY(k -> cache), CPY(v -> cache) of a llama attention block
+// (llama-graph.cpp:1375-1397 + llama-model.cpp:4133-4143).  Arithmetic is that of the unfused kernels above, in the
+// same order: rope result rounded to f32, then the KV-store conversion (f16 RNE / quantize_row_q8_0 / quantize_row_q4_0_ref).
+// grid = (H + 2*Hkv head slots, T tokens); block = 64 threads (one per rotated pair, D <= 128... looped for larger D)
+template <int KVT>
+__global__ void __launch_bounds__(64) b200_rope_store_kernel(const RopeStoreDesc d, RopeParams rp) {
+    __shared__ float sh[512];
+    if (d.use_pdl) { pdl_trigger(); pdl_wait(); }
+    const int slot = blockIdx.x, t = blockIdx.y;
+    const int D = d.D, H = d.H, Hkv = d.Hkv;
+    const bool is_q = slot < H, is_k = !is_q && slot < H + Hkv;
+    const int head = is_q ? slot : (is_k ? slot - H : slot - H - Hkv);
+    const float *src = is_q ? d.q + ((size_t)t * H + head) * D : (is_k ? d.k : d.v) + ((size_t)t * Hkv + head) * D;
+    if (is_q || is_k) {
+        const int p = d.pos[t];
+        const bool neox = (rp.mode & 2) != 0;
+        float *qo = is_q ? (float *)((char *)d.q_out + (size_t)head * d.q_out_nb1 + (size_t)t * d.q_out_nb2) : sh;
+        for (int ip = threadIdx.x; ip < D / 2; ip += blockDim.x) {
+            const int i0 = 2 * ip;
+            if (i0 < rp.n_dims) {
+                float theta = (float)p;
+                for (int k = 0; k < ip; k++) theta = __fmul_rn(theta, rp.theta_scale);
+                const float f = d.freq_factors ? d.freq_factors[ip] : 1.0f;
+                const float te = __fdiv_rn(theta, f);
+                float ti = __fmul_rn(rp.freq_scale, te), th = ti, ms = rp.attn_factor;
+                if (rp.ext_factor != 0.0f) {
+                    const float yv = __fdiv_rn((float)(i0 / 2) - rp.corr0, fmaxf(0.001f, rp.corr1 - rp.corr0));
+                    const float ramp = __fmul_rn(1.0f - fminf(1.0f, fmaxf(0.0f, yv)), rp.ext_factor);
+                    th = __fadd_rn(__fmul_rn(ti, 1.0f - ramp), __fmul_rn(te, ramp));
+                    ms = __fmul_rn(ms, 1.0f + 0.1f * logf(__fdiv_rn(1.0f, rp.freq_scale)));
+                }
+                const float c = __fmul_rn(cosf(th), ms), s = __fmul_rn(sinf(th), ms);
+                const int ia = neox ? ip : i0, ib = neox ? ip + rp.n_dims / 2 : i0 + 1;
+                const float x0 = src[ia], x1 = src[ib];
+                qo[ia] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+                qo[ib] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+            } else {
+                qo[i0] = src[i0];
+                qo[i0 + 1] = src[i0 + 1];
+            }
+        }
+        if (is_q) return;
+    } else {
+        for (int i = threadIdx.x; i < D; i += blockDim.x) sh[i] = src[i];
+    }
+    __syncthreads();
+    // ---- KV store of the row sh[0..D) into the cache: token t, head `head` ----
+    const void *base = is_k ? (d.k_dst_ind ? *d.k_dst_ind : d.k_dst) : (d.v_dst_ind ? *d.v_dst_ind : d.v_dst);
+    if (KVT == B200_TYPE_F16) {
+        __half *o = (__half *)base + ((size_t)t * Hkv + head) * D;
+        for (int i = threadIdx.x; i < D; i += blockDim.x) o[i] = __float2half_rn(sh[i]);
+    } else {
+        constexpr int BB = KVT == B200_TYPE_Q8_0 ? 34 : 18;
+        const int nb = D / 32;
+        if (threadIdx.x < nb) {
+            const float *v = sh + threadIdx.x * 32;
+            uint8_t *o = (uint8_t *)base + (((size_t)t * Hkv + head) * nb + threadIdx.x) * BB;
+            if (KVT == B200_TYPE_Q8_0) {
+                float amax = 0.0f;
+                for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+                const float dd = __fdiv_rn(amax, 127.0f);
+                const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+                *(__half *)o = __float2half_rn(dd);
+                for (int j = 0; j < 32; j++) o[2 + j] = (uint8_t)(int8_t)__float2int_rn(__fmul_rn(v[j], id));
+            } else {
+                float amax = 0.0f, mx = 0.0f;
+                for (int j = 0; j < 32; j++) { const float a = fabsf(v[j]); if (a > amax) { amax = a; mx = v[j]; } }
+                const float dd = __fdiv_rn(mx, -8.0f);
+                const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
+                *(__half *)o = __float2half_rn(dd);
+                for (int j = 0; j < 16; j++) {
+                    const float x0 = __fmul_rn(v[j], id), x1 = __fmul_rn(v[16 + j], id);
+                    int a = (int)(int8_t)(int)__fadd_rn(x0, 8.5f), c = (int)(int8_t)(int)__fadd_rn(x1, 8.5f);
+                    a = a > 15 ? 15 : a; c = c > 15 ? 15 : c;
+                    o[2 + j] = (uint8_t)((a & 0xff) | (c << 4));
+                }
+            }
+        }
+    }
+}
+
+RopeParams make_rope_params(const int32_t *params) {
+    RopeParams rp;
+    auto f = [&](int i) { float v; memcpy(&v, &params[i], 4); return v; };
+    rp.n_dims = params[1]; rp.mode = params[2]; rp.n_ctx_orig = params[4];
+    rp.freq_base = f(5); rp.freq_scale = f(6); rp.ext_factor = f(7);
+    rp.attn_factor = f(8); rp.beta_fast = f(9); rp.beta_slow = f(10);
+    rp.theta_scale = powf(rp.freq_base, -2.0f / rp.n_dims);
+    float lo = floorf(yarn_corr_dim(rp.n_dims, rp.n_ctx_orig, rp.beta_fast, rp.freq_base));
+    float hi = ceilf(yarn_corr_dim(rp.n_dims, rp.n_ctx_orig, rp.beta_slow, rp.freq_base));
+    rp.corr0 = lo < 0 ? 0 : lo;
+    rp.corr1 = hi > rp.n_dims - 1 ? (float)(rp.n_dims - 1) : hi;
+    return rp;
+}
+
 }  // namespace
+
+int launch_rope_store(b200_ctx *ctx, const RopeStoreDesc &din) {
+    RopeStoreDesc d = din;
+    d.use_pdl = ctx->opt_pdl;
+    const RopeParams rp = make_rope_params(d.rope_params);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(d.H + 2 * d.Hkv), (unsigned)d.T);
+    cfg.blockDim = dim3(64);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = d.use_pdl ? 1 : 0;
+    switch (d.kv_type) {
+        case B200_TYPE_F16:  CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_rope_store_kernel<B200_TYPE_F16>, d, rp)); break;
+        case B200_TYPE_Q8_0: CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_rope_store_kernel<B200_TYPE_Q8_0>, d, rp)); break;
+        case B200_TYPE_Q4_0: CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_rope_store_kernel<B200_TYPE_Q4_0>, d, rp)); break;
+        default: b200_set_error("rope_store: kv type %d", d.kv_type); return B200_ERR_UNSUPPORTED;
+    }
+    ctx->launches++;
+    return B200_OK;
+}
 
 bool supports_glue(const b200_op *op) {
     const b200_tensor &a = op->src[0], &b = op->src[1], &d = op->dst;
@@ -490,8 +610,8 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
         case B200_OP_RMS_NORM_MUL: {
             const int64_t rows = tensor_nrows(a);
             if (rows == 0) return B200_OK;
-            if (op->op == B200_OP_RMS_NORM) rms_norm_kernel<false><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, a, d, f32_param(op, 0));
-            else rms_norm_kernel<true><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0));
+            if (op->op == B200_OP_RMS_NORM) b200_rms_norm_kernel<false><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, a, d, f32_param(op, 0));
+            else b200_rms_norm_kernel<true><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0));
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;
@@ -521,8 +641,8 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
             if (a.ne[2] == 0 || a.ne[1] == 0) return B200_OK;
             const dim3 grid((unsigned)a.ne[2], (unsigned)a.ne[1], (unsigned)a.ne[3]);
             const int threads = a.ne[0] / 2 >= 128 ? 128 : (a.ne[0] / 2 >= 64 ? 64 : 32);
-            if (a.type == B200_TYPE_F32) rope_kernel<float><<<grid, threads, 0, ctx->stream>>>(a, b, op->src[2], d, rp, has_ff);
-            else rope_kernel<__half><<<grid, threads, 0, ctx->stream>>>(a, b, op->src[2], d, rp, has_ff);
+            if (a.type == B200_TYPE_F32) b200_rope_kernel<float><<<grid, threads, 0, ctx->stream>>>(a, b, op->src[2], d, rp, has_ff);
+            else b200_rope_kernel<__half><<<grid, threads, 0, ctx->stream>>>(a, b, op->src[2], d, rp, has_ff);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;
@@ -531,7 +651,7 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
         case B200_OP_GET_ROWS: {
             const int64_t total = tensor_nelements(d);
             if (total == 0) return B200_OK;
-            get_rows_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(a, b, d, total);
+            b200_get_rows_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(a, b, d, total);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;
@@ -541,9 +661,9 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
             if (rows == 0) return B200_OK;
             const int has_mask = op->n_src > 1 && b.data != nullptr;
             if (has_mask && b.type == B200_TYPE_F32)
-                soft_max_kernel<float><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), 1);
+                b200_soft_max_kernel<float><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), 1);
             else
-                soft_max_kernel<__half><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), has_mask);
+                b200_soft_max_kernel<__half><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), has_mask);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;
@@ -553,7 +673,7 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
             if (rows == 0) return B200_OK;
             int pad = 1;
             while (pad < a.ne[0]) pad <<= 1;
-            argsort_kernel<<<(unsigned)rows, pad, pad * sizeof(int), ctx->stream>>>(a, d, pad, op->params[0]);
+            b200_argsort_kernel<<<(unsigned)rows, pad, pad * sizeof(int), ctx->stream>>>(a, d, pad, op->params[0]);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;
@@ -561,7 +681,7 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
         case B200_OP_SUM_ROWS: {
             const int64_t rows = tensor_nrows(a);
             if (rows == 0) return B200_OK;
-            sum_rows_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(a, d);
+            b200_sum_rows_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(a, d);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;

@@ -8,7 +8,9 @@
 //   3. when cuda_graphs is on and the very same op list (pointers, shapes, params) was seen before,
 //      replay the captured cudaGraphExec instead of re-launching ~10 kernels per layer.
 #include "common.cuh"
+#include "gemv.h"
 #include <string.h>
+#include <algorithm>
 
 struct GraphCacheEntry {
     std::vector<b200_op> ops;
@@ -56,10 +58,51 @@ extern "C" int b200_op_compute(b200_ctx *ctx, const b200_op *op) {
 }
 
 // ---------------------------------------------------------------------------------------------- fusion
+// graph_compute turns the op list into an EXEC list.  Besides plain ops it knows three fused launches, all of them only
+// for decode-sized ubatches (<= 4 tokens), where kernel boundaries -- not bytes -- dominate:
+//   EX_GEMV        one streaming GEMV over 1-3 weight matrices with the producer ops folded into its prologue
+//                  (rms_norm*weight or silu(gate)*up, activation quantisation) and the residual ADD into its epilogue
+//   EX_ROPE_STORE  ROPE(q) + ROPE(k) + KV-store of k and v
+// A llama layer becomes: [norm+QKV] [rope+store] [flash_attn (+combine)] [wo+residual] [norm+gate|up] [swiglu+down+residual].
+// Intermediates that only lived between the fused ops are never materialised; the matcher proves with a liveness scan
+// over the op list (address ranges, first access after the pattern) that nobody else reads them.
+enum { EX_OP = 0, EX_GEMV = 1, EX_ROPE_STORE = 2 };
+struct ExecNode {
+    int kind = EX_OP;
+    b200_op op;                                  // EX_OP
+    GemvSegDesc seg[GEMV_MAX_SEG]; int nseg = 0; // EX_GEMV
+    int64_t K = 0; GemvActDesc act; int ncols = 0; bool w_const = false;
+    const void *pf_ptr = nullptr; size_t pf_bytes = 0;
+    RopeStoreDesc rs;                            // EX_ROPE_STORE
+    int kv_slot = -1;                            // index of this node's K destination in the KV pointer table (V = +1)
+};
+
 static bool same_tensor(const b200_tensor &a, const b200_tensor &b) {
     return a.data == b.data && a.type == b.type && !memcmp(a.ne, b.ne, sizeof(a.ne)) && !memcmp(a.nb, b.nb, sizeof(a.nb));
 }
-// is tensor t read by any op in [from, n) other than `except`?
+static void tensor_range(const b200_tensor &t, uintptr_t &lo, uintptr_t &hi) {
+    lo = (uintptr_t)t.data;
+    uint64_t span = (uint64_t)b200_type_block_bytes(t.type);
+    const int be = b200_type_block_elems(t.type);
+    span += (uint64_t)(t.ne[0] / be - 1) * t.nb[0];
+    for (int i = 1; i < 4; i++) if (t.ne[i] > 1) span += (uint64_t)(t.ne[i] - 1) * t.nb[i];
+    hi = lo + span;
+}
+static bool overlaps(const b200_tensor &a, const b200_tensor &b) {
+    if (!a.data || !b.data) return false;
+    uintptr_t al, ah, bl, bh;
+    tensor_range(a, al, ah); tensor_range(b, bl, bh);
+    return al < bh && bl < ah;
+}
+// is the VALUE currently held by tensor t still needed by ops[from..n)?  (first touch of its bytes: a read => yes, a write => no)
+static bool live_after(const b200_op *ops, int n, int from, const b200_tensor &t) {
+    for (int i = from; i < n; i++) {
+        for (int s = 0; s < ops[i].n_src && s < B200_MAX_SRC; s++) if (overlaps(ops[i].src[s], t)) return true;
+        if (overlaps(ops[i].dst, t)) return false;
+    }
+    return false;
+}
+// is tensor t read by any op in [from, n) other than `except`?  (old, address-only test for the two-op fusions)
 static bool read_later(const b200_op *ops, int n, int from, int except, const b200_tensor &t) {
     for (int i = from; i < n; i++) {
         if (i == except) continue;
@@ -68,12 +111,241 @@ static bool read_later(const b200_op *ops, int n, int from, int except, const b2
     return false;
 }
 
+static bool is_vec_f32(const b200_tensor &t, int64_t rows) {   // dense f32 [rows, T<=4]
+    return t.type == B200_TYPE_F32 && t.ne[0] == rows && t.ne[1] >= 1 && t.ne[1] <= 4 && t.ne[2] == 1 && t.ne[3] == 1 && t.nb[0] == 4 &&
+           t.nb[1] == (uint64_t)rows * 4 && !((uintptr_t)t.data & 15);
+}
+// a decode-sized quantised matmul the GEMV can take as a segment: W quant rows back to back, x dense [K, T], dst dense [N, T]
+static bool is_decode_mm(const b200_op &o) {
+    if (o.op != B200_OP_MUL_MAT || !supports_mul_mat(&o)) return false;
+    const b200_tensor &w = o.src[0], &x = o.src[1], &d = o.dst;
+    if (!b200_type_is_quant(w.type) || w.ne[2] != 1 || w.ne[3] != 1) return false;
+    return is_vec_f32(x, w.ne[0]) && is_vec_f32(d, w.ne[1]) && x.ne[1] == d.ne[1];
+}
+static GemvSegDesc seg_of(const b200_op &mm, float *dst, size_t dst_stride, const float *residual) {
+    GemvSegDesc g = {};
+    g.type = mm.src[0].type; g.W = (const uint8_t *)mm.src[0].data; g.rb = b200_row_bytes(g.type, mm.src[0].ne[0]); g.N = mm.src[0].ne[1];
+    g.dst = dst; g.dst_stride = dst_stride; g.residual = residual;
+    return g;
+}
+static bool all_weights(const b200_op *const *mms, int n) {
+    for (int i = 0; i < n; i++) if (!(mms[i]->src[0].flags & B200_TENSOR_FLAG_WEIGHT)) return false;
+    return true;
+}
+
+// RMS_NORM(x) -> MUL(norm, w): returns true and the norm weight when ops[i], ops[i+1] form that pair over a dense [E, T<=4] x
+static bool match_norm_mul(const b200_op *ops, int n, int i, const b200_tensor *&xin, const float *&w, float &eps) {
+    if (i + 1 >= n || ops[i].op != B200_OP_RMS_NORM || ops[i + 1].op != B200_OP_MUL) return false;
+    const b200_op &a = ops[i], &b = ops[i + 1];
+    if (!is_vec_f32(a.src[0], a.src[0].ne[0]) || !same_tensor(b.src[0], a.dst) || !is_vec_f32(b.dst, a.src[0].ne[0])) return false;
+    const b200_tensor &nw = b.src[1];
+    if (nw.type != B200_TYPE_F32 || nw.nb[0] != 4 || nw.ne[0] != a.src[0].ne[0] || nw.ne[1] != 1 || nw.ne[2] != 1 || nw.ne[3] != 1 || ((uintptr_t)nw.data & 15)) return false;
+    xin = &a.src[0]; w = (const float *)nw.data;
+    memcpy(&eps, &a.params[0], 4);
+    return true;
+}
+
+struct FuseScratch { float *q, *k, *v, *g, *u; };
+
+// attention block: NORM MUL {MMq MMk MMv ROPEq ROPEk CPYk CPYv in any dependency-respecting order} FA
+static int match_attention(b200_ctx *ctx, const b200_op *ops, int n, int i, const FuseScratch &fs, std::vector<ExecNode> &out) {
+    const b200_tensor *xin; const float *nw; float eps;
+    if (i + 9 >= n || !match_norm_mul(ops, n, i, xin, nw, eps)) return 0;
+    const b200_op &fa = ops[i + 9];
+    if (fa.op != B200_OP_FLASH_ATTN_EXT) return 0;
+    const b200_op *mm[3], *rope[2], *cpy[2];
+    int nmm = 0, nrope = 0, ncpy = 0;
+    for (int j = i + 2; j < i + 9; j++) {
+        const b200_op &o = ops[j];
+        if (o.op == B200_OP_MUL_MAT && nmm < 3) mm[nmm++] = &o;
+        else if (o.op == B200_OP_ROPE && nrope < 2) rope[nrope++] = &o;
+        else if (o.op == B200_OP_CPY && ncpy < 2) cpy[ncpy++] = &o;
+        else return 0;
+    }
+    if (nmm != 3 || nrope != 2 || ncpy != 2) return 0;
+    const b200_tensor &B = ops[i + 1].dst;
+    for (int j = 0; j < 3; j++) if (!is_decode_mm(*mm[j]) || !same_tensor(mm[j]->src[1], B)) return 0;
+    if (!all_weights(mm, 3)) return 0;
+    // roles: q = the matmul whose rope feeds FA; k = the matmul whose rope feeds a CPY; v = the matmul feeding a CPY directly
+    const b200_op *mq = nullptr, *mk = nullptr, *mv = nullptr, *rq = nullptr, *rk = nullptr, *ck = nullptr, *cv = nullptr;
+    for (int r = 0; r < 2; r++) {
+        if (rope[r]->dst.data == fa.src[0].data) rq = rope[r];
+        for (int c = 0; c < 2; c++) if (cpy[c]->src[0].data == rope[r]->dst.data) { rk = rope[r]; ck = cpy[c]; }
+    }
+    if (!rq || !rk || rq == rk) return 0;
+    cv = ck == cpy[0] ? cpy[1] : cpy[0];
+    for (int j = 0; j < 3; j++) {
+        if (mm[j]->dst.data == rq->src[0].data) mq = mm[j];
+        else if (mm[j]->dst.data == rk->src[0].data) mk = mm[j];
+        else if (mm[j]->dst.data == cv->src[0].data) mv = mm[j];
+    }
+    if (!mq || !mk || !mv) return 0;
+    // shapes: rope over [D, heads, T] f32 dense views of the matmul outputs, identical rope parameters and positions
+    const int64_t T = B.ne[1], D = rq->src[0].ne[0], H = rq->src[0].ne[1], Hkv = rk->src[0].ne[1];
+    auto rope_ok = [&](const b200_op *r, int64_t heads) {
+        const b200_tensor &a = r->src[0];
+        return a.type == B200_TYPE_F32 && r->dst.type == B200_TYPE_F32 && a.ne[0] == D && a.ne[1] == heads && a.ne[2] == T && a.ne[3] == 1 &&
+               a.nb[0] == 4 && a.nb[1] == (uint64_t)D * 4 && a.nb[2] == (uint64_t)D * heads * 4 && r->src[1].type == B200_TYPE_I32 &&
+               r->src[1].ne[0] == T && supports_glue(r);
+    };
+    if (D > 512 || D % 32 || !rope_ok(rq, H) || !rope_ok(rk, Hkv)) return 0;
+    if (memcmp(rq->params, rk->params, sizeof(rq->params)) || rq->src[1].data != rk->src[1].data || rq->src[2].data != rk->src[2].data) return 0;
+    if (mq->src[0].ne[1] != H * D || mk->src[0].ne[1] != Hkv * D || mv->src[0].ne[1] != Hkv * D) return 0;
+    const b200_tensor &qd = rq->dst;
+    if (qd.nb[0] != 4 || qd.ne[0] != D || qd.ne[1] != H || qd.ne[2] != T) return 0;
+    // KV store destinations: contiguous runs of T rows of Hkv*D elements in the cache type
+    const int kvt = ck->dst.type;
+    if (kvt != cv->dst.type || (kvt != B200_TYPE_F16 && kvt != B200_TYPE_Q8_0 && kvt != B200_TYPE_Q4_0)) return 0;
+    if (!tensor_is_contiguous(ck->dst) || !tensor_is_contiguous(cv->dst) || tensor_nelements(ck->dst) != Hkv * D * T ||
+        tensor_nelements(cv->dst) != Hkv * D * T) return 0;
+    if (ck->src[0].type != B200_TYPE_F32 || cv->src[0].type != B200_TYPE_F32 || !tensor_is_contiguous(ck->src[0]) || !tensor_is_contiguous(cv->src[0])) return 0;
+    // nobody else may need the intermediates we never write
+    const b200_tensor *dead[] = {&ops[i].dst, &B, &mq->dst, &mk->dst, &mv->dst, &rk->dst};
+    for (const b200_tensor *t : dead) if (live_after(ops, n, i + 9, *t)) return 0;
+    (void)ctx;
+    ExecNode g;
+    g.kind = EX_GEMV; g.nseg = 3; g.K = xin->ne[0]; g.ncols = (int)T; g.w_const = true;
+    g.seg[0] = seg_of(*mq, fs.q, (size_t)(H * D), nullptr);
+    g.seg[1] = seg_of(*mk, fs.k, (size_t)(Hkv * D), nullptr);
+    g.seg[2] = seg_of(*mv, fs.v, (size_t)(Hkv * D), nullptr);
+    g.act = GemvActDesc{};
+    g.act.mode = ACT_F32_NORM; g.act.x = (const float *)xin->data; g.act.x_stride = xin->nb[1]; g.act.x2 = nw; g.act.eps = eps;
+    if (b200_act_mode_q8k(g.seg[0].type) != b200_act_mode_q8k(g.seg[1].type) || b200_act_mode_q8k(g.seg[0].type) != b200_act_mode_q8k(g.seg[2].type)) return 0;
+    out.push_back(g);
+    ExecNode r;
+    r.kind = EX_ROPE_STORE;
+    RopeStoreDesc &d = r.rs;
+    memset(&d, 0, sizeof(d));
+    d.q = fs.q; d.k = fs.k; d.v = fs.v;
+    d.pos = (const int32_t *)rq->src[1].data;
+    d.freq_factors = rq->n_src > 2 ? (const float *)rq->src[2].data : nullptr;
+    d.q_out = (float *)qd.data; d.q_out_nb1 = qd.nb[1]; d.q_out_nb2 = qd.nb[2];
+    d.k_dst = ck->dst.data; d.v_dst = cv->dst.data;
+    d.D = (int)D; d.H = (int)H; d.Hkv = (int)Hkv; d.T = (int)T; d.kv_type = kvt;
+    memcpy(d.rope_params, rq->params, sizeof(d.rope_params));
+    out.push_back(r);
+    ExecNode f;
+    f.kind = EX_OP; f.op = fa;
+    out.push_back(f);
+    return 10;
+}
+
+// FFN block: NORM MUL {MMgate SILU MMup MUL MMdown} ADD
+static int match_ffn(const b200_op *ops, int n, int i, const FuseScratch &fs, std::vector<ExecNode> &out) {
+    const b200_tensor *xin; const float *nw; float eps;
+    if (i + 7 >= n || !match_norm_mul(ops, n, i, xin, nw, eps)) return 0;
+    const b200_op &add = ops[i + 7];
+    if (add.op != B200_OP_ADD) return 0;
+    const b200_op *mm[3], *silu = nullptr, *mul = nullptr;
+    int nmm = 0;
+    for (int j = i + 2; j < i + 7; j++) {
+        const b200_op &o = ops[j];
+        if (o.op == B200_OP_MUL_MAT && nmm < 3) mm[nmm++] = &o;
+        else if (o.op == B200_OP_SILU && !silu) silu = &o;
+        else if (o.op == B200_OP_MUL && !mul) mul = &o;
+        else return 0;
+    }
+    if (nmm != 3 || !silu || !mul) return 0;
+    const b200_tensor &B = ops[i + 1].dst;
+    const b200_op *gate = nullptr, *up = nullptr, *down = nullptr;
+    for (int j = 0; j < 3; j++) {
+        if (!is_decode_mm(*mm[j])) return 0;
+        if (same_tensor(mm[j]->src[1], B)) { if (mm[j]->dst.data == silu->src[0].data) gate = mm[j]; else up = mm[j]; }
+        else down = mm[j];
+    }
+    if (!gate || !up || !down || !all_weights(mm, 3)) return 0;
+    if (!((mul->src[0].data == silu->dst.data && mul->src[1].data == up->dst.data) || (mul->src[1].data == silu->dst.data && mul->src[0].data == up->dst.data))) return 0;
+    if (!same_tensor(down->src[1], mul->dst)) return 0;
+    const b200_tensor *resid = add.src[0].data == down->dst.data ? &add.src[1] : (add.src[1].data == down->dst.data ? &add.src[0] : nullptr);
+    if (!resid) return 0;
+    const int64_t T = B.ne[1], FF = gate->src[0].ne[1], E = down->src[0].ne[1];
+    if (up->src[0].ne[1] != FF || down->src[0].ne[0] != FF || !is_vec_f32(*resid, E) || !is_vec_f32(add.dst, E) || resid->ne[1] != T || add.dst.ne[1] != T) return 0;
+    if (b200_act_mode_q8k(gate->src[0].type) != b200_act_mode_q8k(up->src[0].type)) return 0;
+    const b200_tensor *dead[] = {&ops[i].dst, &B, &gate->dst, &silu->dst, &up->dst, &mul->dst, &down->dst};
+    for (const b200_tensor *t : dead) if (!overlaps(*t, add.dst) && live_after(ops, n, i + 8, *t)) return 0;
+    ExecNode g;
+    g.kind = EX_GEMV; g.nseg = 2; g.K = xin->ne[0]; g.ncols = (int)T; g.w_const = true;
+    g.seg[0] = seg_of(*gate, fs.g, (size_t)FF, nullptr);
+    g.seg[1] = seg_of(*up, fs.u, (size_t)FF, nullptr);
+    g.act = GemvActDesc{};
+    g.act.mode = ACT_F32_NORM; g.act.x = (const float *)xin->data; g.act.x_stride = xin->nb[1]; g.act.x2 = nw; g.act.eps = eps;
+    out.push_back(g);
+    ExecNode d;
+    d.kind = EX_GEMV; d.nseg = 1; d.K = FF; d.ncols = (int)T; d.w_const = true;
+    d.seg[0] = seg_of(*down, (float *)add.dst.data, (size_t)E, (const float *)resid->data);
+    d.act = GemvActDesc{};
+    d.act.mode = ACT_F32_SWIGLU; d.act.x = fs.g; d.act.x_stride = (size_t)FF * 4; d.act.x2 = fs.u;
+    out.push_back(d);
+    return 8;
+}
+
+// MUL_MAT -> ADD(mm, residual)
+static int match_mm_add(const b200_op *ops, int n, int i, std::vector<ExecNode> &out) {
+    if (i + 1 >= n || !is_decode_mm(ops[i]) || ops[i + 1].op != B200_OP_ADD) return 0;
+    const b200_op &mm = ops[i], &add = ops[i + 1];
+    if (!(mm.src[0].flags & B200_TENSOR_FLAG_WEIGHT)) return 0;
+    const b200_tensor *resid = add.src[0].data == mm.dst.data ? &add.src[1] : (add.src[1].data == mm.dst.data ? &add.src[0] : nullptr);
+    const int64_t N = mm.src[0].ne[1], T = mm.dst.ne[1];
+    if (!resid || !is_vec_f32(*resid, N) || !is_vec_f32(add.dst, N) || resid->ne[1] != T || add.dst.ne[1] != T) return 0;
+    if (overlaps(add.dst, mm.src[1])) return 0;
+    if (!overlaps(mm.dst, add.dst) && live_after(ops, n, i + 2, mm.dst)) return 0;
+    ExecNode g;
+    g.kind = EX_GEMV; g.nseg = 1; g.K = mm.src[0].ne[0]; g.ncols = (int)T; g.w_const = true;
+    g.seg[0] = seg_of(mm, (float *)add.dst.data, (size_t)N, (const float *)resid->data);
+    g.act = GemvActDesc{};
+    g.act.mode = ACT_F32; g.act.x = (const float *)mm.src[1].data; g.act.x_stride = mm.src[1].nb[1];
+    out.push_back(g);
+    return 2;
+}
+
+// NORM MUL MUL_MAT (final norm + output projection, or any single consumer)
+static int match_norm_mm(const b200_op *ops, int n, int i, std::vector<ExecNode> &out) {
+    const b200_tensor *xin; const float *nw; float eps;
+    if (i + 2 >= n || !match_norm_mul(ops, n, i, xin, nw, eps) || !is_decode_mm(ops[i + 2])) return 0;
+    const b200_op &mm = ops[i + 2];
+    if (!same_tensor(mm.src[1], ops[i + 1].dst) || !(mm.src[0].flags & B200_TENSOR_FLAG_WEIGHT)) return 0;
+    if (live_after(ops, n, i + 3, ops[i].dst) || live_after(ops, n, i + 3, ops[i + 1].dst)) return 0;
+    if (overlaps(mm.dst, *xin)) return 0;
+    ExecNode g;
+    g.kind = EX_GEMV; g.nseg = 1; g.K = xin->ne[0]; g.ncols = (int)mm.dst.ne[1]; g.w_const = true;
+    g.seg[0] = seg_of(mm, (float *)mm.dst.data, (size_t)mm.src[0].ne[1], nullptr);
+    g.act = GemvActDesc{};
+    g.act.mode = ACT_F32_NORM; g.act.x = (const float *)xin->data; g.act.x_stride = xin->nb[1]; g.act.x2 = nw; g.act.eps = eps;
+    out.push_back(g);
+    return 3;
+}
+
 // returns the list actually executed
-static void fuse(const b200_op *ops, int n, std::vector<b200_op> &out) {
+static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> &out) {
     out.clear();
     out.reserve(n);
-    for (int i = 0; i < n; i++) {
+    // scratch for the intermediates of the layer fusions (q,k,v and gate,up): sized from the largest matmuls in the list
+    FuseScratch fs = {};
+    bool layer_fusion = ctx->opt_fusion >= 2;
+    if (layer_fusion) {
+        int64_t maxN = 0;
+        for (int i = 0; i < n; i++) if (ops[i].op == B200_OP_MUL_MAT && is_decode_mm(ops[i]) && ops[i].src[0].ne[1] < (1 << 16)) maxN = std::max(maxN, ops[i].src[0].ne[1]);
+        if (maxN == 0) layer_fusion = false;
+        else {
+            const size_t per = (size_t)maxN * 4 * 4;      // up to 4 columns
+            float *base = (float *)ctx->get_scratch(SCRATCH_FUSE, per * 5);
+            if (!base) return B200_ERR_ALLOC;
+            fs.q = base; fs.k = base + per / 4; fs.v = base + 2 * (per / 4); fs.g = base + 3 * (per / 4); fs.u = base + 4 * (per / 4);
+        }
+    }
+    for (int i = 0; i < n;) {
         const b200_op &a = ops[i];
+        if (layer_fusion) {
+            int used = 0;
+            if (a.op == B200_OP_RMS_NORM) {
+                used = match_attention(ctx, ops, n, i, fs, out);
+                if (!used) used = match_ffn(ops, n, i, fs, out);
+                if (!used) used = match_norm_mm(ops, n, i, out);
+            } else if (a.op == B200_OP_MUL_MAT) {
+                used = match_mm_add(ops, n, i, out);
+            }
+            if (used) { i += used; continue; }
+        }
         if (i + 1 < n) {
             const b200_op &b = ops[i + 1];
             // RMS_NORM -> MUL(norm, weight): y = rms_norm(x) * w
@@ -85,7 +357,7 @@ static void fuse(const b200_op *ops, int n, std::vector<b200_op> &out) {
                 f.n_src = 2;
                 f.src[1] = b.src[1];
                 f.dst = b.dst;
-                if (supports_glue(&f)) { out.push_back(f); i++; continue; }
+                if (supports_glue(&f)) { ExecNode e; e.op = f; out.push_back(e); i += 2; continue; }
             }
             // SILU(gate) -> MUL(silu, up)
             if (a.op == B200_OP_SILU && b.op == B200_OP_MUL && same_tensor(b.src[0], a.dst) &&
@@ -95,16 +367,34 @@ static void fuse(const b200_op *ops, int n, std::vector<b200_op> &out) {
                 f.n_src = 2;
                 f.src[1] = b.src[1];
                 f.dst = b.dst;
-                if (supports_glue(&f)) { out.push_back(f); i++; continue; }
+                if (supports_glue(&f)) { ExecNode e; e.op = f; out.push_back(e); i += 2; continue; }
             }
         }
-        out.push_back(a);
+        ExecNode e;
+        e.op = a;
+        out.push_back(e);
+        i++;
     }
+    // weight look-ahead: every fused GEMV asks the L2 to start fetching the weights of the next GEMV-like node
+    const ExecNode *next = nullptr;
+    for (int i = (int)out.size() - 1; i >= 0; i--) {
+        ExecNode &e = out[i];
+        const bool mm_op = e.kind == EX_OP && e.op.op == B200_OP_MUL_MAT && b200_type_is_quant(e.op.src[0].type) && (e.op.src[0].flags & B200_TENSOR_FLAG_WEIGHT);
+        if (e.kind == EX_GEMV && next) {
+            if (next->kind == EX_GEMV) { e.pf_ptr = next->seg[0].W; e.pf_bytes = (size_t)next->seg[0].N * next->seg[0].rb; }
+            else { e.pf_ptr = next->op.src[0].data; e.pf_bytes = (size_t)next->op.src[0].ne[1] * b200_row_bytes(next->op.src[0].type, next->op.src[0].ne[0]); }
+        }
+        if (e.kind == EX_GEMV || mm_op) next = &e;
+    }
+    return B200_OK;
 }
 
-static int run_list(b200_ctx *ctx, const std::vector<b200_op> &ops) {
-    for (const b200_op &op : ops) {
-        int rc = dispatch(ctx, &op);
+static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
+    for (const ExecNode &e : list) {
+        int rc;
+        if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf_ptr, e.pf_bytes);
+        else if (e.kind == EX_ROPE_STORE) rc = launch_rope_store(ctx, e.rs);
+        else rc = dispatch(ctx, &e.op);
         if (rc) return rc;
     }
     return B200_OK;
@@ -123,9 +413,9 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
             b200_set_error("graph op %d (id %d) not supported", i, ops[i].op);
             return B200_ERR_UNSUPPORTED;
         }
-    std::vector<b200_op> list;
-    if (ctx->opt_fusion) fuse(ops, n_ops, list);
-    else list.assign(ops, ops + n_ops);
+    std::vector<ExecNode> list;
+    if (ctx->opt_fusion) { int frc = fuse(ctx, ops, n_ops, list); if (frc) return frc; }
+    else { list.resize(n_ops); for (int i = 0; i < n_ops; i++) list[i].op = ops[i]; }
 
     if (!ctx->opt_cuda_graphs || n_ops < 8) return run_list(ctx, list);
 

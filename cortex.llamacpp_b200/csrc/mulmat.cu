@@ -16,6 +16,8 @@ int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);
 int launch_gemv_f32(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const float *x, size_t x_stride_bytes,
                     int ncols, float *dst, size_t dst_col_stride, bool w_const, int fuse_mode, const float *x2, float eps,
                     const float *residual);
+int launch_gemv_expert(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, size_t expert_stride, const int32_t *expert_id, int64_t N,
+                       int64_t K, const float *x, float *dst);
 int launch_gemm_i8(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
                    int64_t ncols, float *dst, size_t dst_col_stride, bool *handled);
 
@@ -35,7 +37,7 @@ template <> __device__ __forceinline__ float x_round<__half>(float v) { return _
 template <> __device__ __forceinline__ float x_round<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 template <typename WT>
-__global__ void __launch_bounds__(128) mul_mat_float_kernel(b200_tensor w, b200_tensor x, b200_tensor d) {
+__global__ void __launch_bounds__(128) b200_mul_mat_float_kernel(b200_tensor w, b200_tensor x, b200_tensor d) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     const int64_t N = d.ne[0], M = d.ne[1];
@@ -60,9 +62,9 @@ int mul_mat_float(b200_ctx *ctx, const b200_tensor &w, const b200_tensor &x, con
     if (total == 0) return B200_OK;
     const unsigned grid = (unsigned)((total + 3) / 4);
     switch (w.type) {
-        case B200_TYPE_F32:  mul_mat_float_kernel<float><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
-        case B200_TYPE_F16:  mul_mat_float_kernel<__half><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
-        case B200_TYPE_BF16: mul_mat_float_kernel<__nv_bfloat16><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
+        case B200_TYPE_F32:  b200_mul_mat_float_kernel<float><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
+        case B200_TYPE_F16:  b200_mul_mat_float_kernel<__half><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
+        case B200_TYPE_BF16: b200_mul_mat_float_kernel<__nv_bfloat16><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
         default: return B200_ERR_UNSUPPORTED;
     }
     ctx->launches++;
@@ -152,6 +154,42 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
             float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
             int rc = mul_mat_q_cols(ctx, w.type, wp, rb, N, K, act + (size_t)((i3 * x.ne[2] + i2) * M) * L.col_bytes, M, dp,
                                     d.nb[1] / 4, w_const);
+            if (rc) return rc;
+        }
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MUL_MAT_ID (ggml_compute_forward_mul_mat_id, ggml-cpu.c:8902-...): dst[:, slot, tok] = as[ids[slot, tok]] . b[:, slot % b_ne1, tok]
+// The expert index is read ON THE DEVICE by the GEMV (no D2H copy of ids + stream sync as in ggml-cuda.cu:1976-1979), so
+// the op is capturable in a CUDA graph.  One streaming GEMV per (token, slot); a grouped tcgen05 GEMM takes the large
+// batches (gemm_i8.cu) when the tokens-per-expert counts make it worthwhile.
+// ---------------------------------------------------------------------------------------------------
+bool supports_mul_mat_id(const b200_op *op) {
+    const b200_tensor &as = op->src[0], &b = op->src[1], &ids = op->src[2], &d = op->dst;
+    if (!b200_type_is_quant(as.type) || b.type != B200_TYPE_F32 || d.type != B200_TYPE_F32 || ids.type != B200_TYPE_I32) return false;
+    const int64_t K = as.ne[0];
+    if (K % b200_type_block_elems(as.type) != 0 || K % 32 != 0 || b.ne[0] != K) return false;
+    if (as.nb[0] != (uint64_t)b200_type_block_bytes(as.type) || as.nb[1] != b200_row_bytes(as.type, K)) return false;
+    if ((as.type == B200_TYPE_Q4_K || as.type == B200_TYPE_Q5_K) && (((uintptr_t)as.data & 15) || (as.nb[2] & 15))) return false;
+    if (as.ne[3] != 1 || b.ne[3] != 1 || d.ne[3] != 1) return false;
+    if (b.nb[0] != 4 || d.nb[0] != 4 || ids.nb[0] != 4) return false;
+    if ((b.nb[1] & 15) || (b.nb[2] & 15) || ((uintptr_t)b.data & 15)) return false;
+    if (d.ne[0] != as.ne[1] || d.ne[1] != ids.ne[0] || d.ne[2] != ids.ne[1] || b.ne[2] != ids.ne[1]) return false;
+    if (b.ne[1] != 1 && b.ne[1] != ids.ne[0]) return false;
+    return true;
+}
+
+int op_mul_mat_id(b200_ctx *ctx, const b200_op *op) {
+    const b200_tensor &as = op->src[0], &b = op->src[1], &ids = op->src[2], &d = op->dst;
+    const int64_t K = as.ne[0], N = as.ne[1], n_used = ids.ne[0], n_tok = ids.ne[1];
+    const size_t rb = b200_row_bytes(as.type, K);
+    for (int64_t t = 0; t < n_tok; t++)
+        for (int64_t s = 0; s < n_used; s++) {
+            const int32_t *idp = (const int32_t *)((const char *)ids.data + s * ids.nb[0] + t * ids.nb[1]);
+            const float *xp = (const float *)((const char *)b.data + (s % b.ne[1]) * b.nb[1] + t * b.nb[2]);
+            float *dp = (float *)((char *)d.data + s * d.nb[1] + t * d.nb[2]);
+            int rc = launch_gemv_expert(ctx, as.type, (const uint8_t *)as.data, rb, as.nb[2], idp, N, K, xp, dp);
             if (rc) return rc;
         }
     return B200_OK;

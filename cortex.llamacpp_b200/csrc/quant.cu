@@ -14,7 +14,7 @@
 namespace {
 
 // one warp per 256 elements; lane owns 8 consecutive elements
-__global__ void __launch_bounds__(128) quantize_q8k_kernel(const float *__restrict__ x, size_t x_col_stride, int64_t K,
+__global__ void __launch_bounds__(128) b200_quantize_q8k_kernel(const float *__restrict__ x, size_t x_col_stride, int64_t K,
                                                            int64_t ncols, uint8_t *__restrict__ out, ActLayout L) {
     const int lane = threadIdx.x & 31;
     const int64_t nblk = K / 256;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) quantize_q8k_kernel(const float *__restri
 }
 
 // one warp per 256 elements = 8 blocks of 32; 4 lanes per block
-__global__ void __launch_bounds__(128) quantize_q80_kernel(const float *__restrict__ x, size_t x_col_stride, int64_t K,
+__global__ void __launch_bounds__(128) b200_quantize_q80_kernel(const float *__restrict__ x, size_t x_col_stride, int64_t K,
                                                            int64_t ncols, uint8_t *__restrict__ out, ActLayout L) {
     const int lane = threadIdx.x & 31;
     const int64_t nchunk = (K + 255) / 256;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) quantize_q80_kernel(const float *__restri
 }
 
 // scratch layout -> the reference's canonical block bytes (test hook only)
-__global__ void repack_q8k_kernel(const uint8_t *__restrict__ in, ActLayout L, int64_t ncols, uint8_t *__restrict__ blocks) {
+__global__ void b200_repack_q8k_kernel(const uint8_t *__restrict__ in, ActLayout L, int64_t ncols, uint8_t *__restrict__ blocks) {
     const int64_t nblk = L.K / 256;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblk * ncols) return;
@@ -80,7 +80,7 @@ __global__ void repack_q8k_kernel(const uint8_t *__restrict__ in, ActLayout L, i
     for (int j = 0; j < 256; j++) o[4 + j] = ic[b * 256 + j];
     for (int j = 0; j < 16; j++) *(int16_t *)(o + 260 + 2 * j) = ((const int16_t *)(ic + L.off_sums))[b * 16 + j];
 }
-__global__ void repack_q80_kernel(const uint8_t *__restrict__ in, ActLayout L, int64_t ncols, uint8_t *__restrict__ blocks) {
+__global__ void b200_repack_q80_kernel(const uint8_t *__restrict__ in, ActLayout L, int64_t ncols, uint8_t *__restrict__ blocks) {
     const int64_t nblk = L.K / 32;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblk * ncols) return;
@@ -98,8 +98,8 @@ int launch_quantize_act(b200_ctx *ctx, int q8k, const float *x, size_t x_col_str
     const int64_t warps = (q8k ? K / 256 : (K + 255) / 256) * ncols;
     if (warps == 0) return B200_OK;
     const unsigned grid = (unsigned)((warps + 3) / 4);
-    if (q8k) quantize_q8k_kernel<<<grid, 128, 0, ctx->stream>>>(x, x_col_stride, K, ncols, scratch, L);
-    else     quantize_q80_kernel<<<grid, 128, 0, ctx->stream>>>(x, x_col_stride, K, ncols, scratch, L);
+    if (q8k) b200_quantize_q8k_kernel<<<grid, 128, 0, ctx->stream>>>(x, x_col_stride, K, ncols, scratch, L);
+    else     b200_quantize_q80_kernel<<<grid, 128, 0, ctx->stream>>>(x, x_col_stride, K, ncols, scratch, L);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
@@ -117,8 +117,8 @@ extern "C" int b200_quantize_act(b200_ctx *ctx, int32_t act_type, const float *x
     int rc = launch_quantize_act(ctx, q8k, x, (size_t)K * 4, K, rows, s);
     if (rc) return rc;
     const int64_t n = (K / (q8k ? 256 : 32)) * rows;
-    if (q8k) repack_q8k_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(s, L, rows, (uint8_t *)blocks);
-    else     repack_q80_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(s, L, rows, (uint8_t *)blocks);
+    if (q8k) b200_repack_q8k_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(s, L, rows, (uint8_t *)blocks);
+    else     b200_repack_q80_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(s, L, rows, (uint8_t *)blocks);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;

@@ -106,7 +106,7 @@ def test_flash_attn_vs_oracle(b200, ctx, tk, D, H, Hkv, n_q, n_kv):
     want = R.orc_flash_attn(q, kb, vb, mask, D, n_kv, Hkv, tk, tk, scale)
     assert np.isfinite(got).all()
     # (1) the reference's own bar against the CPU semantics (fp16 V accumulator for f16 V): NMSE <= 5e-4
-    assert nmse(got, want) <= (5e-4 if tk == R.F16 else 1e-11), nmse(got, want)
+    assert nmse(got, want) <= (5e-4 if tk == R.F16 else 1e-10), nmse(got, want)
     # (2) against the exact answer we must be at least as accurate as the CPU path, and tight in absolute terms
     exact = exact_attention(q, kb, vb, mask, D, n_kv, Hkv, tk, scale)
     assert nmse(got, exact) <= 1e-10, nmse(got, exact)          # f32-accurate: rel L2 <= ~3e-6

@@ -151,3 +151,29 @@ def test_batched_columns_prequantised_path(b200, ctx, t):
     got = gpu_mul_mat(b200, ctx, t, W, x, N, K)
     want = R.orc_mul_mat(t, W, x, N, K)
     assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("t", [R.Q4_K, R.Q6_K, R.Q8_0])
+@pytest.mark.parametrize("b_ne1", [1, 2])
+def test_mul_mat_id_device_side_routing(b200, ctx, t, b_ne1):
+    """MoE: experts chosen on the device from `ids` (a strided view of the argsort output, as build_moe_ffn makes it)"""
+    rng = np.random.default_rng(11 + t + b_ne1)
+    n_expert, n_used, n_tok, N, K = 8, 2, 3, 160, 1024
+    As = rand_quant_rows(t, n_expert * N, K, rng)
+    b = rng.standard_normal((n_tok, b_ne1, K)).astype(np.float32)
+    sel = np.stack([rng.permutation(n_expert) for _ in range(n_tok)]).astype(np.int32)      # [n_tok, n_expert] "argsort" rows
+    ids = np.ascontiguousarray(sel[:, :n_used])
+    rb = R.row_size(t, K)
+    Ad = dev_bytes(As.size + 256, 0)
+    Ad[:As.size] = to_dev(As)
+    bd, seld = to_dev(b), to_dev(sel)
+    out = dev_bytes(n_tok * n_used * N * 4, 0xFF)
+    op = b200.make_op(b200.OP_MUL_MAT_ID, b200.tensor(out.data_ptr(), b200.F32, [N, n_used, n_tok]),
+                      [b200.tensor(Ad.data_ptr(), t, [K, N, n_expert], flags=1), b200.tensor(bd.data_ptr(), b200.F32, [K, b_ne1, n_tok]),
+                       b200.tensor(seld.data_ptr(), b200.I32, [n_used, n_tok], [4, n_expert * 4, n_expert * 4 * n_tok, n_expert * 4 * n_tok])])
+    assert b200.supports(op)
+    ctx.compute_op(op)
+    ctx.sync()
+    got = out.cpu().numpy().view(np.float32).reshape(n_tok, n_used, N)
+    want = R.orc_mul_mat_id(t, As, b, ids, N, K, n_expert)
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
