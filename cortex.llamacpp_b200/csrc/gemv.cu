@@ -66,15 +66,17 @@ struct GemvParams {
     unsigned long long *prof;         // optional [grid][16] globaltimer stamps (tools/gemv_prof.py)
 };
 
-// first global row (over the concatenated segments) of CTA c: ranges are balanced by BYTES, cut at row boundaries
-__device__ __forceinline__ int split_row(const GemvParams &p, unsigned long long total_bytes, int total_rows, int c, int G) {
+// first global row (over the concatenated segments) of CTA c: ranges are balanced by BYTES, cut at row boundaries.
+// 32-bit arithmetic in units of 16 bytes (64-bit divisions cost ~0.3 us each at kernel start); total < 64 GB.
+__device__ __forceinline__ int split_row(const GemvParams &p, uint32_t share16, int total_rows, int c, int G) {
     if (c >= G) return total_rows;
-    unsigned long long target = total_bytes * (unsigned long long)c / (unsigned long long)G;
+    uint32_t target = share16 * (uint32_t)c;          // <= total bytes / 16
     int before = 0;
     for (int s = 0; s < p.nseg; s++) {
-        const unsigned long long sb = (unsigned long long)p.seg[s].N * p.seg[s].rb;
+        const uint32_t rb16 = p.seg[s].rb >> 4 ? p.seg[s].rb >> 4 : 1;     // row bytes in 16-byte units (>= 1; exact for K-quants)
+        const uint32_t sb = (uint32_t)p.seg[s].N * rb16;
         if (target < sb || s == p.nseg - 1) {
-            const int r = (int)(target / p.seg[s].rb);
+            const int r = (int)(target / rb16);
             return before + (r < p.seg[s].N ? r : p.seg[s].N);
         }
         target -= sb;
@@ -220,12 +222,18 @@ __device__ __forceinline__ void consume_rpw(const GemvParams &p, const GemvSeg &
     consume_chunk<TYPE, NC, 1, DBG>(p, sg, rowp, row, nr, A, lane, empty_bar);
 }
 
-template <int NC, bool DBG>
-__global__ void __launch_bounds__(288, 2) b200_gemv_kernel(const GemvParams p) {
+// TYPES: bit mask of the segment types this instantiation can meet (bit 0 Q4_K, 1 Q5_K, 2 Q6_K, 3 Q4_0, 4 Q8_0); single-type
+// launches compile to straight-line code, mixed launches (wq|wk|wv of a K_M file) dispatch per ring stage.
+constexpr int TM_Q4_K = 1, TM_Q5_K = 2, TM_Q6_K = 4, TM_Q4_0 = 8, TM_Q8_0 = 16;
+constexpr int GEMV_THREADS = 640;
+static_assert(GEMV_THREADS / 32 - 1 <= 32, "s_red holds one double per consumer warp");        // 19 consumer warps + 1 producer warp, one CTA per SM, <= 96 registers per thread
+
+template <int TYPES, int NC, bool DBG>
+__global__ void __launch_bounds__(GEMV_THREADS, 1) b200_gemv_kernel(const GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full  = (uint64_t *)smem;
     uint64_t *empty = full + MAX_STAGES;
-    float *   s_red = (float *)(empty + MAX_STAGES);       // 32 floats: rms_norm reduction
+    double *  s_red = (double *)(empty + MAX_STAGES);      // 32 doubles: rms_norm reduction, one per consumer warp
     volatile int *s_seq = (volatile int *)(s_red + 32);    // chunk index currently held by each stage
     float *   s_ad  = (float *)(smem + p.off_ad);
     int16_t * s_as  = (int16_t *)(smem + p.off_as);
@@ -241,10 +249,11 @@ __global__ void __launch_bounds__(288, 2) b200_gemv_kernel(const GemvParams p) {
     //      loops need the registers) ------------------------------------------------------------------------------
     volatile int *s_lo = s_seq + MAX_STAGES, *s_hi = s_lo + GEMV_MAX_SEG, *s_ch0 = s_hi + GEMV_MAX_SEG;   // [3], [3], [4]
     if (threadIdx.x == 0) {
-        unsigned long long total_bytes = 0;
+        uint32_t total16 = 0;
         int total_rows = 0;
-        for (int s = 0; s < p.nseg; s++) { total_bytes += (unsigned long long)p.seg[s].N * p.seg[s].rb; total_rows += p.seg[s].N; }
-        const int g0 = split_row(p, total_bytes, total_rows, c, G), g1 = split_row(p, total_bytes, total_rows, c + 1, G);
+        for (int s = 0; s < p.nseg; s++) { total16 += (uint32_t)p.seg[s].N * (p.seg[s].rb >> 4 ? p.seg[s].rb >> 4 : 1); total_rows += p.seg[s].N; }
+        const uint32_t share16 = (total16 + (uint32_t)G - 1) / (uint32_t)G;
+        const int g0 = split_row(p, share16, total_rows, c, G), g1 = split_row(p, share16, total_rows, c + 1, G);
         int base = 0, chunks = 0;
         for (int s = 0; s < GEMV_MAX_SEG; s++) {
             int a = 0, b = 0;
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(288, 2) b200_gemv_kernel(const GemvParams p) {
     mbar_fence_init();
     __syncthreads();
     const int nchunks = s_ch0[GEMV_MAX_SEG];
+    if (warp == 0) PROF(1);
     // Programmatic dependent launch: let the next kernel of the stream become resident right away (its producer streams
     // its constant weights, everything else blocks in griddepcontrol.wait until this grid has completed and flushed).
     if (p.use_pdl) pdl_trigger();
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(288, 2) b200_gemv_kernel(const GemvParams p) {
                 double s = 0.0;
                 for (int i = threadIdx.x; i < p.K; i += nct) { const float v = xp[i]; s += (double)__fmul_rn(v, v); }
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                double *sd = (double *)s_red;
+                double *sd = s_red;
                 named_bar_sync(1, nct);
                 if (lane == 0) sd[warp] = s;
                 named_bar_sync(1, nct);
@@ -376,13 +386,12 @@ __global__ void __launch_bounds__(288, 2) b200_gemv_kernel(const GemvParams p) {
         const uint8_t *Wb = sg.expert_id ? sg.W + (size_t)(*sg.expert_id) * sg.expert_stride : sg.W;
         const uint32_t extra = (uint32_t)((uintptr_t)(Wb + (size_t)row * sg.rb) & 15);
         const uint8_t *rowp = ring + (size_t)st * p.stage_bytes + extra;
-        switch (sg.type) {
-            case T_Q4_K: consume_rpw<T_Q4_K, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]); break;
-            case T_Q5_K: consume_rpw<T_Q5_K, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]); break;
-            case T_Q6_K: consume_rpw<T_Q6_K, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]); break;
-            case T_Q4_0: consume_rpw<T_Q4_0, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]); break;
-            default:     consume_rpw<T_Q8_0, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]); break;
-        }
+        const int ty = sg.type;
+        if ((TYPES & TM_Q4_K) && (TYPES == TM_Q4_K || ty == T_Q4_K)) consume_rpw<T_Q4_K, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]);
+        else if ((TYPES & TM_Q5_K) && (TYPES == TM_Q5_K || ty == T_Q5_K)) consume_rpw<T_Q5_K, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]);
+        else if ((TYPES & TM_Q6_K) && (TYPES == TM_Q6_K || ty == T_Q6_K)) consume_rpw<T_Q6_K, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]);
+        else if ((TYPES & TM_Q4_0) && (TYPES == TM_Q4_0 || ty == T_Q4_0)) consume_rpw<T_Q4_0, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]);
+        else if (TYPES & TM_Q8_0) consume_rpw<T_Q8_0, NC, DBG>(p, sg, rowp, row, nr, smem, s_ad, s_as, lane, &empty[st]);
         if (i == 0) PROF(7);
         if (i + ncw >= nchunks && warp == (nchunks - 1) % ncw) PROF(8);
     }
@@ -394,12 +403,12 @@ bool item64(int type) { return type == B200_TYPE_Q4_K || type == B200_TYPE_Q5_K;
 int g_gemv_warps = 0, g_gemv_stage_kb = 0, g_gemv_smem_kb = 0, g_gemv_ctas = 0, g_gemv_l2pf = -1;     // tuning overrides (env GGML_B200_GEMV_*)
 
 // rows per stage for a given column count: keep a stage around 8-12 KB so the ring holds >= 16 stages
-int choose_rpw(uint32_t rb, int ncols, int64_t rows_per_cta) {
+int choose_rpw(uint32_t rb, int ncols, int64_t rows_per_cta, int nwarps) {
     const uint32_t target = (uint32_t)(g_gemv_stage_kb > 0 ? g_gemv_stage_kb : 10) * 1024;
     const int maxr = ncols == 1 ? 4 : (ncols == 2 ? 2 : 1);
     int r = maxr;
     // small stages when a CTA owns few rows (every consumer warp should get >= 2 chunks), bounded stage bytes otherwise
-    while (r > 1 && ((size_t)r * rb > target || rows_per_cta / r < 16)) r >>= 1;
+    while (r > 1 && ((size_t)r * rb > target || rows_per_cta / r < 2 * nwarps)) r >>= 1;
     return r;
 }
 
@@ -417,7 +426,7 @@ bool plan(const b200_ctx *ctx, int64_t K, int ncols, GemvParams &p, size_t &smem
     p.aq128_col = (uint32_t)(((K + 127) / 128) * 144);
     p.ad_col = (uint32_t)(((K / (q8k ? 256 : 32)) + 4 + 3) & ~3);
     p.as_col = (uint32_t)(((K / (q8k ? 16 : 32)) + 8 + 7) & ~7);
-    uint32_t off = 2 * MAX_STAGES * 8 + 128 + MAX_STAGES * 4 + 64;      // barriers, s_red, s_seq, s_lo/s_hi/s_ch0
+    uint32_t off = 2 * MAX_STAGES * 8 + 256 + MAX_STAGES * 4 + 64;      // barriers, s_red, s_seq, s_lo/s_hi/s_ch0
     off = (off + 15) & ~15u;
     p.off_aq64 = 0; p.off_aq128 = 0;
     if (need64)  { p.off_aq64 = off;  off += p.aq64_col * ncols;  off = (off + 15) & ~15u; }
@@ -427,9 +436,8 @@ bool plan(const b200_ctx *ctx, int64_t K, int ncols, GemvParams &p, size_t &smem
     p.off_as = off;   off += p.as_col * 2 * ncols;
     off = (off + 127) & ~127u;
     p.off_ring = off;
-    size_t budget = ctx->smem_optin;
-    const size_t half = (size_t)(g_gemv_smem_kb > 0 ? g_gemv_smem_kb : 112) * 1024;
-    if ((size_t)off + 24 * 1024 <= half) budget = half;
+    size_t budget = g_gemv_smem_kb > 0 ? (size_t)g_gemv_smem_kb * 1024 : ctx->smem_optin;
+    if (budget > ctx->smem_optin) budget = ctx->smem_optin;
     if ((size_t)off + 1024 > budget) return false;
     const size_t ring_budget = budget - off;
     int ns = (int)(ring_budget / max_stage);
@@ -440,9 +448,9 @@ bool plan(const b200_ctx *ctx, int64_t K, int ncols, GemvParams &p, size_t &smem
     return true;
 }
 
-template <int NC, bool DBG>
+template <int TYPES, int NC, bool DBG>
 int launch_t(b200_ctx *ctx, const GemvParams &p, int grid, int nwarps, size_t smem_bytes) {
-    auto kern = b200_gemv_kernel<NC, DBG>;
+    auto kern = b200_gemv_kernel<TYPES, NC, DBG>;
     static bool attr_set[16] = {false};   // per device
     if (!attr_set[ctx->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -467,16 +475,45 @@ int launch_t(b200_ctx *ctx, const GemvParams &p, int grid, int nwarps, size_t sm
     return B200_OK;
 }
 
+template <int TYPES>
 int launch_cols(b200_ctx *ctx, const GemvParams &p, int ncols, bool dbg, int grid, int nwarps, size_t smem) {
-    if (dbg) return ncols == 1 ? launch_t<1, true>(ctx, p, grid, nwarps, smem) : B200_ERR_UNSUPPORTED;
+    if (dbg) {
+        if constexpr (TYPES == TM_Q4_K || TYPES == TM_Q5_K || TYPES == TM_Q6_K || TYPES == TM_Q4_0 || TYPES == TM_Q8_0)
+            if (ncols == 1) return launch_t<TYPES, 1, true>(ctx, p, grid, nwarps, smem);
+        return B200_ERR_UNSUPPORTED;
+    }
     switch (ncols) {
-        case 1: return launch_t<1, false>(ctx, p, grid, nwarps, smem);
-        case 2: return launch_t<2, false>(ctx, p, grid, nwarps, smem);
-        case 3: return launch_t<3, false>(ctx, p, grid, nwarps, smem);
-        case 4: return launch_t<4, false>(ctx, p, grid, nwarps, smem);
+        case 1: return launch_t<TYPES, 1, false>(ctx, p, grid, nwarps, smem);
+        case 2: return launch_t<TYPES, 2, false>(ctx, p, grid, nwarps, smem);
+        case 3: return launch_t<TYPES, 3, false>(ctx, p, grid, nwarps, smem);
+        case 4: return launch_t<TYPES, 4, false>(ctx, p, grid, nwarps, smem);
     }
     b200_set_error("gemv: ncols=%d", ncols);
     return B200_ERR_UNSUPPORTED;
+}
+
+int type_bit(int type) {
+    switch (type) {
+        case B200_TYPE_Q4_K: return TM_Q4_K; case B200_TYPE_Q5_K: return TM_Q5_K; case B200_TYPE_Q6_K: return TM_Q6_K;
+        case B200_TYPE_Q4_0: return TM_Q4_0; default: return TM_Q8_0;
+    }
+}
+
+int launch_mask(b200_ctx *ctx, const GemvParams &p, int ncols, bool dbg, int grid, int nwarps, size_t smem) {
+    int mask = 0;
+    for (int s = 0; s < p.nseg; s++) mask |= type_bit(p.seg[s].type);
+    switch (mask) {
+        case TM_Q4_K: return launch_cols<TM_Q4_K>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        case TM_Q5_K: return launch_cols<TM_Q5_K>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        case TM_Q6_K: return launch_cols<TM_Q6_K>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        case TM_Q4_0: return launch_cols<TM_Q4_0>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        case TM_Q8_0: return launch_cols<TM_Q8_0>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        case TM_Q4_K | TM_Q6_K: return launch_cols<TM_Q4_K | TM_Q6_K>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        case TM_Q4_0 | TM_Q8_0: return launch_cols<TM_Q4_0 | TM_Q8_0>(ctx, p, ncols, dbg, grid, nwarps, smem);
+        default:
+            if (mask & (TM_Q4_0 | TM_Q8_0)) { b200_set_error("gemv: type mix %d", mask); return B200_ERR_UNSUPPORTED; }
+            return launch_cols<TM_Q4_K | TM_Q5_K | TM_Q6_K>(ctx, p, ncols, dbg, grid, nwarps, smem);
+    }
 }
 
 void read_env() {
@@ -517,10 +554,10 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
     }
     if (total_rows <= 0) return B200_OK;
     const ActLayout L = ActLayout::make(q8k, K);
-    const int nwarps = g_gemv_warps > 0 ? (g_gemv_warps > 8 ? 8 : g_gemv_warps) : 8;
-    // one CTA per SM with <= half the shared memory, so that under PDL the NEXT matmul's CTAs co-reside and stream
-    // their weights while this one computes; very tall matrices (output projection) take both slots themselves
-    const int ctas_per_sm = g_gemv_ctas > 0 ? g_gemv_ctas : (total_rows >= 32768 ? 2 : 1);
+    constexpr int MAXW = GEMV_THREADS / 32 - 1;
+    const int nwarps = g_gemv_warps > 0 ? (g_gemv_warps > MAXW ? MAXW : g_gemv_warps) : MAXW;
+    // one persistent CTA per SM: 19 consumer warps hide the shared-memory / dp4a latency of the block decoders
+    const int ctas_per_sm = 1;
     const bool dbg = segs[0].dbgP != nullptr;
     GemvParams p = {};
     size_t smem = 0;
@@ -534,7 +571,7 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
             for (int s = 0; s < nseg; s++) {
                 GemvSeg &g = p.seg[s];
                 g.W = segs[s].W; g.rb = (uint32_t)segs[s].rb; g.type = segs[s].type; g.N = (int)segs[s].N;
-                g.rpw = choose_rpw(g.rb, nc, total_rows / ((int64_t)ctx->sm_count * ctas_per_sm));
+                g.rpw = choose_rpw(g.rb, nc, total_rows / ((int64_t)ctx->sm_count * ctas_per_sm), nwarps);
                 g.dst = segs[s].dst + (size_t)c0 * segs[s].dst_stride; g.dst_stride = segs[s].dst_stride;
                 g.residual = segs[s].residual ? segs[s].residual + (size_t)c0 * segs[s].dst_stride : nullptr;
                 g.expert_id = segs[s].expert_id; g.expert_stride = segs[s].expert_stride;
@@ -542,8 +579,7 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
             }
             if (plan(ctx, K, nc, p, smem)) break;
         }
-        int cps = ctas_per_sm;
-        if (smem > 114 * 1024) cps = 1;
+        const int cps = ctas_per_sm;
         p.K = (int)K;
         p.act_mode = ga.mode;
         p.act = ga.act ? ga.act + (size_t)c0 * L.col_bytes : nullptr;
@@ -567,7 +603,7 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
         for (int s = 0; s < nseg; s++) min_chunks += (segs[s].N + p.seg[s].rpw - 1) / p.seg[s].rpw;
         const int64_t maxg = (int64_t)ctx->sm_count * cps;
         const int grid = (int)(min_chunks < maxg ? min_chunks : maxg);
-        int rc = launch_cols(ctx, p, nc, dbg, grid, nwarps, smem);
+        int rc = launch_mask(ctx, p, nc, dbg, grid, nwarps, smem);
         if (rc) return rc;
         c0 += nc;
     }

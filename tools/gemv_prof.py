@@ -30,4 +30,6 @@ t0 = p[:, 0][p[:, 0] > 0].min()
 names = ["cta start", "after init+sync", "first copy issued", "all copies issued", "prologue done", "after prologue bar", "first stage landed", "first chunk done", "last chunk done"]
 for i, n in enumerate(names):
     v = p[:, i][p[:, i] > 0] - t0
+    if len(v) == 0:
+        continue
     print("%-22s min %6d  median %6d  max %6d ns  (n=%d)" % (n, v.min(), np.median(v), v.max(), len(v)))

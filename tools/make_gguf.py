@@ -25,6 +25,7 @@ MODELS = {
     "tiny-d64":    (2,  256,  4,  2,  64,  512,   512,    10000.0,   0, 0),
     "tiny-d128":   (2,  512,  4,  2,  128, 1024,  512,    10000.0,   0, 0),
     "tiny-moe":    (2,  512,  4,  2,  128, 512,   512,    10000.0,   4, 2),
+    "mid-d128":    (2,  2048, 16, 4,  128, 5632,  4096,   10000.0,   0, 0),
     "tinyllama":   (22, 2048, 32, 4,  64,  5632,  32000,  10000.0,   0, 0),
     "llama2-7b":   (32, 4096, 32, 32, 128, 11008, 32000,  10000.0,   0, 0),
     "llama3-8b":   (32, 4096, 32, 8,  128, 14336, 128256, 500000.0,  0, 0),
