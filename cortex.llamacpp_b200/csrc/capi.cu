@@ -33,6 +33,7 @@ void *b200_ctx::get_scratch(int slot, size_t size) {
 
 struct b200_event { int device; cudaEvent_t ev; };
 void graph_cache_free(b200_ctx *ctx);   // graph.cu
+extern int g_gemm_desc_swap;            // gemm_i8.cu
 
 extern "C" {
 
@@ -116,6 +117,7 @@ int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     else if (k == "fusion") ctx->opt_fusion = value;
     else if (k == "pdl") ctx->opt_pdl = value;
     else if (k == "l2_prefetch") ctx->opt_l2_prefetch = value;
+    else if (k == "gemm_desc_swap") g_gemm_desc_swap = value;
     else { b200_set_error("unknown option %s", key); return B200_ERR_UNSUPPORTED; }
     return B200_OK;
 }

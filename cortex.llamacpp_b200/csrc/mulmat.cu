@@ -11,6 +11,7 @@
 // loops experts there).
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include "gemm_i8.h"
 
 int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);
 int launch_gemv_f32(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const float *x, size_t x_stride_bytes,
@@ -18,8 +19,6 @@ int launch_gemv_f32(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes,
                     const float *residual);
 int launch_gemv_expert(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, size_t expert_stride, const int32_t *expert_id, int64_t N,
                        int64_t K, const float *x, float *dst);
-int launch_gemm_i8(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
-                   int64_t ncols, float *dst, size_t dst_col_stride, bool *handled);
 
 namespace {
 
@@ -75,12 +74,6 @@ int mul_mat_float(b200_ctx *ctx, const b200_tensor &w, const b200_tensor &x, con
 // one quantised matmul: W [N rows of K] x cols (already quantised into `act`) -> dst
 int mul_mat_q_cols(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int64_t ncols,
                    float *dst, size_t dst_stride, bool w_const) {
-    if (ncols > 8) {
-        bool handled = false;
-        int rc = launch_gemm_i8(ctx, type, W, rb, N, K, act, ncols, dst, dst_stride, &handled);
-        if (rc) return rc;
-        if (handled) return B200_OK;
-    }
     const size_t col_bytes = ActLayout::make(b200_act_mode_q8k(type), K).col_bytes;
     // GEMV path; launch_gemv chunks columns by what fits in shared memory
     for (int64_t c0 = 0; c0 < ncols; c0 += 64) {
@@ -134,6 +127,19 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
                 const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
                 float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
                 int rc = launch_gemv_f32(ctx, w.type, wp, rb, N, K, xp, x.nb[1], (int)M, dp, d.nb[1] / 4, w_const, 0, nullptr, 0.0f, nullptr);
+                if (rc) return rc;
+            }
+        return B200_OK;
+    }
+    // prefill: K-quant weights go to the tensor cores (tcgen05 int8 GEMM with the CPU's exact q8_K integer stage)
+    if (gemm_i8_supported(w.type, N, K, M) && x.nb[0] == 4) {
+        for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+                const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+                const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+                const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+                float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+                int rc = gemm_i8_run(ctx, w.type, wp, rb, N, K, xp, x.nb[1], M, dp, d.nb[1] / 4);
                 if (rc) return rc;
             }
         return B200_OK;
