@@ -553,6 +553,12 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
         total_rows += segs[s].N;
     }
     if (total_rows <= 0) return B200_OK;
+    if (ncols == 1) {
+        // batch-1 decode over K-quants: the compact half-SM kernel (gemv_bs1.cu); anything it does not take falls through
+        const int l2pf = g_gemv_l2pf >= 0 ? g_gemv_l2pf : ctx->opt_l2_prefetch;
+        const int rc = gemv_bs1_try_launch(ctx, segs, nseg, K, ga, w_const, pf_ptr, pf_bytes, l2pf);
+        if (rc != 0) return rc < 0 ? rc : B200_OK;
+    }
     const ActLayout L = ActLayout::make(q8k, K);
     constexpr int MAXW = GEMV_THREADS / 32 - 1;
     const int nwarps = g_gemv_warps > 0 ? (g_gemv_warps > MAXW ? MAXW : g_gemv_warps) : MAXW;

@@ -1,0 +1,492 @@
+// gemv_bs1.cu -- the batch-1 decode GEMV for K-quant weights (Q4_K / Q5_K / Q6_K): the kernel a decoded token spends
+// most of its time in.  Same contract as gemv.cu (it is dispatched from gemv_launch for ncols == 1), different shape:
+//
+//   * gemv.cu's general kernel is ~100 KB of SASS (1-4 columns x 1/2/4 rows per stage x five formats) and owns a whole
+//     SM (227 KB ring, 96 registers x 640 threads).  At batch 1 a CTA of a Llama-3-8B matmul only sees 64-450 KB of
+//     weights, so a launch lives for a few microseconds and its cost is start-up, instruction fetch and tail, not
+//     streaming (ncu: stall_no_instruction was the top stall, profiles/r1_gemv_v5_diag.txt).  This kernel is built
+//     for that regime:
+//   * HALF an SM per CTA (<= 113 KB shared memory, 512 threads, <= 64 registers): under programmatic dependent launch
+//     the NEXT matmul's CTA becomes resident next to the current one and streams its (constant) weights into its own
+//     ring while the current one is still computing -- HBM keeps streaming across the kernel boundary;
+//   * tiny code: one row at a time, one item-loop per format, nothing unrolled over rows or columns;
+//   * lean block decoders: Q4_K needs ~80 instructions per 64 weights (packed 6-bit scale unpack with PRMT, high
+//     nibbles multiplied in place (x16, exact) instead of shifted, mins through dp2a on per-32 activation sums);
+//     Q6_K walks its 2-byte aligned blocks with aligned 32-bit loads + a run-time PRMT selector (no divergent paths);
+//   * the producer warp never blocks: every lane owns one ring stage and polls its `empty` barrier, so stages are
+//     re-armed as soon as they are released (no round-synchronous bursts); consumer warp w owns stages w, w+ncw, ...
+//     for the whole launch, so the 1-bit mbarrier phase can never alias;
+//   * rows are split evenly per segment (CTA c takes rows [N*c/G, N*(c+1)/G) of every segment): no search, no
+//     thread-0 prologue, and the producer issues its first copies before the CTA-wide barrier.
+// Integer arithmetic is the CPU oracle's (ggml_vec_dot_q{4,5,6}_K_q8_K) bit for bit; activations are quantised in the
+// prologue exactly like quantize_row_q8_K_ref (quant_warp.cuh).
+// Algorithmic bytes per launch: sum N*K*bpw (weights) + 4K (f32 activations, x2 for swiglu) + 4N (output).
+#include "common.cuh"
+#include "quant_warp.cuh"
+#include "gemv.h"
+
+namespace {
+
+constexpr int BS1_MAX_STAGES = 32;      // one producer lane per stage
+constexpr int BS1_THREADS    = 512;     // 15 consumer warps + 1 producer warp
+constexpr int BS1_NCW        = BS1_THREADS / 32 - 1;
+
+struct Bs1Seg {
+    const uint8_t *W;
+    float *        dst;
+    const float *  residual;
+    const int32_t *expert_id;
+    size_t         expert_stride;
+    uint32_t       rb;                  // bytes per row
+    int            type, N, R;          // rows per ring stage
+};
+
+struct Bs1Params {
+    Bs1Seg         seg[GEMV_MAX_SEG];
+    int            nseg, K, act_mode;
+    const float *  x, *x2;
+    float          eps;
+    int            nstages;
+    uint32_t       stage_bytes;
+    int            w_const, use_pdl;
+    uint32_t       off_aq64, off_aq128, off_ad, off_s32, off_s16, off_ring;   // 0 = layout not needed (aq*, s*)
+    const uint8_t *pf_ptr;
+    unsigned long long pf_bytes;
+};
+
+constexpr int TB_Q4_K = 1, TB_Q5_K = 2, TB_Q6_K = 4;
+
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {      // non-blocking poll
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a16x2, uint32_t b8, int c) {   // a.lo16*b.byte0 + a.hi16*b.byte1 (signed x unsigned)
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8), "r"(c));
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------- Q4_K / Q5_K
+// item = 64 weights (one 32-byte qs group g of a 144/176-byte block): low nibbles -> sub-block 2g, high -> 2g+1
+template <bool Q5>
+__device__ __forceinline__ float item_q45k(const uint8_t *row, int it, const uint8_t *aq, const uint32_t *s32, const float *ad) {
+    constexpr int BYTES = Q5 ? 176 : 144;
+    const uint8_t *b = row + (it >> 2) * BYTES;
+    const int g = it & 3;
+    const uint4 hdr = *(const uint4 *)b;
+    const uint8_t *qp = b + (Q5 ? 48 : 16) + g * 32;
+    const uint4 qa = *(const uint4 *)qp, qb = *(const uint4 *)(qp + 16);
+    const uint8_t *ap = aq + it * 80;
+    // all eight 6-bit (scale, min) pairs as packed bytes (get_scale_min_k4, ggml-quants.c:631), then bytes 2g, 2g+1
+    const uint32_t sc_lo = hdr.y & 0x3f3f3f3fu, mn_lo = hdr.z & 0x3f3f3f3fu;
+    const uint32_t sc_hi = (hdr.w & 0x0f0f0f0fu) | ((hdr.y >> 2) & 0x30303030u);
+    const uint32_t mn_hi = ((hdr.w >> 4) & 0x0f0f0f0fu) | ((hdr.z >> 2) & 0x30303030u);
+    const uint32_t sel = 0x7710u + 0x22u * (uint32_t)g;            // result bytes: [2g], [2g+1], x, x
+    const uint32_t scp = __byte_perm(sc_lo, sc_hi, sel), mnp = __byte_perm(mn_lo, mn_hi, sel);
+    int sA, sB;
+    if (!Q5) {
+        const uint4 a0 = *(const uint4 *)ap, a1 = *(const uint4 *)(ap + 16);
+        int s0 = __dp4a((int)(qa.x & 0x0f0f0f0fu), (int)a0.x, 0), s1 = __dp4a((int)(qa.y & 0x0f0f0f0fu), (int)a0.y, 0);
+        s0 = __dp4a((int)(qa.z & 0x0f0f0f0fu), (int)a0.z, s0); s1 = __dp4a((int)(qa.w & 0x0f0f0f0fu), (int)a0.w, s1);
+        s0 = __dp4a((int)(qb.x & 0x0f0f0f0fu), (int)a1.x, s0); s1 = __dp4a((int)(qb.y & 0x0f0f0f0fu), (int)a1.y, s1);
+        s0 = __dp4a((int)(qb.z & 0x0f0f0f0fu), (int)a1.z, s0); s1 = __dp4a((int)(qb.w & 0x0f0f0f0fu), (int)a1.w, s1);
+        sA = s0 + s1;
+        const uint4 a2 = *(const uint4 *)(ap + 32), a3 = *(const uint4 *)(ap + 48);
+        // high nibbles stay in place: sum (16 q) a = 16 sum q a, exact in int32 (|sum| < 2^20)
+        int t0 = dp4a_us(qa.x & 0xf0f0f0f0u, a2.x, 0), t1 = dp4a_us(qa.y & 0xf0f0f0f0u, a2.y, 0);
+        t0 = dp4a_us(qa.z & 0xf0f0f0f0u, a2.z, t0); t1 = dp4a_us(qa.w & 0xf0f0f0f0u, a2.w, t1);
+        t0 = dp4a_us(qb.x & 0xf0f0f0f0u, a3.x, t0); t1 = dp4a_us(qb.y & 0xf0f0f0f0u, a3.y, t1);
+        t0 = dp4a_us(qb.z & 0xf0f0f0f0u, a3.z, t0); t1 = dp4a_us(qb.w & 0xf0f0f0f0u, a3.w, t1);
+        sB = (t0 + t1) >> 4;
+    } else {
+        const uint4 ha = *(const uint4 *)(b + 16), hb = *(const uint4 *)(b + 32);
+        const uint4 a0 = *(const uint4 *)ap, a1 = *(const uint4 *)(ap + 16), a2 = *(const uint4 *)(ap + 32), a3 = *(const uint4 *)(ap + 48);
+        const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        const uint32_t hw[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        const uint32_t al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const uint32_t ah[8] = {a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+        int s0 = 0, s1 = 0, t0 = 0, t1 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t hsh = hw[i] >> (2 * g);
+            const uint32_t lo = (qw[i] & 0x0f0f0f0fu) | ((hsh << 4) & 0x10101010u);
+            const uint32_t hi = ((qw[i] >> 4) & 0x0f0f0f0fu) | ((hsh << 3) & 0x10101010u);
+            if (i & 1) { s1 = __dp4a((int)lo, (int)al[i], s1); t1 = __dp4a((int)hi, (int)ah[i], t1); }
+            else       { s0 = __dp4a((int)lo, (int)al[i], s0); t0 = __dp4a((int)hi, (int)ah[i], t0); }
+        }
+        sA = s0 + s1; sB = t0 + t1;
+    }
+    const int P = (int)(scp & 0xffu) * sA + (int)((scp >> 8) & 0xffu) * sB;
+    const int M = dp2a_lo_su(s32[it], mnp, 0);
+    const float da = ad[it >> 2];
+    const float d = half_bits_to_float(hdr.x), dmin = half_bits_to_float(hdr.x >> 16);
+    return (d * da) * (float)P - (dmin * da) * (float)M;
+}
+
+// ---------------------------------------------------------------------------------------------- Q6_K
+// item = 128 weights (half h of a 210-byte block: ql 64 B at 64h, qh 32 B at 128+32h, int8 scales 8 B at 192+8h, half d at 208).
+// Blocks are only 2-byte aligned: every 4-byte word is fetched as two aligned words and a PRMT whose selector is computed
+// from the address, so both alignments run the same instructions.
+__device__ __forceinline__ void ld4_words(const uint32_t *W, int word, uint32_t sel, uint32_t (&out)[4]) {
+    const uint32_t r0 = W[word], r1 = W[word + 1], r2 = W[word + 2], r3 = W[word + 3], r4 = W[word + 4];
+    out[0] = __byte_perm(r0, r1, sel); out[1] = __byte_perm(r1, r2, sel); out[2] = __byte_perm(r2, r3, sel); out[3] = __byte_perm(r3, r4, sel);
+}
+__device__ __forceinline__ float item_q6k(const uint8_t *row, int it, const uint8_t *aq, const uint4 *s16, const float *ad) {
+    const uint8_t *b = row + (it >> 1) * 210;
+    const int h = it & 1;
+    const uint32_t mis = (uint32_t)(uintptr_t)b & 2u;
+    const uint32_t *W = (const uint32_t *)(b - mis);
+    const uint32_t sel = mis ? 0x5432u : 0x3210u;
+    const uint8_t *ap = aq + it * 144;
+    const uint4 bs = s16[it];
+    const uint32_t bsw[4] = {bs.x, bs.y, bs.z, bs.w};
+    uint32_t S[2];
+    {
+        const int w = 48 + 2 * h;
+        const uint32_t r0 = W[w], r1 = W[w + 1], r2 = W[w + 2];
+        S[0] = __byte_perm(r0, r1, sel); S[1] = __byte_perm(r1, r2, sel);
+    }
+    int P = 0;
+#pragma unroll
+    for (int hs = 0; hs < 2; hs++) {
+        uint32_t H[4];
+        ld4_words(W, 32 + 8 * h + 4 * hs, sel, H);
+#pragma unroll
+        for (int tl = 0; tl < 2; tl++) {
+            uint32_t L[4];
+            ld4_words(W, 16 * h + 8 * tl + 4 * hs, sel, L);
+#pragma unroll
+            for (int nib = 0; nib < 2; nib++) {
+                const int t = tl + 2 * nib, sg = 2 * t + hs;
+                const uint4 a = *(const uint4 *)(ap + 16 * sg);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t lo = nib ? (L[k] >> 4) : L[k];
+                    const uint32_t hi = t == 0 ? (H[k] << 4) : t == 1 ? (H[k] << 2) : t == 2 ? H[k] : (H[k] >> 2);
+                    s = __dp4a((int)((lo & 0x0f0f0f0fu) | (hi & 0x30303030u)), (int)aw[k], s);
+                }
+                // quants kept unsigned (0..63); the -32 offset goes through the activation bsums (exact)
+                const int bsum = (int)(int16_t)((sg & 1) ? (bsw[sg >> 1] >> 16) : (bsw[sg >> 1] & 0xffffu));
+                const int scale = (int)(int8_t)((S[sg >> 2] >> (8 * (sg & 3))) & 0xffu);
+                P += scale * (s - 32 * bsum);
+            }
+        }
+    }
+    const float d = half_bits_to_float(*(const uint16_t *)(b + 208));
+    return (d * ad[it >> 1]) * (float)P;
+}
+
+// ---------------------------------------------------------------------------------------------- prologue
+// f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref
+__device__ __forceinline__ void bs1_quantize(const Bs1Params &p, uint8_t *smem, int warp, int lane, float norm_scale) {
+    const int nchunk = p.K >> 8;
+    float *s_ad = (float *)(smem + p.off_ad);
+    int16_t *s_s32 = (int16_t *)(smem + p.off_s32), *s_s16 = (int16_t *)(smem + p.off_s16);
+    for (int b0 = warp; b0 < nchunk; b0 += 2 * BS1_NCW) {
+        float4 xa[2][2], xb[2][2];                       // two 256-element chunks in flight per warp
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = b0 + u * BS1_NCW;
+            if (b < nchunk) {
+                const int e0 = b * 256 + lane * 8;
+                xa[u][0] = *(const float4 *)(p.x + e0); xa[u][1] = *(const float4 *)(p.x + e0 + 4);
+                if (p.act_mode != ACT_F32) { xb[u][0] = *(const float4 *)(p.x2 + e0); xb[u][1] = *(const float4 *)(p.x2 + e0 + 4); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = b0 + u * BS1_NCW;
+            if (b >= nchunk) break;
+            const int e0 = b * 256 + lane * 8;
+            float v[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
+            if (p.act_mode != ACT_F32) {
+                const float w[8] = {xb[u][0].x, xb[u][0].y, xb[u][0].z, xb[u][0].w, xb[u][1].x, xb[u][1].y, xb[u][1].z, xb[u][1].w};
+                if (p.act_mode == ACT_F32_NORM) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fmul_rn(v[j], norm_scale), w[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fdiv_rn(v[j], 1.0f + expf(-v[j])), w[j]);
+                }
+            }
+            uint2 qp; float d; int pair;
+            warp_quant_q8k(v, lane, qp, d, pair);                // pair: 16-element sum, valid in even lanes
+            const int quad = pair + __shfl_xor_sync(0xffffffffu, pair, 2);
+            if (p.off_s16 && (lane & 1) == 0) s_s16[b * 16 + (lane >> 1)] = (int16_t)pair;
+            if (p.off_s32 && (lane & 3) == 0) s_s32[b * 8 + (lane >> 2)] = (int16_t)quad;
+            if (lane == 0) s_ad[b] = d;
+            if (p.off_aq64)  *(uint2 *)(smem + p.off_aq64 + (e0 >> 6) * 80 + (e0 & 63)) = qp;
+            if (p.off_aq128) *(uint2 *)(smem + p.off_aq128 + (e0 >> 7) * 144 + (e0 & 127)) = qp;
+        }
+    }
+}
+
+template <int TYPES>
+__global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full  = (uint64_t *)smem;                  // [32]
+    uint64_t *empty = full + BS1_MAX_STAGES;             // [32]
+    double *  s_red = (double *)(empty + BS1_MAX_STAGES);    // [16]
+    uint8_t * ring  = smem + p.off_ring;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int ns = p.nstages;
+    // programmatic dependent launch: the next kernel's CTAs may become resident right away (half an SM is left for them);
+    // everything of theirs that depends on our output blocks in griddepcontrol.wait until this grid has completed
+    if (p.use_pdl) pdl_trigger();
+
+    // ---- this CTA's rows: an even share of every segment; chunk = R rows of one segment ----
+    int lo[GEMV_MAX_SEG], hi[GEMV_MAX_SEG], ch0[GEMV_MAX_SEG + 1];
+    ch0[0] = 0;
+#pragma unroll
+    for (int s = 0; s < GEMV_MAX_SEG; s++) {
+        lo[s] = hi[s] = 0;
+        if (s < p.nseg) {
+            lo[s] = (int)(((unsigned)p.seg[s].N * (unsigned)c) / (unsigned)G);
+            hi[s] = (int)(((unsigned)p.seg[s].N * (unsigned)(c + 1)) / (unsigned)G);
+        }
+        ch0[s + 1] = ch0[s] + (s < p.nseg ? (hi[s] - lo[s] + p.seg[s].R - 1) / p.seg[s].R : 0);
+    }
+    const int nchunks = ch0[GEMV_MAX_SEG];
+
+    if (warp == BS1_NCW) {
+        // ------------------------------------------------------------------ producer: lane l owns ring stage l
+        if (lane < ns) { mbar_init(&full[lane], 1); mbar_init(&empty[lane], 1); }
+        mbar_fence_init();
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"r"(BS1_THREADS) : "memory");       // consumers learn about the barriers at the end of their prologue
+        bool any_expert = false;
+#pragma unroll
+        for (int s = 0; s < GEMV_MAX_SEG; s++) any_expert |= s < p.nseg && p.seg[s].expert_id != nullptr;
+        bool waited = false;
+        if (p.use_pdl && (!p.w_const || any_expert)) { pdl_wait(); waited = true; }
+        const uint64_t pol = l2_policy_evict_first();
+        int i = lane, use = 0;
+        bool first_pass = true;
+        while (__any_sync(0xffffffffu, lane < ns && i < nchunks)) {
+            if (lane < ns && i < nchunks && (use == 0 || mbar_test_wait(&empty[lane], (use - 1) & 1))) {
+                int s = 0, lo_s = lo[0], hi_s = hi[0], c0 = 0;
+#pragma unroll
+                for (int t = 1; t < GEMV_MAX_SEG; t++) if (t < p.nseg && i >= ch0[t]) { s = t; lo_s = lo[t]; hi_s = hi[t]; c0 = ch0[t]; }
+                const Bs1Seg &sg = p.seg[s];
+                const int row = lo_s + (i - c0) * sg.R;
+                const int nr = min(sg.R, hi_s - row);
+                const uint8_t *Wb = sg.expert_id ? sg.W + (size_t)(*sg.expert_id) * sg.expert_stride : sg.W;
+                const uint8_t *src = Wb + (size_t)row * sg.rb;
+                const uint32_t extra = (uint32_t)((uintptr_t)src & 15);
+                const uint32_t bytes = (extra + (uint32_t)nr * sg.rb + 15u) & ~15u;
+                mbar_arrive_expect_tx(&full[lane], bytes);
+                bulk_g2s_hint(ring + (size_t)lane * p.stage_bytes, src - extra, bytes, &full[lane], pol);
+                i += ns; use++;
+            }
+            if (first_pass) {
+                first_pass = false;
+                // the NEXT matmul's weights: ask the L2 to start fetching this CTA's 1/G of them now
+                if (p.pf_bytes) {
+                    const unsigned long long per = ((p.pf_bytes / G) + 15ull) & ~15ull;
+                    const unsigned long long b0 = per * c, lim = p.pf_bytes & ~15ull;
+                    const unsigned long long b1 = b0 + per < lim ? b0 + per : lim;
+                    constexpr unsigned long long PIECE = 8192;
+                    for (unsigned long long o = b0 + (unsigned long long)lane * PIECE; o < b1; o += 32 * PIECE) {
+                        const uint32_t n = (uint32_t)(b1 - o < PIECE ? b1 - o : PIECE);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + o), "r"(n) : "memory");
+                    }
+                }
+            }
+        }
+        if (p.use_pdl && !waited) pdl_wait();
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers: prologue
+    if (p.use_pdl) pdl_wait();          // the activations belong to the previous kernels
+    {
+        float norm_scale = 1.0f;
+        if (p.act_mode == ACT_F32_NORM) {
+            // rms_norm like glue.cu / the CPU oracle: sum of squares in double, fixed reduction order
+            double s = 0.0;
+            for (int i = threadIdx.x; i < p.K; i += BS1_NCW * 32) { const float v = p.x[i]; s += (double)__fmul_rn(v, v); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) s_red[warp] = s;
+            named_bar_sync(2, BS1_NCW * 32);
+            double t = 0.0;
+#pragma unroll 1
+            for (int i = 0; i < BS1_NCW; i++) t += s_red[i];
+            norm_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)p.K), p.eps)));
+        }
+        bs1_quantize(p, smem, warp, lane, norm_scale);
+    }
+    named_bar_sync(1, BS1_THREADS);     // activations complete + mbarriers initialised (producer arrived long ago)
+    if (nchunks == 0) return;
+
+    // ---------------------------------------------------------------------- consumers: main loop
+    const uint8_t *aq64 = smem + p.off_aq64, *aq128 = smem + p.off_aq128;
+    const uint32_t *s32 = (const uint32_t *)(smem + p.off_s32);
+    const uint4 *s16 = (const uint4 *)(smem + p.off_s16);
+    const float *ad = (const float *)(smem + p.off_ad);
+    const int nit64 = p.K >> 6, nit128 = p.K >> 7;
+#pragma unroll 1
+    for (int use = 0; use * ns < nchunks; use++) {
+#pragma unroll 1
+        for (int st = warp; st < ns; st += BS1_NCW) {
+            const int i = use * ns + st;
+            if (i >= nchunks) break;
+            int s = 0, lo_s = lo[0], hi_s = hi[0], c0 = 0;
+#pragma unroll
+            for (int t = 1; t < GEMV_MAX_SEG; t++) if (t < p.nseg && i >= ch0[t]) { s = t; lo_s = lo[t]; hi_s = hi[t]; c0 = ch0[t]; }
+            const Bs1Seg &sg = p.seg[s];
+            const int row0 = lo_s + (i - c0) * sg.R;
+            const int nr = min(sg.R, hi_s - row0);
+            const uint8_t *Wb = sg.expert_id ? sg.W + (size_t)(*sg.expert_id) * sg.expert_stride : sg.W;
+            const uint32_t extra = (uint32_t)((uintptr_t)(Wb + (size_t)row0 * sg.rb) & 15);
+            const uint8_t *rowp = ring + (size_t)st * p.stage_bytes + extra;
+            const int ty = sg.type;
+            mbar_wait(&full[st], use & 1);
+#pragma unroll 1
+            for (int r = 0; r < nr; r++, rowp += sg.rb) {
+                float acc = 0.0f;
+                if ((TYPES & TB_Q4_K) && (TYPES == TB_Q4_K || ty == B200_TYPE_Q4_K)) {
+#pragma unroll 1
+                    for (int it = lane; it < nit64; it += 32) acc += item_q45k<false>(rowp, it, aq64, s32, ad);
+                } else if ((TYPES & TB_Q5_K) && (TYPES == TB_Q5_K || ty == B200_TYPE_Q5_K)) {
+#pragma unroll 1
+                    for (int it = lane; it < nit64; it += 32) acc += item_q45k<true>(rowp, it, aq64, s32, ad);
+                } else if (TYPES & TB_Q6_K) {
+#pragma unroll 1
+                    for (int it = lane; it < nit128; it += 32) acc += item_q6k(rowp, it, aq128, s16, ad);
+                }
+                if (r == nr - 1) {                       // stage bytes consumed: hand it back before the reduction
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
+                }
+                acc = warp_reduce_sum(acc);
+                if (lane == 0) {
+                    const int o = row0 + r;
+                    if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
+                    sg.dst[o] = acc;
+                }
+            }
+        }
+    }
+}
+
+int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0;
+bool g_bs1_env = false;
+
+template <int TYPES>
+int bs1_launch_t(b200_ctx *ctx, const Bs1Params &p, int grid, size_t smem_bytes) {
+    auto kern = b200_gemv_bs1_kernel<TYPES>;
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        attr_set[ctx->device & 15] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(BS1_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    if (p.use_pdl) {
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        nattr++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = nattr;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    ctx->launches++;
+    return B200_OK;
+}
+
+}  // namespace
+
+// 1 = launched, 0 = not eligible (caller falls through to the general kernel), < 0 = error
+int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, bool w_const,
+                        const void *pf_ptr, size_t pf_bytes, int l2pf) {
+    if (!g_bs1_env) {
+        if (const char *e = getenv("GGML_B200_BS1_CTAS")) g_bs1_ctas = atoi(e);          // CTAs per SM (1 or 2; default 2)
+        if (const char *e = getenv("GGML_B200_BS1_SMEM_KB")) g_bs1_smem_kb = atoi(e);    // shared memory per CTA
+        if (const char *e = getenv("GGML_B200_BS1_OFF")) g_bs1_off = atoi(e);
+        g_bs1_env = true;
+    }
+    if (g_bs1_off || nseg < 1 || nseg > GEMV_MAX_SEG || K <= 0 || (K & 255) || K > 65536) return 0;
+    if (ga.mode != ACT_F32 && ga.mode != ACT_F32_NORM && ga.mode != ACT_F32_SWIGLU) return 0;
+    if (((uintptr_t)ga.x & 15) || (ga.mode != ACT_F32 && ((uintptr_t)ga.x2 & 15))) return 0;
+    int mask = 0;
+    for (int s = 0; s < nseg; s++) {
+        const int t = segs[s].type;
+        if (t == B200_TYPE_Q4_K) mask |= TB_Q4_K; else if (t == B200_TYPE_Q5_K) mask |= TB_Q5_K; else if (t == B200_TYPE_Q6_K) mask |= TB_Q6_K; else return 0;
+        if (segs[s].dbgP || segs[s].N <= 0 || segs[s].N > (1 << 22)) return 0;
+        if (t != B200_TYPE_Q6_K && (((uintptr_t)segs[s].W & 15) || (segs[s].rb & 15) || (segs[s].expert_stride & 15))) return 0;
+        if (t == B200_TYPE_Q6_K && (((uintptr_t)segs[s].W & 1) || (segs[s].expert_stride & 1))) return 0;
+    }
+    Bs1Params p = {};
+    p.nseg = nseg; p.K = (int)K; p.act_mode = ga.mode; p.x = ga.x; p.x2 = ga.x2; p.eps = ga.eps;
+    p.w_const = w_const ? 1 : 0; p.use_pdl = ctx->opt_pdl;
+    // shared memory: barriers | s_red | aq64 | aq128 | d | s32 | s16 | ring
+    uint32_t off = 2 * BS1_MAX_STAGES * 8 + 16 * 8;
+    const bool need64 = (mask & (TB_Q4_K | TB_Q5_K)) != 0, need128 = (mask & TB_Q6_K) != 0;
+    if (need64)  { p.off_aq64 = off;  off += (uint32_t)(K / 64) * 80;   off = (off + 15) & ~15u; }
+    if (need128) { p.off_aq128 = off; off += (uint32_t)(K / 128) * 144; off = (off + 15) & ~15u; }
+    p.off_ad = off; off += (uint32_t)(K / 256) * 4; off = (off + 15) & ~15u;
+    if (need64)  { p.off_s32 = off; off += (uint32_t)(K / 32) * 2; off = (off + 15) & ~15u; }
+    if (need128) { p.off_s16 = off; off += (uint32_t)(K / 16) * 2; off = (off + 15) & ~15u; }
+    off = (off + 127) & ~127u;
+    p.off_ring = off;
+    const int cps = g_bs1_ctas == 1 ? 1 : 2;
+    size_t budget = g_bs1_smem_kb > 0 ? (size_t)g_bs1_smem_kb * 1024 : (size_t)113 * 1024;     // two CTAs (this launch's, or this + the next launch's) per SM
+    if (budget > ctx->smem_optin) budget = ctx->smem_optin;
+    uint32_t max_rb = 0;
+    for (int s = 0; s < nseg; s++) max_rb = segs[s].rb > max_rb ? (uint32_t)segs[s].rb : max_rb;
+    if ((size_t)off + 2 * ((size_t)max_rb + 160) > budget) return 0;                            // needs >= 2 stages of one row
+    const size_t ring_budget = budget - off;
+    // stage: whole rows, about ring/32 bytes, at least one row
+    const uint32_t target = (uint32_t)(ring_budget / BS1_MAX_STAGES);
+    uint32_t stage = 0;
+    for (int s = 0; s < nseg; s++) {
+        Bs1Seg &g = p.seg[s];
+        g.W = segs[s].W; g.dst = segs[s].dst; g.residual = segs[s].residual; g.expert_id = segs[s].expert_id; g.expert_stride = segs[s].expert_stride;
+        g.rb = (uint32_t)segs[s].rb; g.type = segs[s].type; g.N = (int)segs[s].N;
+        int R = (int)(target / g.rb);
+        g.R = R < 1 ? 1 : (R > 8 ? 8 : R);
+        const uint32_t sb = (uint32_t)(((size_t)g.R * g.rb + 32 + 127) & ~(size_t)127);       // +16 misalignment, +16 over-read
+        stage = sb > stage ? sb : stage;
+    }
+    int ns = (int)(ring_budget / stage);
+    if (ns > BS1_MAX_STAGES) ns = BS1_MAX_STAGES;
+    if (ns >= BS1_NCW) ns = ns / BS1_NCW * BS1_NCW;      // every consumer warp owns the same number of stages
+    if (ns < 2) return 0;
+    p.nstages = ns; p.stage_bytes = stage;
+    const size_t smem_bytes = off + (size_t)ns * stage;
+    if (l2pf && pf_ptr && pf_bytes) {
+        p.pf_ptr = (const uint8_t *)pf_ptr;
+        p.pf_bytes = pf_bytes < ((size_t)48 << 20) ? pf_bytes : ((size_t)48 << 20);
+        const uintptr_t mis = (uintptr_t)p.pf_ptr & 15;
+        if (mis) { p.pf_ptr += 16 - mis; p.pf_bytes = p.pf_bytes > 16 ? p.pf_bytes - 16 : 0; }
+    }
+    int64_t min_rows = segs[0].N;
+    for (int s = 1; s < nseg; s++) min_rows = segs[s].N < min_rows ? segs[s].N : min_rows;
+    int64_t grid = (int64_t)ctx->sm_count * cps;
+    if (grid > min_rows) grid = min_rows;                // every CTA gets at least one row of every segment
+    int rc;
+    switch (mask) {
+        case TB_Q4_K: rc = bs1_launch_t<TB_Q4_K>(ctx, p, (int)grid, smem_bytes); break;
+        case TB_Q6_K: rc = bs1_launch_t<TB_Q6_K>(ctx, p, (int)grid, smem_bytes); break;
+        case TB_Q5_K: rc = bs1_launch_t<TB_Q5_K>(ctx, p, (int)grid, smem_bytes); break;
+        case TB_Q4_K | TB_Q6_K: rc = bs1_launch_t<TB_Q4_K | TB_Q6_K>(ctx, p, (int)grid, smem_bytes); break;
+        default: rc = bs1_launch_t<TB_Q4_K | TB_Q5_K | TB_Q6_K>(ctx, p, (int)grid, smem_bytes); break;
+    }
+    return rc ? rc : 1;
+}
