@@ -130,6 +130,7 @@ struct b200_ctx {
     GraphCache *  graph_cache = nullptr;
     bool          capturing = false;
     void *        prof_buf = nullptr;   // debug: per-CTA timestamps (b200_debug_set_prof)
+    int           prof_launch = 0;
 
     void *get_scratch(int slot, size_t size);   // grows (sync + realloc) when too small; nullptr on OOM
 };

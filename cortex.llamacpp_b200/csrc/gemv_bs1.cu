@@ -52,6 +52,7 @@ struct Bs1Params {
     uint32_t       off_aq64, off_aq128, off_ad, off_s32, off_s16, off_ring;   // 0 = layout not needed (aq*, s*)
     const uint8_t *pf_ptr;
     unsigned long long pf_bytes;
+    unsigned long long *prof;           // optional [grid][32] globaltimer stamps (tools/bs1_prof.py)
 };
 
 constexpr int TB_Q4_K = 1, TB_Q5_K = 2, TB_Q6_K = 4;
@@ -187,6 +188,7 @@ __device__ __forceinline__ float item_q6k(const uint8_t *row, int it, const uint
 
 // ---------------------------------------------------------------------------------------------- prologue
 // f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref
+#define PROFQ(slot) do { if (p.prof && lane == 0 && warp == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[(size_t)blockIdx.x * 32 + (slot)] = t_; } } while (0)
 __device__ __forceinline__ void bs1_quantize(const Bs1Params &p, uint8_t *smem, int warp, int lane, float norm_scale) {
     const int nchunk = p.K >> 8;
     float *s_ad = (float *)(smem + p.off_ad);
@@ -218,8 +220,10 @@ __device__ __forceinline__ void bs1_quantize(const Bs1Params &p, uint8_t *smem, 
                     for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fdiv_rn(v[j], 1.0f + expf(-v[j])), w[j]);
                 }
             }
+            if (p.prof) { asm volatile("" : "+f"(v[0])); if (u == 0) PROFQ(24); }
             uint2 qp; float d; int pair;
             warp_quant_q8k(v, lane, qp, d, pair);                // pair: 16-element sum, valid in even lanes
+            if (p.prof) { asm volatile("" : "+f"(d)); if (u == 0) PROFQ(25); }
             const int quad = pair + __shfl_xor_sync(0xffffffffu, pair, 2);
             if (p.off_s16 && (lane & 1) == 0) s_s16[b * 16 + (lane >> 1)] = (int16_t)pair;
             if (p.off_s32 && (lane & 3) == 0) s_s32[b * 8 + (lane >> 2)] = (int16_t)quad;
@@ -240,6 +244,8 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, c = blockIdx.x;
     const int ns = p.nstages;
+#define PROF(slot) do { if (p.prof && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[(size_t)blockIdx.x * 32 + (slot)] = t_; } } while (0)
+    if (warp == 0) PROF(0);
     // programmatic dependent launch: the next kernel's CTAs may become resident right away (half an SM is left for them);
     // everything of theirs that depends on our output blocks in griddepcontrol.wait until this grid has completed
     if (p.use_pdl) pdl_trigger();
@@ -272,6 +278,7 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
         const uint64_t pol = l2_policy_evict_first();
         int i = lane, use = 0;
         bool first_pass = true;
+        PROF(1);
         while (__any_sync(0xffffffffu, lane < ns && i < nchunks)) {
             if (lane < ns && i < nchunks && (use == 0 || mbar_test_wait(&empty[lane], (use - 1) & 1))) {
                 int s = 0, lo_s = lo[0], hi_s = hi[0], c0 = 0;
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
             }
             if (first_pass) {
                 first_pass = false;
+                PROF(2);
                 // the NEXT matmul's weights: ask the L2 to start fetching this CTA's 1/G of them now
                 if (p.pf_bytes) {
                     const unsigned long long per = ((p.pf_bytes / G) + 15ull) & ~15ull;
@@ -303,12 +311,14 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
                 }
             }
         }
+        PROF(3);
         if (p.use_pdl && !waited) pdl_wait();
         return;
     }
 
     // ---------------------------------------------------------------------- consumers: prologue
     if (p.use_pdl) pdl_wait();          // the activations belong to the previous kernels
+    if (warp == 0) PROF(4);
     {
         float norm_scale = 1.0f;
         if (p.act_mode == ACT_F32_NORM) {
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
         bs1_quantize(p, smem, warp, lane, norm_scale);
     }
     named_bar_sync(1, BS1_THREADS);     // activations complete + mbarriers initialised (producer arrived long ago)
+    if (warp == 0) PROF(5);
     if (nchunks == 0) return;
 
     // ---------------------------------------------------------------------- consumers: main loop
@@ -352,6 +363,7 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
             const uint8_t *rowp = ring + (size_t)st * p.stage_bytes + extra;
             const int ty = sg.type;
             mbar_wait(&full[st], use & 1);
+            if (i == 0) PROF(6);
 #pragma unroll 1
             for (int r = 0; r < nr; r++, rowp += sg.rb) {
                 float acc = 0.0f;
@@ -376,8 +388,11 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
                     sg.dst[o] = acc;
                 }
             }
+            if (i == 0) PROF(7);
         }
     }
+    PROF(8 + warp);                      // each consumer warp's finish time
+#undef PROF
 }
 
 int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0;
@@ -445,8 +460,8 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     if (need128) { p.off_s16 = off; off += (uint32_t)(K / 16) * 2; off = (off + 15) & ~15u; }
     off = (off + 127) & ~127u;
     p.off_ring = off;
-    const int cps = g_bs1_ctas == 1 ? 1 : 2;
-    size_t budget = g_bs1_smem_kb > 0 ? (size_t)g_bs1_smem_kb * 1024 : (size_t)113 * 1024;     // two CTAs (this launch's, or this + the next launch's) per SM
+    const int cps = g_bs1_ctas == 2 ? 2 : 1;
+    size_t budget = g_bs1_smem_kb > 0 ? (size_t)g_bs1_smem_kb * 1024 : (size_t)220 * 1024;     // measured best: one CTA per SM with a deep ring (profiles/r1_bs1_ab.txt)
     if (budget > ctx->smem_optin) budget = ctx->smem_optin;
     uint32_t max_rb = 0;
     for (int s = 0; s < nseg; s++) max_rb = segs[s].rb > max_rb ? (uint32_t)segs[s].rb : max_rb;
@@ -475,6 +490,10 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         p.pf_bytes = pf_bytes < ((size_t)48 << 20) ? pf_bytes : ((size_t)48 << 20);
         const uintptr_t mis = (uintptr_t)p.pf_ptr & 15;
         if (mis) { p.pf_ptr += 16 - mis; p.pf_bytes = p.pf_bytes > 16 ? p.pf_bytes - 16 : 0; }
+    }
+    if (ctx->prof_buf) {                 // rotating per-launch slots so consecutive launches can be laid on one timeline
+        p.prof = (unsigned long long *)ctx->prof_buf + (size_t)(ctx->prof_launch % 8) * 296 * 32;
+        ctx->prof_launch++;
     }
     int64_t min_rows = segs[0].N;
     for (int s = 1; s < nseg; s++) min_rows = segs[s].N < min_rows ? segs[s].N : min_rows;
