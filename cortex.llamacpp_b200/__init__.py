@@ -23,7 +23,7 @@ BLOCK = {F32: (1, 4), F16: (1, 2), BF16: (1, 2), I32: (1, 4), Q4_0: (32, 18), Q8
 
 (OP_NONE, OP_MUL_MAT, OP_MUL_MAT_ID, OP_FLASH_ATTN_EXT, OP_RMS_NORM, OP_ROPE, OP_CPY, OP_CONT, OP_ADD, OP_SUB, OP_MUL,
  OP_DIV, OP_SILU, OP_GELU, OP_RELU, OP_TANH, OP_SIGMOID, OP_GET_ROWS, OP_SOFT_MAX, OP_ARGSORT, OP_SUM_ROWS, OP_SCALE,
- OP_SWIGLU_FUSED, OP_RMS_NORM_MUL, OP_COUNT) = range(25)
+ OP_SWIGLU_FUSED, OP_RMS_NORM_MUL, OP_ALLREDUCE, OP_COUNT) = range(26)
 
 TENSOR_FLAG_WEIGHT = 1
 
@@ -94,6 +94,13 @@ def lib():
         "b200_quantize_act": (C.c_int, [vp, i32, vp, vp, i64, i64]),
         "b200_block_sums": (C.c_int, [vp, i32, vp, vp, i64, i64, vp, vp]),
         "b200_debug_set_prof": (C.c_int, [vp, vp]),
+        "b200_comm_unique_id": (C.c_int, [vp]),
+        "b200_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "b200_comm_peer_handle": (C.c_int, [vp, vp]),
+        "b200_comm_peer_attach": (C.c_int, [vp, vp]),
+        "b200_comm_rank": (C.c_int, [vp]),
+        "b200_comm_world": (C.c_int, [vp]),
+        "b200_comm_destroy": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here == the .so does not export what the header declares
@@ -153,6 +160,24 @@ class Context:
 
     def compute_op(self, op):
         check(lib().b200_op_compute(self.h, C.byref(op)), "op_compute")
+
+    def comm_init(self, rank, world, exchange):
+        """Join a tensor-parallel group of `world` processes (one GPU each).  `exchange(blob, src)` must return, on every
+        rank, the list of every rank's `blob` (bytes) -- e.g. torch.distributed.all_gather_object; it is the only thing
+        the library needs from the host's process launcher (b200_comm_* in include/ggml_b200.h)."""
+        L = lib()
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            check(L.b200_comm_unique_id(uid), "comm_unique_id")
+        uid_all = exchange(bytes(uid.raw))
+        uid0 = C.create_string_buffer(uid_all[0], 128)
+        check(L.b200_comm_init(self.h, uid0, rank, world), "comm_init")
+        if world > 1:
+            hb = C.create_string_buffer(64)
+            check(L.b200_comm_peer_handle(self.h, hb), "comm_peer_handle")
+            hs = exchange(bytes(hb.raw))
+            allh = C.create_string_buffer(b"".join(hs), 64 * world)
+            check(L.b200_comm_peer_attach(self.h, allh), "comm_peer_attach")
 
 
 def tensor(data_ptr, type_, ne, nb=None, flags=0):

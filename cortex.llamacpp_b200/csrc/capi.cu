@@ -96,6 +96,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     graph_cache_free(ctx);
+    b200_comm_destroy(ctx);
     for (int i = 0; i < SCRATCH_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

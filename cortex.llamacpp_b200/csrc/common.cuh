@@ -112,6 +112,7 @@ struct ActLayout {
 // context
 // ------------------------------------------------------------------------------------------------
 struct GraphCache;   // graph.cu
+struct b200_comm;    // comm.cu
 
 struct b200_ctx {
     int           device   = 0;
@@ -128,6 +129,7 @@ struct b200_ctx {
     int           opt_pdl         = 0;
     int           opt_l2_prefetch = 1;
     GraphCache *  graph_cache = nullptr;
+    b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
     bool          capturing = false;
     void *        prof_buf = nullptr;   // debug: per-CTA timestamps (b200_debug_set_prof)
     int           prof_launch = 0;
@@ -146,6 +148,8 @@ bool supports_mul_mat(const b200_op *op);
 bool supports_mul_mat_id(const b200_op *op);
 bool supports_flash_attn_ext(const b200_op *op);
 bool supports_glue(const b200_op *op);
+int op_allreduce(b200_ctx *ctx, const b200_op *op);     // comm.cu
+bool supports_allreduce(const b200_op *op);
 
 // fused ROPE(q) + ROPE(k) + KV-store of k and v for a decode ubatch (glue.cu); q/k/v are contiguous [D, heads, T] f32
 struct RopeStoreDesc {

@@ -34,6 +34,7 @@ static int dispatch(b200_ctx *ctx, const b200_op *op) {
         case B200_OP_MUL_MAT: return op_mul_mat(ctx, op);
         case B200_OP_MUL_MAT_ID: return op_mul_mat_id(ctx, op);
         case B200_OP_FLASH_ATTN_EXT: return op_flash_attn_ext(ctx, op);
+        case B200_OP_ALLREDUCE: return op_allreduce(ctx, op);
         default: return op_glue(ctx, op);
     }
 }
@@ -46,6 +47,7 @@ extern "C" int b200_supports_op(int device, const b200_op *op) {
         case B200_OP_MUL_MAT: return supports_mul_mat(op) ? 1 : 0;
         case B200_OP_MUL_MAT_ID: return supports_mul_mat_id(op) ? 1 : 0;
         case B200_OP_FLASH_ATTN_EXT: return supports_flash_attn_ext(op) ? 1 : 0;
+        case B200_OP_ALLREDUCE: return supports_allreduce(op) ? 1 : 0;
         default: return supports_glue(op) ? 1 : 0;
     }
 }
@@ -235,7 +237,8 @@ static int match_ffn(const b200_op *ops, int n, int i, const FuseScratch &fs, st
     const b200_tensor *xin; const float *nw; float eps;
     if (i + 7 >= n || !match_norm_mul(ops, n, i, xin, nw, eps)) return 0;
     const b200_op &add = ops[i + 7];
-    if (add.op != B200_OP_ADD) return 0;
+    const bool tp = add.op == B200_OP_ALLREDUCE;       // tensor parallel: down's partial sums go to the all-reduce (which adds the residual)
+    if (add.op != B200_OP_ADD && !tp) return 0;
     const b200_op *mm[3], *silu = nullptr, *mul = nullptr;
     int nmm = 0;
     for (int j = i + 2; j < i + 7; j++) {
@@ -256,13 +259,20 @@ static int match_ffn(const b200_op *ops, int n, int i, const FuseScratch &fs, st
     if (!gate || !up || !down || !all_weights(mm, 3)) return 0;
     if (!((mul->src[0].data == silu->dst.data && mul->src[1].data == up->dst.data) || (mul->src[1].data == silu->dst.data && mul->src[0].data == up->dst.data))) return 0;
     if (!same_tensor(down->src[1], mul->dst)) return 0;
-    const b200_tensor *resid = add.src[0].data == down->dst.data ? &add.src[1] : (add.src[1].data == down->dst.data ? &add.src[0] : nullptr);
-    if (!resid) return 0;
     const int64_t T = B.ne[1], FF = gate->src[0].ne[1], E = down->src[0].ne[1];
-    if (up->src[0].ne[1] != FF || down->src[0].ne[0] != FF || !is_vec_f32(*resid, E) || !is_vec_f32(add.dst, E) || resid->ne[1] != T || add.dst.ne[1] != T) return 0;
     if (b200_act_mode_q8k(gate->src[0].type) != b200_act_mode_q8k(up->src[0].type)) return 0;
-    const b200_tensor *dead[] = {&ops[i].dst, &B, &gate->dst, &silu->dst, &up->dst, &mul->dst, &down->dst};
-    for (const b200_tensor *t : dead) if (!overlaps(*t, add.dst) && live_after(ops, n, i + 8, *t)) return 0;
+    const b200_tensor *resid = nullptr;
+    if (tp) {
+        if (add.src[0].data != down->dst.data || !is_vec_f32(down->dst, E) || up->src[0].ne[1] != FF || down->src[0].ne[0] != FF) return 0;
+        const b200_tensor *dead[] = {&ops[i].dst, &B, &gate->dst, &silu->dst, &up->dst, &mul->dst};
+        for (const b200_tensor *t : dead) if (!overlaps(*t, down->dst) && live_after(ops, n, i + 7, *t)) return 0;
+    } else {
+        resid = add.src[0].data == down->dst.data ? &add.src[1] : (add.src[1].data == down->dst.data ? &add.src[0] : nullptr);
+        if (!resid) return 0;
+        if (up->src[0].ne[1] != FF || down->src[0].ne[0] != FF || !is_vec_f32(*resid, E) || !is_vec_f32(add.dst, E) || resid->ne[1] != T || add.dst.ne[1] != T) return 0;
+        const b200_tensor *dead[] = {&ops[i].dst, &B, &gate->dst, &silu->dst, &up->dst, &mul->dst, &down->dst};
+        for (const b200_tensor *t : dead) if (!overlaps(*t, add.dst) && live_after(ops, n, i + 8, *t)) return 0;
+    }
     ExecNode g;
     g.kind = EX_GEMV; g.nseg = 2; g.K = xin->ne[0]; g.ncols = (int)T; g.w_const = true;
     g.seg[0] = seg_of(*gate, fs.g, (size_t)FF, nullptr);
@@ -272,11 +282,11 @@ static int match_ffn(const b200_op *ops, int n, int i, const FuseScratch &fs, st
     out.push_back(g);
     ExecNode d;
     d.kind = EX_GEMV; d.nseg = 1; d.K = FF; d.ncols = (int)T; d.w_const = true;
-    d.seg[0] = seg_of(*down, (float *)add.dst.data, (size_t)E, (const float *)resid->data);
+    d.seg[0] = tp ? seg_of(*down, (float *)down->dst.data, (size_t)E, nullptr) : seg_of(*down, (float *)add.dst.data, (size_t)E, (const float *)resid->data);
     d.act = GemvActDesc{};
     d.act.mode = ACT_F32_SWIGLU; d.act.x = fs.g; d.act.x_stride = (size_t)FF * 4; d.act.x2 = fs.u;
     out.push_back(d);
-    return 8;
+    return tp ? 7 : 8;
 }
 
 // MUL_MAT -> ADD(mm, residual)

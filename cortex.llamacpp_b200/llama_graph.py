@@ -60,13 +60,47 @@ def device_rand_blocks(torch, t, nrows, K, amp, gen, device):
     return out
 
 
+def tp_plan(model_dims, world):
+    """Megatron split of a llama layer over `world` ranks: heads / KV heads / FFN columns per rank.
+    wq|wk|wv and gate|up are split by OUTPUT ROWS (whole heads, whole FF rows), wo and down by K; K-quant shards must
+    start on 256-element super-block boundaries.  Raises if the model does not divide."""
+    H, Hkv, D, FF = model_dims
+    if H % world or Hkv % world or FF % world:
+        raise ValueError("tensor parallel %d does not divide H=%d Hkv=%d FF=%d" % (world, H, Hkv, FF))
+    Hl, Hkvl, FFl = H // world, Hkv // world, FF // world
+    if (Hl * D) % 256 or FFl % 256:
+        raise ValueError("K-split shards must be multiples of 256 elements: H/N*D=%d FF/N=%d" % (Hl * D, FFl))
+    return Hl, Hkvl, FFl
+
+
+def shard_rows(buf, t, K, N, rank, world):
+    """column-parallel shard: rows [rank*N/world, (rank+1)*N/world) of a [K, N] GGUF tensor are one contiguous byte range"""
+    rb = row_size(t, K)
+    n = N // world
+    return buf[rank * n * rb:(rank + 1) * n * rb]
+
+
+def shard_k(buf, t, K, N, rank, world):
+    """row-parallel shard: columns [rank*K/world, (rank+1)*K/world) of every row = whole blocks; returns a contiguous copy
+    (what a split buffer type's set_tensor would store on this rank).  Works on torch (device) and numpy (host) uint8."""
+    be, bb = BLOCK[t]
+    nbk = K // be
+    assert nbk % world == 0, (K, be, world)
+    per = nbk // world
+    v = buf[:N * nbk * bb].reshape(N, nbk, bb)[:, rank * per:(rank + 1) * per, :]
+    return v.reshape(-1).clone() if hasattr(v, "clone") else v.reshape(-1).copy()
+
+
 class LlamaGraph:
     """Synthetic llama-architecture model in HBM + builders for the per-ubatch op list.
 
     n_ctx cells of KV cache per layer (one unified cache as llama_kv_cache_unified, llama-kv-cache.cpp:76-113).
     """
 
-    def __init__(self, b200, model="llama3-8b", ftype="q4_k_m", kv="f16", n_ctx=4096, layers=0, seed=1234, device=0, max_tokens=1):
+    def __init__(self, b200, model="llama3-8b", ftype="q4_k_m", kv="f16", n_ctx=4096, layers=0, seed=1234, device=0, max_tokens=1,
+                 tp_rank=0, tp_world=1):
+        """tp_world > 1: this process holds rank tp_rank's shard of a row-split tensor-parallel model.  Every rank draws the
+        SAME full tensors from the same seed and keeps only its shard, so TP=N computes the same model as TP=1."""
         import torch
         self.torch, self.b200 = torch, b200
         self.dev = torch.device("cuda", device)
@@ -76,6 +110,11 @@ class LlamaGraph:
         if n_expert:
             raise NotImplementedError("MoE graphs are built by the tests directly")
         self.model, self.ftype = model, ftype
+        self.tp_rank, self.tp_world = tp_rank, tp_world
+        self.H_full, self.Hkv_full, self.FF_full = H, Hkv, FF
+        Hf, Hkvf, FFf = H, Hkv, FF
+        if tp_world > 1:
+            H, Hkv, FF = tp_plan((H, Hkv, D, FF), tp_world)
         self.L, self.E, self.H, self.Hkv, self.D, self.FF, self.V, self.rope_base = L, E, H, Hkv, D, FF, V, rope_base
         self.kv_type = KV_TYPES[kv]
         self.n_ctx = n_ctx
@@ -86,13 +125,20 @@ class LlamaGraph:
         self.weight_bytes = 0
         self.weight_bytes_by_type = {}
 
-        def weight(name, K, N, il, gain=1.0):
-            t = tensor_type(name, ftype, il, L, 0, H // Hkv)
+        def weight(name, K, N, il, gain=1.0, split=None):
+            """K, N are the FULL dimensions; split = None (replicated) | "rows" (column parallel) | "k" (row parallel)"""
+            t = tensor_type(name, ftype, il, L, 0, Hf // Hkvf)
             amp = gain * math.sqrt(3.0 / K)
             if t == F32:
                 buf = ((torch.rand(N * K, device=self.dev, generator=gen) * 2 - 1) * amp).view(torch.uint8)
             else:
                 buf = device_rand_blocks(torch, t, N, K, amp, gen, self.dev)
+            if tp_world > 1 and split == "rows":
+                buf = torch.cat([shard_rows(buf, t, K, N, tp_rank, tp_world), torch.zeros(256, dtype=torch.uint8, device=self.dev)])
+                N = N // tp_world
+            elif tp_world > 1 and split == "k":
+                buf = torch.cat([shard_k(buf, t, K, N, tp_rank, tp_world), torch.zeros(256, dtype=torch.uint8, device=self.dev)])
+                K = K // tp_world
             self.keep.append(buf)
             nbytes = N * row_size(t, K)
             self.weight_bytes += nbytes
@@ -109,11 +155,11 @@ class LlamaGraph:
             p = "blk.%d." % il
             lw = dict(
                 attn_norm=norm(),
-                wq=weight(p + "attn_q.weight", E, H * D, il), wk=weight(p + "attn_k.weight", E, Hkv * D, il),
-                wv=weight(p + "attn_v.weight", E, Hkv * D, il), wo=weight(p + "attn_output.weight", H * D, E, il),
+                wq=weight(p + "attn_q.weight", E, Hf * D, il, split="rows"), wk=weight(p + "attn_k.weight", E, Hkvf * D, il, split="rows"),
+                wv=weight(p + "attn_v.weight", E, Hkvf * D, il, split="rows"), wo=weight(p + "attn_output.weight", Hf * D, E, il, split="k"),
                 ffn_norm=norm(),
-                gate=weight(p + "ffn_gate.weight", E, FF, il), down=weight(p + "ffn_down.weight", FF, E, il),
-                up=weight(p + "ffn_up.weight", E, FF, il))
+                gate=weight(p + "ffn_gate.weight", E, FFf, il, split="rows"), down=weight(p + "ffn_down.weight", FFf, E, il, split="k"),
+                up=weight(p + "ffn_up.weight", E, FFf, il, split="rows"))
             rs = row_size(self.kv_type, Hkv * D)
             kc = torch.zeros(rs * n_ctx, dtype=torch.uint8, device=self.dev)
             vc = torch.zeros(rs * n_ctx, dtype=torch.uint8, device=self.dev)
@@ -199,7 +245,10 @@ class LlamaGraph:
             ops.append(b.make_op(b.OP_FLASH_ATTN_EXT, t(p(self.att), F32, [D, H, T]), [qv, kv_, vv, mk],
                                  [1.0 / math.sqrt(D), 0.0, 0.0]))
             ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.tmpE), F32, [E, T]), [lw["wo"], t(p(self.att), F32, [H * D, T])]))
-            ops.append(b.make_op(b.OP_ADD, t(p(other), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), xin]))
+            if self.tp_world > 1:      # partial sums over this rank's heads -> sum over ranks (+ residual)
+                ops.append(b.make_op(b.OP_ALLREDUCE, t(p(other), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), xin]))
+            else:
+                ops.append(b.make_op(b.OP_ADD, t(p(other), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), xin]))
             ffn_inp = t(p(other), F32, [E, T])
             # FFN
             ops.append(b.make_op(b.OP_RMS_NORM, t(p(self.cur), F32, [E, T]), [ffn_inp], [1e-5]))
@@ -210,7 +259,10 @@ class LlamaGraph:
             ops.append(b.make_op(b.OP_MUL, t(p(self.gu), F32, [FF, T]), [t(p(self.gu), F32, [FF, T]), t(p(self.u), F32, [FF, T])]))
             ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.tmpE), F32, [E, T]), [lw["down"], t(p(self.gu), F32, [FF, T])]))
             nxt = self.resid2 if other is self.resid else self.resid
-            ops.append(b.make_op(b.OP_ADD, t(p(nxt), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), ffn_inp]))
+            if self.tp_world > 1:
+                ops.append(b.make_op(b.OP_ALLREDUCE, t(p(nxt), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), ffn_inp]))
+            else:
+                ops.append(b.make_op(b.OP_ADD, t(p(nxt), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), ffn_inp]))
             inp, other = nxt, (self.resid if nxt is self.resid2 else self.resid2)
         ops.append(b.make_op(b.OP_RMS_NORM, t(p(self.cur), F32, [E, T]), [t(p(inp), F32, [E, T])], [1e-5]))
         ops.append(b.make_op(b.OP_MUL, t(p(self.cur2), F32, [E, T]), [t(p(self.cur), F32, [E, T]), self.output_norm]))

@@ -64,6 +64,8 @@ typedef enum b200_op_id {
     B200_OP_SCALE,           /* params[0] = scale                                                      (scale.cu)           */
     B200_OP_SWIGLU_FUSED,    /* dst = silu(src0) * src1 (fusion of UNARY(SILU)+MUL emitted by the backend's matcher)        */
     B200_OP_RMS_NORM_MUL,    /* dst = rms_norm(src0) * src1  (fusion of RMS_NORM+MUL)                                       */
+    B200_OP_ALLREDUCE,       /* dst = sum over tensor-parallel ranks of src0 (+ src1 residual, optional); f32, contiguous:   */
+                             /* the exchange that replaces ggml_cuda_op_mul_mat's row gather (ggml-cuda.cu:1363-1671)        */
     B200_OP_COUNT
 } b200_op_id;
 
@@ -133,6 +135,23 @@ B200_API int         b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n
 B200_API int         b200_op_compute(b200_ctx *ctx, const b200_op *op);   /* single op, no fusion */
 B200_API int64_t     b200_kernel_launches(const b200_ctx *ctx);       /* kernels launched by this ctx so far (bench: gpu_launches) */
 B200_API int         b200_set_option(b200_ctx *ctx, const char *key, int value); /* "cuda_graphs", "fusion", "pdl" */
+
+/* ---- tensor parallelism: one process (and one b200_ctx) per GPU ------------------------------
+ * Replaces the split-buffer matmul driver ggml_cuda_op_mul_mat + ggml_backend_cuda_split_buffer_type
+ * (ggml-cuda.cu:725-1050, 1363-1671) and ggml_cuda_set_peer_access (:1285-1341): weights are sharded
+ * Megatron-style by the host (wq/wk/wv/gate/up by rows, wo/down by K at block boundaries) and the only
+ * exchange is B200_OP_ALLREDUCE after wo and after down.  The host transports two opaque blobs between
+ * its ranks (any way it likes: torch.distributed, MPI, a socket): the 128-byte communicator id of rank 0
+ * and the 64-byte peer-memory handle of every rank. */
+#define B200_COMM_ID_BYTES     128
+#define B200_COMM_HANDLE_BYTES 64
+B200_API int         b200_comm_unique_id(void *id128);                                   /* rank 0 */
+B200_API int         b200_comm_init(b200_ctx *ctx, const void *id128, int rank, int world); /* collective */
+B200_API int         b200_comm_peer_handle(b200_ctx *ctx, void *handle64);               /* this rank's exchange buffer */
+B200_API int         b200_comm_peer_attach(b200_ctx *ctx, const void *handles);          /* world x 64 bytes, rank order */
+B200_API int         b200_comm_rank(const b200_ctx *ctx);
+B200_API int         b200_comm_world(const b200_ctx *ctx);
+B200_API int         b200_comm_destroy(b200_ctx *ctx);
 
 /* ---- test hooks: expose the integer stage of the quantised dot so parity can be bit-exact ---- */
 /* x f32 [rows, K] (row stride K) -> act blocks in the reference's block_q8_0 / block_q8_K byte layout */
