@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("GGML_B200_PDL", "1")))
     ap.add_argument("--fusion", type=int, default=2)
     ap.add_argument("--l2pf", type=int, default=1)
+    ap.add_argument("--tp-model", default="llama3-70b", help="N>1: model of the extra row-split tensor-parallel leg ('' = skip)")
+    ap.add_argument("--tp-layers", type=int, default=0, help="debug: fewer layers in the TP leg (reported as INVALID)")
     a = ap.parse_args()
     if a.impl == "reference":
         return reference_arm(a)
@@ -297,11 +299,84 @@ def main():
                                     "sample": "8 decode steps after a %d-token prompt, llama_decode on the reference ggml CPU backend" % DEPTH}
         except Exception as ex:           # the baseline is a report, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": host_threads(), "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
+    # ---------------------------------------------------------------- N > 1: row-split tensor-parallel leg
+    if world > 1 and a.tp_model:
+        try:
+            del ops, ops_arr, q4k, q4k_arr
+            g.keep.clear(); g.layers.clear()
+            del g
+            torch.cuda.empty_cache()
+            line["tp"] = tp_leg(a, b200, lg, L, ctx, rank, world, local, peak)
+        except Exception as ex:
+            line["tp"] = {"error": str(ex)[:300]}
     if rank == 0:
         print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def tp_leg(a, b200, lg, L, ctx, rank, world, local, peak):
+    """Row-split tensor parallelism over all `world` GPUs: ONE model (default Llama-3-70B Q4_K_M, random-init shards drawn
+    from a common seed), wq/wk/wv/gate/up split by rows, wo/down by K, B200_OP_ALLREDUCE (one-shot peer-memory kernel over
+    NVLink) after wo and down.  scaling = strong: tok/s of the single bs1 stream; roofline = per-GPU shard bytes / step time."""
+    import torch
+    import torch.distributed as dist
+
+    def exchange(blob):
+        out = [None] * world
+        dist.all_gather_object(out, blob)
+        return out
+    ctx.comm_init(rank, world, exchange)
+    depth = DEPTH
+    g = lg.LlamaGraph(b200, model=a.tp_model, ftype=FTYPE, kv=KV, n_ctx=1024, layers=a.tp_layers, device=local, max_tokens=1,
+                      tp_rank=rank, tp_world=world)
+    g.fill_cache(depth)
+    kv_head, n_kv = depth, (depth + 1 + 255) // 256 * 256
+    rng = np.random.default_rng(0)                               # same inputs on every rank
+    emb, pos, mask = g.set_inputs_host(1, kv_head, n_kv, rng)
+    g.inp_embd[:g.E] = torch.from_numpy(emb.reshape(-1)).cuda(local)
+    g.pos[:1] = torch.from_numpy(pos).cuda(local)
+    g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda(local)
+    torch.cuda.synchronize()
+    ops = g.build(1, kv_head, n_kv)
+    arr = (b200.Op * len(ops))(*ops)
+    ctx.set_option("cuda_graphs", a.graphs); ctx.set_option("fusion", a.fusion)
+    e0, e1 = L.b200_event_create(local), L.b200_event_create(local)
+    W, K = max(a.warmup, 3), a.steps
+    n0 = ctx.launches()
+    b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step"); ctx.sync()
+    launches = ctx.launches() - n0
+    for _ in range(W):
+        b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step")
+    ctx.sync(); dist.barrier(); torch.cuda.synchronize()
+    L.b200_event_record(ctx.h, e0)
+    for _ in range(K):
+        b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step")
+    L.b200_event_record(ctx.h, e1)
+    L.b200_event_synchronize(e1)
+    ctx.sync(); dist.barrier()
+    ms = L.b200_event_elapsed_ms(e0, e1)
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    logits = g.logits[:g.V].clone()
+    ref = logits.clone()
+    dist.broadcast(ref, 0)
+    same = bool(torch.equal(ref, logits))
+    flag = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    sb = g.step_bytes(1, n_kv)
+    tok_s = K / (ms / 1e3)
+    out = {"model": "%s %s row-split over %d GPUs (random-init shards of one common-seed model)" % (a.tp_model, FTYPE, world), "world": world,
+           "value": tok_s, "unit": "tok/s", "scaling": "strong", "ms_per_step": ms / K, "steps": K, "warmup": W,
+           "allreduce": "B200_OP_ALLREDUCE x%d per step: one-shot peer-memory kernel over NVLink (f32 [E] = %d bytes), residual add fused" % (2 * g.L, g.E * 4),
+           "gpu_launches_per_step": int(launches), "logits_identical_on_all_ranks": bool(flag.item()),
+           "per_gpu_bytes_per_step": sb["total"], "per_gpu_achieved_gbs": sb["total"] * tok_s / 1e9, "per_gpu_hbm_frac": sb["total"] * tok_s / 1e9 / peak,
+           "single_gpu_roofline_tok_s": None}
+    if a.tp_layers:
+        out["INVALID"] = "--tp-layers override"
+    return out
 
 
 if __name__ == "__main__":

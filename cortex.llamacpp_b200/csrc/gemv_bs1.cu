@@ -28,8 +28,7 @@
 namespace {
 
 constexpr int BS1_MAX_STAGES = 32;      // one producer lane per stage
-constexpr int BS1_THREADS    = 512;     // 15 consumer warps + 1 producer warp
-constexpr int BS1_NCW        = BS1_THREADS / 32 - 1;
+constexpr int BS1_MAX_THREADS = 1024;   // consumer warps + 1 producer warp; the launch picks 512 or 1024 (GGML_B200_BS1_WARPS)
 
 struct Bs1Seg {
     const uint8_t *W;
@@ -48,7 +47,7 @@ struct Bs1Params {
     float          eps;
     int            nstages;
     uint32_t       stage_bytes;
-    int            w_const, use_pdl;
+    int            w_const, use_pdl, ncw;      // ncw: consumer warps (blockDim / 32 - 1)
     uint32_t       off_aq64, off_aq128, off_ad, off_s32, off_s16, off_ring;   // 0 = layout not needed (aq*, s*)
     const uint8_t *pf_ptr;
     unsigned long long pf_bytes;
@@ -131,6 +130,70 @@ __device__ __forceinline__ float item_q45k(const uint8_t *row, int it, const uin
     return (d * da) * (float)P - (dmin * da) * (float)M;
 }
 
+// Whole 256-weight block per lane (16 lanes walk one row, the two half-warps take two rows of the stage at once): the 16-byte
+// header, the 6-bit scale unpack, d/dmin and the activation scale are paid once per 256 weights instead of once per 64
+// (~54 instead of ~80 instructions per 64 weights), and one shuffle tree reduces two rows.
+// Activations: aq at 272 bytes per block (256 + 16 pad: conflict-free 128-bit loads at lane stride), s32 8 x int16 per block.
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a16x2, uint32_t b8, int c) {   // a.lo16*b.byte2 + a.hi16*b.byte3
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8), "r"(c));
+    return d;
+}
+template <bool Q5>
+__device__ __forceinline__ float block_q45k(const uint8_t *b, const uint8_t *ap, uint4 sums, float da) {
+    const uint4 hdr = *(const uint4 *)b;
+    const uint32_t sc_lo = hdr.y & 0x3f3f3f3fu, mn_lo = hdr.z & 0x3f3f3f3fu;
+    const uint32_t sc_hi = (hdr.w & 0x0f0f0f0fu) | ((hdr.y >> 2) & 0x30303030u);
+    const uint32_t mn_hi = ((hdr.w >> 4) & 0x0f0f0f0fu) | ((hdr.z >> 2) & 0x30303030u);
+    uint4 ha, hb;
+    if (Q5) { ha = *(const uint4 *)(b + 16); hb = *(const uint4 *)(b + 32); }
+    int P = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const uint8_t *qp = b + (Q5 ? 48 : 16) + g * 32;
+        const uint4 qa = *(const uint4 *)qp, qb = *(const uint4 *)(qp + 16);
+        const uint4 a0 = *(const uint4 *)(ap + g * 64), a1 = *(const uint4 *)(ap + g * 64 + 16);
+        const uint4 a2 = *(const uint4 *)(ap + g * 64 + 32), a3 = *(const uint4 *)(ap + g * 64 + 48);
+        int sA, sB;
+        if (!Q5) {
+            int s0 = __dp4a((int)(qa.x & 0x0f0f0f0fu), (int)a0.x, 0), s1 = __dp4a((int)(qa.y & 0x0f0f0f0fu), (int)a0.y, 0);
+            s0 = __dp4a((int)(qa.z & 0x0f0f0f0fu), (int)a0.z, s0); s1 = __dp4a((int)(qa.w & 0x0f0f0f0fu), (int)a0.w, s1);
+            s0 = __dp4a((int)(qb.x & 0x0f0f0f0fu), (int)a1.x, s0); s1 = __dp4a((int)(qb.y & 0x0f0f0f0fu), (int)a1.y, s1);
+            s0 = __dp4a((int)(qb.z & 0x0f0f0f0fu), (int)a1.z, s0); s1 = __dp4a((int)(qb.w & 0x0f0f0f0fu), (int)a1.w, s1);
+            sA = s0 + s1;
+            int t0 = dp4a_us(qa.x & 0xf0f0f0f0u, a2.x, 0), t1 = dp4a_us(qa.y & 0xf0f0f0f0u, a2.y, 0);      // high nibbles in place: 16x, exact
+            t0 = dp4a_us(qa.z & 0xf0f0f0f0u, a2.z, t0); t1 = dp4a_us(qa.w & 0xf0f0f0f0u, a2.w, t1);
+            t0 = dp4a_us(qb.x & 0xf0f0f0f0u, a3.x, t0); t1 = dp4a_us(qb.y & 0xf0f0f0f0u, a3.y, t1);
+            t0 = dp4a_us(qb.z & 0xf0f0f0f0u, a3.z, t0); t1 = dp4a_us(qb.w & 0xf0f0f0f0u, a3.w, t1);
+            sB = (t0 + t1) >> 4;
+        } else {
+            const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const uint32_t hw[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const uint32_t al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const uint32_t ah[8] = {a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+            int s0 = 0, s1 = 0, t0 = 0, t1 = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t hsh = hw[i] >> (2 * g);
+                const uint32_t lo = (qw[i] & 0x0f0f0f0fu) | ((hsh << 4) & 0x10101010u);
+                const uint32_t hi = ((qw[i] >> 4) & 0x0f0f0f0fu) | ((hsh << 3) & 0x10101010u);
+                if (i & 1) { s1 = __dp4a((int)lo, (int)al[i], s1); t1 = __dp4a((int)hi, (int)ah[i], t1); }
+                else       { s0 = __dp4a((int)lo, (int)al[i], s0); t0 = __dp4a((int)hi, (int)ah[i], t0); }
+            }
+            sA = s0 + s1; sB = t0 + t1;
+        }
+        const uint32_t scw = g < 2 ? sc_lo : sc_hi;
+        const int sh = (g & 1) * 16;
+        P += (int)((scw >> sh) & 0xffu) * sA + (int)((scw >> (sh + 8)) & 0xffu) * sB;
+    }
+    int M = dp2a_lo_su(sums.x, mn_lo, 0);
+    M = dp2a_hi_su(sums.y, mn_lo, M);
+    M = dp2a_lo_su(sums.z, mn_hi, M);
+    M = dp2a_hi_su(sums.w, mn_hi, M);
+    const float d = half_bits_to_float(hdr.x), dmin = half_bits_to_float(hdr.x >> 16);
+    return (d * da) * (float)P - (dmin * da) * (float)M;
+}
+
 // ---------------------------------------------------------------------------------------------- Q6_K
 // item = 128 weights (half h of a 210-byte block: ql 64 B at 64h, qh 32 B at 128+32h, int8 scales 8 B at 192+8h, half d at 208).
 // Blocks are only 2-byte aligned: every 4-byte word is fetched as two aligned words and a PRMT whose selector is computed
@@ -190,6 +253,7 @@ __device__ __forceinline__ float item_q6k(const uint8_t *row, int it, const uint
 // f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref
 #define PROFQ(slot) do { if (p.prof && lane == 0 && warp == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[(size_t)blockIdx.x * 32 + (slot)] = t_; } } while (0)
 __device__ __forceinline__ void bs1_quantize(const Bs1Params &p, uint8_t *smem, int warp, int lane, float norm_scale) {
+    const int BS1_NCW = p.ncw;
     const int nchunk = p.K >> 8;
     float *s_ad = (float *)(smem + p.off_ad);
     int16_t *s_s32 = (int16_t *)(smem + p.off_s32), *s_s16 = (int16_t *)(smem + p.off_s16);
@@ -228,18 +292,19 @@ __device__ __forceinline__ void bs1_quantize(const Bs1Params &p, uint8_t *smem, 
             if (p.off_s16 && (lane & 1) == 0) s_s16[b * 16 + (lane >> 1)] = (int16_t)pair;
             if (p.off_s32 && (lane & 3) == 0) s_s32[b * 8 + (lane >> 2)] = (int16_t)quad;
             if (lane == 0) s_ad[b] = d;
-            if (p.off_aq64)  *(uint2 *)(smem + p.off_aq64 + (e0 >> 6) * 80 + (e0 & 63)) = qp;
+            if (p.off_aq64)  *(uint2 *)(smem + p.off_aq64 + (e0 >> 8) * 272 + (e0 & 255)) = qp;
             if (p.off_aq128) *(uint2 *)(smem + p.off_aq128 + (e0 >> 7) * 144 + (e0 & 127)) = qp;
         }
     }
 }
 
 template <int TYPES>
-__global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1Params p) {
+__global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const Bs1Params p) {
+    const int BS1_NCW = p.ncw, BS1_THREADS = (p.ncw + 1) * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full  = (uint64_t *)smem;                  // [32]
     uint64_t *empty = full + BS1_MAX_STAGES;             // [32]
-    double *  s_red = (double *)(empty + BS1_MAX_STAGES);    // [16]
+    double *  s_red = (double *)(empty + BS1_MAX_STAGES);    // [32]
     uint8_t * ring  = smem + p.off_ring;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, c = blockIdx.x;
@@ -345,7 +410,7 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
     const uint32_t *s32 = (const uint32_t *)(smem + p.off_s32);
     const uint4 *s16 = (const uint4 *)(smem + p.off_s16);
     const float *ad = (const float *)(smem + p.off_ad);
-    const int nit64 = p.K >> 6, nit128 = p.K >> 7;
+    const int nblk = p.K >> 8, nit128 = p.K >> 7;
 #pragma unroll 1
     for (int use = 0; use * ns < nchunks; use++) {
 #pragma unroll 1
@@ -364,28 +429,52 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
             const int ty = sg.type;
             mbar_wait(&full[st], use & 1);
             if (i == 0) PROF(6);
+            if ((TYPES & (TB_Q4_K | TB_Q5_K)) && ((TYPES & TB_Q6_K) == 0 || ty != B200_TYPE_Q6_K)) {
+                // Q4_K / Q5_K: two rows per pass, one per half-warp, a whole block per lane
+                const bool q5 = (TYPES & TB_Q5_K) && (TYPES == TB_Q5_K || ty == B200_TYPE_Q5_K);
+                const int sub = lane >> 4, bl = lane & 15;
+                const uint4 *sums4 = (const uint4 *)s32;
+                const uint32_t bbytes = q5 ? 176u : 144u;
 #pragma unroll 1
-            for (int r = 0; r < nr; r++, rowp += sg.rb) {
-                float acc = 0.0f;
-                if ((TYPES & TB_Q4_K) && (TYPES == TB_Q4_K || ty == B200_TYPE_Q4_K)) {
+                for (int r = 0; r < nr; r += 2) {
+                    const bool mine = r + sub < nr;
+                    const uint8_t *rp = rowp + (size_t)(r + (mine ? sub : 0)) * sg.rb;
+                    float acc = 0.0f;
 #pragma unroll 1
-                    for (int it = lane; it < nit64; it += 32) acc += item_q45k<false>(rowp, it, aq64, s32, ad);
-                } else if ((TYPES & TB_Q5_K) && (TYPES == TB_Q5_K || ty == B200_TYPE_Q5_K)) {
+                    for (int blk = bl; blk < nblk; blk += 16) {
+                        const uint8_t *b = rp + blk * bbytes;
+                        const uint8_t *ap = aq64 + blk * 272;
+                        if ((TYPES & TB_Q5_K) && q5) acc += block_q45k<true>(b, ap, sums4[blk], ad[blk]);
+                        else if (TYPES & TB_Q4_K) acc += block_q45k<false>(b, ap, sums4[blk], ad[blk]);
+                    }
+                    if (r + 2 >= nr) {                   // stage bytes consumed: hand it back before the reduction
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[st]);
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (bl == 0 && mine) {
+                        const int o = row0 + r + sub;
+                        if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
+                        sg.dst[o] = acc;
+                    }
+                }
+            } else if (TYPES & TB_Q6_K) {
 #pragma unroll 1
-                    for (int it = lane; it < nit64; it += 32) acc += item_q45k<true>(rowp, it, aq64, s32, ad);
-                } else if (TYPES & TB_Q6_K) {
+                for (int r = 0; r < nr; r++, rowp += sg.rb) {
+                    float acc = 0.0f;
 #pragma unroll 1
                     for (int it = lane; it < nit128; it += 32) acc += item_q6k(rowp, it, aq128, s16, ad);
-                }
-                if (r == nr - 1) {                       // stage bytes consumed: hand it back before the reduction
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[st]);
-                }
-                acc = warp_reduce_sum(acc);
-                if (lane == 0) {
-                    const int o = row0 + r;
-                    if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
-                    sg.dst[o] = acc;
+                    if (r == nr - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[st]);
+                    }
+                    acc = warp_reduce_sum(acc);
+                    if (lane == 0) {
+                        const int o = row0 + r;
+                        if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
+                        sg.dst[o] = acc;
+                    }
                 }
             }
             if (i == 0) PROF(7);
@@ -395,7 +484,7 @@ __global__ void __launch_bounds__(BS1_THREADS, 2) b200_gemv_bs1_kernel(const Bs1
 #undef PROF
 }
 
-int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0;
+int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0, g_bs1_warps = 0;
 bool g_bs1_env = false;
 
 template <int TYPES>
@@ -408,7 +497,7 @@ int bs1_launch_t(b200_ctx *ctx, const Bs1Params &p, int grid, size_t smem_bytes)
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(BS1_THREADS);
+    cfg.blockDim = dim3((unsigned)(p.ncw + 1) * 32);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -434,6 +523,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         if (const char *e = getenv("GGML_B200_BS1_CTAS")) g_bs1_ctas = atoi(e);          // CTAs per SM (1 or 2; default 2)
         if (const char *e = getenv("GGML_B200_BS1_SMEM_KB")) g_bs1_smem_kb = atoi(e);    // shared memory per CTA
         if (const char *e = getenv("GGML_B200_BS1_OFF")) g_bs1_off = atoi(e);
+        if (const char *e = getenv("GGML_B200_BS1_WARPS")) g_bs1_warps = atoi(e);       // 16 or 32 warps per CTA (default 32)
         g_bs1_env = true;
     }
     if (g_bs1_off || nseg < 1 || nseg > GEMV_MAX_SEG || K <= 0 || (K & 255) || K > 65536) return 0;
@@ -451,9 +541,9 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     p.nseg = nseg; p.K = (int)K; p.act_mode = ga.mode; p.x = ga.x; p.x2 = ga.x2; p.eps = ga.eps;
     p.w_const = w_const ? 1 : 0; p.use_pdl = ctx->opt_pdl;
     // shared memory: barriers | s_red | aq64 | aq128 | d | s32 | s16 | ring
-    uint32_t off = 2 * BS1_MAX_STAGES * 8 + 16 * 8;
+    uint32_t off = 2 * BS1_MAX_STAGES * 8 + 32 * 8;
     const bool need64 = (mask & (TB_Q4_K | TB_Q5_K)) != 0, need128 = (mask & TB_Q6_K) != 0;
-    if (need64)  { p.off_aq64 = off;  off += (uint32_t)(K / 64) * 80;   off = (off + 15) & ~15u; }
+    if (need64)  { p.off_aq64 = off;  off += (uint32_t)(K / 256) * 272; off = (off + 15) & ~15u; }
     if (need128) { p.off_aq128 = off; off += (uint32_t)(K / 128) * 144; off = (off + 15) & ~15u; }
     p.off_ad = off; off += (uint32_t)(K / 256) * 4; off = (off + 15) & ~15u;
     if (need64)  { p.off_s32 = off; off += (uint32_t)(K / 32) * 2; off = (off + 15) & ~15u; }
@@ -475,13 +565,20 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         g.W = segs[s].W; g.dst = segs[s].dst; g.residual = segs[s].residual; g.expert_id = segs[s].expert_id; g.expert_stride = segs[s].expert_stride;
         g.rb = (uint32_t)segs[s].rb; g.type = segs[s].type; g.N = (int)segs[s].N;
         int R = (int)(target / g.rb);
-        g.R = R < 1 ? 1 : (R > 8 ? 8 : R);
+        R = R < 1 ? 1 : (R > 8 ? 8 : R);
+        if (g.type != B200_TYPE_Q6_K) {                  // pair decoder: even number of rows per stage while two rows stay <= 16 KB
+            if (R < 2 && 2 * (size_t)g.rb <= 16384) R = 2;
+            if (R > 2) R &= ~1;
+        }
+        g.R = R;
         const uint32_t sb = (uint32_t)(((size_t)g.R * g.rb + 32 + 127) & ~(size_t)127);       // +16 misalignment, +16 over-read
         stage = sb > stage ? sb : stage;
     }
     int ns = (int)(ring_budget / stage);
     if (ns > BS1_MAX_STAGES) ns = BS1_MAX_STAGES;
-    if (ns >= BS1_NCW) ns = ns / BS1_NCW * BS1_NCW;      // every consumer warp owns the same number of stages
+    const int ncw = g_bs1_warps == 16 ? 15 : 31;
+    p.ncw = ncw;
+    if (ns >= ncw) ns = ns / ncw * ncw;                  // every consumer warp owns the same number of stages
     if (ns < 2) return 0;
     p.nstages = ns; p.stage_bytes = stage;
     const size_t smem_bytes = off + (size_t)ns * stage;
