@@ -114,10 +114,17 @@ int b200_synchronize(b200_ctx *ctx) {
 
 int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     std::string k(key);
+    int *slot = k == "fusion" ? &ctx->opt_fusion : k == "pdl" ? &ctx->opt_pdl : k == "l2_prefetch" ? &ctx->opt_l2_prefetch :
+                k == "debug_skip" ? &ctx->opt_debug_skip : nullptr;
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
-    else if (k == "fusion") ctx->opt_fusion = value;
-    else if (k == "pdl") ctx->opt_pdl = value;
-    else if (k == "l2_prefetch") ctx->opt_l2_prefetch = value;
+    else if (slot) {
+        if (*slot != value) {                 // captured graphs bake these options in: drop them
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(ctx->stream);
+            graph_cache_free(ctx);
+        }
+        *slot = value;
+    }
     else if (k == "gemm_desc_swap") g_gemm_desc_swap = value;
     else { b200_set_error("unknown option %s", key); return B200_ERR_UNSUPPORTED; }
     return B200_OK;

@@ -127,7 +127,8 @@ struct b200_ctx {
     int           opt_cuda_graphs = 0;
     int           opt_fusion      = 2;      // 0 off, 1 two-op fusions, 2 + llama layer fusions for decode ubatches
     int           opt_pdl         = 0;
-    int           opt_l2_prefetch = 1;
+    int           opt_l2_prefetch = 0;      // L2 look-ahead of the next matmul's weights: measured neutral on B200 (profiles/r1_gemv_diag.md), off
+    int           opt_debug_skip  = 0;      // timing experiments only: bit 0 flash_attn, 1 rope+store, 2 GEMV are not launched
     GraphCache *  graph_cache = nullptr;
     b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
     bool          capturing = false;

@@ -400,8 +400,9 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
 }
 
 static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
-    // timing experiments only (results are then wrong): GGML_B200_DEBUG_SKIP bit 0 flash_attn, 1 rope+store, 2 GEMV
-    static const int dbg_skip = getenv("GGML_B200_DEBUG_SKIP") ? atoi(getenv("GGML_B200_DEBUG_SKIP")) : 0;
+    // timing experiments only (results are then wrong): option "debug_skip" / GGML_B200_DEBUG_SKIP bit 0 flash_attn, 1 rope+store, 2 GEMV
+    static const int env_skip = getenv("GGML_B200_DEBUG_SKIP") ? atoi(getenv("GGML_B200_DEBUG_SKIP")) : 0;
+    const int dbg_skip = env_skip | ctx->opt_debug_skip;
     for (const ExecNode &e : list) {
         int rc;
         if (dbg_skip) {
