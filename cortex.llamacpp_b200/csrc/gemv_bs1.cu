@@ -37,7 +37,8 @@ struct Bs1Seg {
     const int32_t *expert_id;
     size_t         expert_stride;
     uint32_t       rb;                  // bytes per row
-    int            type, N, R;          // rows per ring stage
+    int            type, N, R;          // rows per ring stage (power of two)
+    int            q, rem, lgR;         // N = q * grid + rem: CTA c owns rows [c*q + min(c, rem), (c+1)*q + min(c+1, rem))
 };
 
 struct Bs1Params {
@@ -252,49 +253,99 @@ __device__ __forceinline__ float item_q6k(const uint8_t *row, int it, const uint
 // ---------------------------------------------------------------------------------------------- prologue
 // f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref
 #define PROFQ(slot) do { if (p.prof && lane == 0 && warp == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[(size_t)blockIdx.x * 32 + (slot)] = t_; } } while (0)
-__device__ __forceinline__ void bs1_quantize(const Bs1Params &p, uint8_t *smem, int warp, int lane, float norm_scale) {
-    const int BS1_NCW = p.ncw;
-    const int nchunk = p.K >> 8;
+// one warp: 256 activations (lane owns v[0..7]) -> q8_K block b in the shared-memory layouts
+__device__ __forceinline__ void bs1_quant_chunk(const Bs1Params &p, uint8_t *smem, int b, int lane, const float (&v)[8]) {
     float *s_ad = (float *)(smem + p.off_ad);
     int16_t *s_s32 = (int16_t *)(smem + p.off_s32), *s_s16 = (int16_t *)(smem + p.off_s16);
-    for (int b0 = warp; b0 < nchunk; b0 += 2 * BS1_NCW) {
-        float4 xa[2][2], xb[2][2];                       // two 256-element chunks in flight per warp
+    const int e0 = b * 256 + lane * 8;
+    uint2 qp; float d; int pair;
+    warp_quant_q8k(v, lane, qp, d, pair);                // pair: 16-element sum, valid in even lanes
+    const int quad = pair + __shfl_xor_sync(0xffffffffu, pair, 2);
+    if (p.off_s16 && (lane & 1) == 0) s_s16[b * 16 + (lane >> 1)] = (int16_t)pair;
+    if (p.off_s32 && (lane & 3) == 0) s_s32[b * 8 + (lane >> 2)] = (int16_t)quad;
+    if (lane == 0) s_ad[b] = d;
+    if (p.off_aq64)  *(uint2 *)(smem + p.off_aq64 + (e0 >> 8) * 272 + (e0 & 255)) = qp;
+    if (p.off_aq128) *(uint2 *)(smem + p.off_aq128 + (e0 >> 7) * 144 + (e0 & 127)) = qp;
+}
+__device__ __forceinline__ void bs1_apply_mode(const Bs1Params &p, float (&v)[8], const float4 &w0, const float4 &w1, float norm_scale) {
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    if (p.act_mode == ACT_F32_NORM) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fmul_rn(v[j], norm_scale), w[j]);
+    } else if (p.act_mode == ACT_F32_SWIGLU) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fdiv_rn(v[j], 1.0f + expf(-v[j])), w[j]);
+    }
+}
+// sum over the consumer warps of per-warp partial sums of squares -> 1/rms (rms_norm like glue.cu / the CPU oracle: sum in double)
+__device__ __forceinline__ float bs1_norm_scale(const Bs1Params &p, double *s_red, double s, int warp, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_red[warp] = s;
+    named_bar_sync(2, p.ncw * 32);
+    // every warp adds the <= 31 partial sums with the same shuffle tree (fixed order => identical on all warps and CTAs)
+    double t = lane < p.ncw ? s_red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)p.K), p.eps)));
+}
+// f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref.
+// K <= 2 * 256 * ncw (every llama shape at batch 1): each warp holds its <= 2 blocks in registers, so x is read ONCE even
+// when the rms_norm needs the sum of squares of the whole vector first.
+__device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, double *s_red, int warp, int lane) {
+    const int nchunk = p.K >> 8, ncw = p.ncw;
+    if (nchunk <= 2 * ncw) {
+        float4 xa[2][2], xb[2][2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int b = b0 + u * BS1_NCW;
+            const int b = warp + u * ncw;
+            xa[u][0] = xa[u][1] = xb[u][0] = xb[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (b < nchunk) {
                 const int e0 = b * 256 + lane * 8;
                 xa[u][0] = *(const float4 *)(p.x + e0); xa[u][1] = *(const float4 *)(p.x + e0 + 4);
                 if (p.act_mode != ACT_F32) { xb[u][0] = *(const float4 *)(p.x2 + e0); xb[u][1] = *(const float4 *)(p.x2 + e0 + 4); }
             }
         }
+        float norm_scale = 1.0f;
+        if (p.act_mode == ACT_F32_NORM) {
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const float v[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) s += (double)__fmul_rn(v[j], v[j]);
+            }
+            norm_scale = bs1_norm_scale(p, s_red, s, warp, lane);
+        }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int b = b0 + u * BS1_NCW;
-            if (b >= nchunk) break;
-            const int e0 = b * 256 + lane * 8;
-            float v[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
-            if (p.act_mode != ACT_F32) {
-                const float w[8] = {xb[u][0].x, xb[u][0].y, xb[u][0].z, xb[u][0].w, xb[u][1].x, xb[u][1].y, xb[u][1].z, xb[u][1].w};
-                if (p.act_mode == ACT_F32_NORM) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fmul_rn(v[j], norm_scale), w[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fdiv_rn(v[j], 1.0f + expf(-v[j])), w[j]);
-                }
+            const int b = warp + u * ncw;
+            if (b < nchunk) {
+                float v[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
+                if (p.prof) { asm volatile("" : "+f"(v[0])); if (u == 0) PROFQ(24); }
+                bs1_apply_mode(p, v, xb[u][0], xb[u][1], norm_scale);
+                bs1_quant_chunk(p, smem, b, lane, v);
+                if (p.prof && u == 0) PROFQ(25);
             }
-            if (p.prof) { asm volatile("" : "+f"(v[0])); if (u == 0) PROFQ(24); }
-            uint2 qp; float d; int pair;
-            warp_quant_q8k(v, lane, qp, d, pair);                // pair: 16-element sum, valid in even lanes
-            if (p.prof) { asm volatile("" : "+f"(d)); if (u == 0) PROFQ(25); }
-            const int quad = pair + __shfl_xor_sync(0xffffffffu, pair, 2);
-            if (p.off_s16 && (lane & 1) == 0) s_s16[b * 16 + (lane >> 1)] = (int16_t)pair;
-            if (p.off_s32 && (lane & 3) == 0) s_s32[b * 8 + (lane >> 2)] = (int16_t)quad;
-            if (lane == 0) s_ad[b] = d;
-            if (p.off_aq64)  *(uint2 *)(smem + p.off_aq64 + (e0 >> 8) * 272 + (e0 & 255)) = qp;
-            if (p.off_aq128) *(uint2 *)(smem + p.off_aq128 + (e0 >> 7) * 144 + (e0 & 127)) = qp;
         }
+        return;
+    }
+    // long rows: stream the blocks (x is read twice in rms_norm mode)
+    float norm_scale = 1.0f;
+    if (p.act_mode == ACT_F32_NORM) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < p.K; i += ncw * 32) { const float v = p.x[i]; s += (double)__fmul_rn(v, v); }
+        norm_scale = bs1_norm_scale(p, s_red, s, warp, lane);
+    }
+#pragma unroll 1
+    for (int b = warp; b < nchunk; b += ncw) {
+        const int e0 = b * 256 + lane * 8;
+        const float4 a0 = *(const float4 *)(p.x + e0), a1 = *(const float4 *)(p.x + e0 + 4);
+        float4 w0 = a0, w1 = a1;
+        if (p.act_mode != ACT_F32) { w0 = *(const float4 *)(p.x2 + e0); w1 = *(const float4 *)(p.x2 + e0 + 4); }
+        float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        bs1_apply_mode(p, v, w0, w1, norm_scale);
+        bs1_quant_chunk(p, smem, b, lane, v);
     }
 }
 
@@ -322,10 +373,10 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
     for (int s = 0; s < GEMV_MAX_SEG; s++) {
         lo[s] = hi[s] = 0;
         if (s < p.nseg) {
-            lo[s] = (int)(((unsigned)p.seg[s].N * (unsigned)c) / (unsigned)G);
-            hi[s] = (int)(((unsigned)p.seg[s].N * (unsigned)(c + 1)) / (unsigned)G);
+            lo[s] = c * p.seg[s].q + min(c, p.seg[s].rem);
+            hi[s] = (c + 1) * p.seg[s].q + min(c + 1, p.seg[s].rem);
         }
-        ch0[s + 1] = ch0[s] + (s < p.nseg ? (hi[s] - lo[s] + p.seg[s].R - 1) / p.seg[s].R : 0);
+        ch0[s + 1] = ch0[s] + (s < p.nseg ? (hi[s] - lo[s] + p.seg[s].R - 1) >> p.seg[s].lgR : 0);
     }
     const int nchunks = ch0[GEMV_MAX_SEG];
 
@@ -384,23 +435,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
     // ---------------------------------------------------------------------- consumers: prologue
     if (p.use_pdl) pdl_wait();          // the activations belong to the previous kernels
     if (warp == 0) PROF(4);
-    {
-        float norm_scale = 1.0f;
-        if (p.act_mode == ACT_F32_NORM) {
-            // rms_norm like glue.cu / the CPU oracle: sum of squares in double, fixed reduction order
-            double s = 0.0;
-            for (int i = threadIdx.x; i < p.K; i += BS1_NCW * 32) { const float v = p.x[i]; s += (double)__fmul_rn(v, v); }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_red[warp] = s;
-            named_bar_sync(2, BS1_NCW * 32);
-            double t = 0.0;
-#pragma unroll 1
-            for (int i = 0; i < BS1_NCW; i++) t += s_red[i];
-            norm_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)p.K), p.eps)));
-        }
-        bs1_quantize(p, smem, warp, lane, norm_scale);
-    }
+    bs1_prologue(p, smem, s_red, warp, lane);
     named_bar_sync(1, BS1_THREADS);     // activations complete + mbarriers initialised (producer arrived long ago)
     if (warp == 0) PROF(5);
     if (nchunks == 0) return;
@@ -566,11 +601,10 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         g.rb = (uint32_t)segs[s].rb; g.type = segs[s].type; g.N = (int)segs[s].N;
         int R = (int)(target / g.rb);
         R = R < 1 ? 1 : (R > 8 ? 8 : R);
-        if (g.type != B200_TYPE_Q6_K) {                  // pair decoder: even number of rows per stage while two rows stay <= 16 KB
-            if (R < 2 && 2 * (size_t)g.rb <= 16384) R = 2;
-            if (R > 2) R &= ~1;
-        }
-        g.R = R;
+        if (g.type != B200_TYPE_Q6_K && R < 2 && 2 * (size_t)g.rb <= 16384) R = 2;      // pair decoder: two rows per stage while they stay <= 16 KB
+        int lg = 0;
+        while ((2 << lg) <= R) lg++;
+        g.R = 1 << lg; g.lgR = lg;
         const uint32_t sb = (uint32_t)(((size_t)g.R * g.rb + 32 + 127) & ~(size_t)127);       // +16 misalignment, +16 over-read
         stage = sb > stage ? sb : stage;
     }
@@ -596,6 +630,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     for (int s = 1; s < nseg; s++) min_rows = segs[s].N < min_rows ? segs[s].N : min_rows;
     int64_t grid = (int64_t)ctx->sm_count * cps;
     if (grid > min_rows) grid = min_rows;                // every CTA gets at least one row of every segment
+    for (int s = 0; s < nseg; s++) { p.seg[s].q = (int)(segs[s].N / grid); p.seg[s].rem = (int)(segs[s].N % grid); }
     int rc;
     switch (mask) {
         case TB_Q4_K: rc = bs1_launch_t<TB_Q4_K>(ctx, p, (int)grid, smem_bytes); break;
