@@ -97,6 +97,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     graph_cache_free(ctx);
     b200_comm_destroy(ctx);
+    if (ctx->fattn_counters) cudaFree(ctx->fattn_counters);
     for (int i = 0; i < SCRATCH_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

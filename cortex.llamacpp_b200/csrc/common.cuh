@@ -130,6 +130,7 @@ struct b200_ctx {
     int           opt_l2_prefetch = 0;      // L2 look-ahead of the next matmul's weights: measured neutral on B200 (profiles/r1_gemv_diag.md), off
     int           opt_debug_skip  = 0;      // timing experiments only: bit 0 flash_attn, 1 rope+store, 2 GEMV are not launched
     GraphCache *  graph_cache = nullptr;
+    void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)
     b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
     bool          capturing = false;
     void *        prof_buf = nullptr;   // debug: per-CTA timestamps (b200_debug_set_prof)

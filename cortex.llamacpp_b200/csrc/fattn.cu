@@ -34,6 +34,7 @@ struct FaParams {
     const char *mask; uint64_t m_nb1;
     float *dst;
     float *part;                 // [tile][split][16][D + 2]
+    int *counters;               // [tile] arrivals of the KV splits (self-resetting); NULL: separate combine kernel
     int n_q, n_kv, H, Hkv, gq, HG, QC, n_headtiles, n_coltiles, n_splits, kv_per_split;
     float scale, softcap, max_bias, m0, m1;
     int n_head_log2;
@@ -377,6 +378,39 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
             if (d == 0) { pp[D] = M; pp[D + 1] = L; }
         }
     }
+    // ---- the LAST split of a tile to arrive merges all splits (log-sum-exp, fixed split order => deterministic):
+    //      saves the combine kernel and its launch boundary on the decode critical path ----
+    if (p.n_splits > 1 && p.counters) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int prev = atomicAdd(&p.counters[tile_id], 1);
+            s_last = prev == p.n_splits - 1;
+            if (s_last) p.counters[tile_id] = 0;           // ready for the next launch (CUDA-graph replay)
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const float *base = p.part + (uint64_t)tile_id * p.n_splits * 16 * (D + 2);
+        const uint64_t sstride = (uint64_t)16 * (D + 2);
+        for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
+            const int r = e / D, d = e % D;
+            const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+            if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) continue;
+            const float *rp = base + (uint64_t)r * (D + 2);
+            float M = -INFINITY;
+            for (int sp = 0; sp < p.n_splits; sp++) M = fmaxf(M, __ldcg(rp + sp * sstride + D));
+            float Lsum = 0.0f, acc = 0.0f;
+            for (int sp = 0; sp < p.n_splits; sp++) {
+                const float ms = __ldcg(rp + sp * sstride + D);
+                const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+                Lsum += __ldcg(rp + sp * sstride + D + 1) * f;
+                acc += __ldcg(rp + sp * sstride + d) * f;
+            }
+            p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / Lsum;
+        }
+    }
 }
 
 // merge of the KV splits: one WARP per (tile, query row); lanes first reduce the per-split (max, sum) pairs, then each lane
@@ -448,7 +482,7 @@ int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     cfg.numAttrs = p.use_pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ctx->launches++;
-    if (p.n_splits > 1) {
+    if (p.n_splits > 1 && !p.counters) {
         cfg.gridDim = dim3((unsigned)((n_tiles * 16 + 3) / 4));
         cfg.blockDim = dim3(128);
         cfg.dynamicSmemBytes = 0;
@@ -537,6 +571,16 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     if (ns > 1) {
         p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)n_tiles * ns * 16 * (D + 2) * 4);
         if (!p.part) return B200_ERR_ALLOC;
+        // merging the splits in the last-arriving CTA instead of a second kernel was measured SLOWER on B200 (471 vs 523 tok/s on
+        // Llama-3-8B bs1: a PDL kernel boundary costs ~1 us, the serialised fence + atomic + 128-thread merge costs more): off
+        static const int fuse_combine = getenv("GGML_B200_FA_FUSED_COMBINE") ? atoi(getenv("GGML_B200_FA_FUSED_COMBINE")) : 0;
+        if (fuse_combine && n_tiles <= 4096) {
+            if (!ctx->fattn_counters) {       // zeroed once; the kernel leaves every counter at zero again
+                if (cudaMalloc(&ctx->fattn_counters, 4096 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); ctx->fattn_counters = nullptr; }
+                else CUDA_TRY(cudaMemset(ctx->fattn_counters, 0, 4096 * sizeof(int)));
+            }
+            p.counters = (int *)ctx->fattn_counters;
+        }
     }
     const int kt = kv_kind(k.type), vt = kv_kind(v.type);
     if (D == 128) return launch_fa_types<128>(ctx, p, n_tiles, kt, vt);
