@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("GGML_B200_PDL", "1")))
     ap.add_argument("--fusion", type=int, default=2)
     ap.add_argument("--l2pf", type=int, default=0)
+    ap.add_argument("--no-batch", action="store_true", help="skip the bs32-decode / prefill legs")
     ap.add_argument("--tp-model", default="llama3-70b", help="N>1: model of the extra row-split tensor-parallel leg ('' = skip)")
     ap.add_argument("--tp-layers", type=int, default=0, help="debug: fewer layers in the TP leg (reported as INVALID)")
     a = ap.parse_args()
@@ -307,6 +308,15 @@ def main():
                                     "sample": "8 decode steps after a %d-token prompt, llama_decode on the reference ggml CPU backend" % DEPTH}
         except Exception as ex:           # the baseline is a report, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": host_threads(), "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
+    # ---------------------------------------------------------------- N = 1: the other two numbers of the metric (bs32 decode, prefill)
+    if world == 1 and not a.layers and not a.no_batch:
+        try:
+            g.keep.clear(); g.layers.clear()
+            torch.cuda.empty_cache()
+            line["batched"] = batch_legs(a, b200, lg, L, ctx, local, peak)
+        except Exception as ex:
+            line["batched"] = {"error": str(ex)[:300]}
+
     # ---------------------------------------------------------------- N > 1: row-split tensor-parallel leg
     if world > 1 and a.tp_model:
         try:
@@ -322,6 +332,72 @@ def main():
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def batch_legs(a, b200, lg, L, ctx, local, peak):
+    """BASELINE.json config #3 shape: Llama-3-8B Q4_K_M, n_parallel = 32 slots, q8_0 KV cache.  Two ubatches through the same
+    C ABI: (a) continuous-batching decode, 32 slots x 1 token at depth 512 per slot (weights read once per step: HBM roofline
+    = weights + the slots' KV); (b) a 512-token prefill ubatch (tcgen05 int8 GEMM + tensor-core flash attention: tensor
+    roofline, quoted against 2 x the measured bf16 peak because MEASURED_PEAKS.json holds no int8 number)."""
+    import torch
+    slots, depth, PP = 32, 512, 512
+    n_ctx = ((slots * depth + slots + 255) // 256 + 1) * 256
+    g = lg.LlamaGraph(b200, model=MODEL, ftype=FTYPE, kv="q8_0", n_ctx=n_ctx, device=local, max_tokens=PP)
+    g.fill_cache(slots * depth)
+    rng = np.random.default_rng(1)
+    e0, e1 = L.b200_event_create(local), L.b200_event_create(local)
+    out = {"kv": "q8_0", "slots": slots}
+
+    def timed(ops, reps, warm):
+        arr = (b200.Op * len(ops))(*ops)
+        n0 = ctx.launches()
+        b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "batched step"); ctx.sync()
+        launches = ctx.launches() - n0
+        for _ in range(warm):
+            b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "batched step")
+        ctx.sync()
+        L.b200_event_record(ctx.h, e0)
+        for _ in range(reps):
+            b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "batched step")
+        L.b200_event_record(ctx.h, e1)
+        L.b200_event_synchronize(e1)
+        return L.b200_event_elapsed_ms(e0, e1) / reps, int(launches)
+
+    def upload(emb, pos, mask, T):
+        g.inp_embd[:T * g.E] = torch.from_numpy(emb.reshape(-1)).cuda(local)
+        g.pos[:T] = torch.from_numpy(pos).cuda(local)
+        g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda(local)
+        torch.cuda.synchronize()
+
+    # (a) bs32 continuous-batching decode
+    n_kv = (slots * depth + slots + 255) // 256 * 256
+    emb, pos, mask, kv_head = g.set_inputs_slots_host(slots, depth, n_kv, rng)
+    upload(emb, pos, mask, slots)
+    ms, launches = timed(g.build(slots, kv_head, n_kv), max(8, a.steps // 4), 3)
+    kv_row = lg.row_size(g.kv_type, g.Hkv * g.D)
+    bytes_ = g.weight_bytes + 2 * g.L * slots * (depth + 1) * kv_row
+    out["bs32_decode"] = {"value": slots / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms, "depth_per_slot": depth, "gpu_launches_per_step": launches,
+                          "hbm_bytes_per_step": bytes_, "achieved_gbs": bytes_ / (ms / 1e3) / 1e9, "hbm_frac": bytes_ / (ms / 1e3) / 1e9 / peak,
+                          "assert_finite": bool(torch.isfinite(g.logits[:slots * g.V]).all().item())}
+    # (b) prefill: one 512-token ubatch into an empty region of the cache
+    emb, pos, mask = g.set_inputs_host(PP, 0, PP, rng)
+    upload(emb, pos, mask, PP)
+    ms, launches = timed(g.build(PP, 0, PP, n_outputs=1), max(4, a.steps // 8), 2)       # a prompt ubatch asks for the last token's logits only
+    flops = 2.0 * (g.weight_bytes_by_type and sum(nb / (lg.BLOCK[t][1] / lg.BLOCK[t][0]) for t, nb in g.weight_bytes_by_type.items())) * PP
+    flops -= 2.0 * g.V * g.E * (PP - 1)                        # logits for the last token only
+    flops += 4.0 * g.L * g.H * g.D * PP * PP / 2
+    bf16 = 1631.8
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    out["prefill_pp512"] = {"value": PP / (ms / 1e3), "unit": "tok/s", "ms_per_ubatch": ms, "gpu_launches_per_ubatch": launches, "flops_per_ubatch": flops,
+                            "achieved_tops": flops / (ms / 1e3) / 1e12, "peak_tops": 2 * bf16, "peak_note": "2 x measured bf16 burst (no int8 number in MEASURED_PEAKS.json)",
+                            "tensor_frac": flops / (ms / 1e3) / 1e12 / (2 * bf16),
+                            "assert_finite": bool(torch.isfinite(g.logits[:g.V]).all().item())}
+    g.keep.clear(); g.layers.clear()
+    torch.cuda.empty_cache()
+    return out
 
 
 def tp_leg(a, b200, lg, L, ctx, rank, world, local, peak):

@@ -237,7 +237,8 @@ struct SmemLayout {
     uint32_t pad[31];
 };
 
-template <int TYPE>
+// PARTIAL: the token tile may hold fewer than TN real tokens (decode-sized ubatches): drain only the accumulator columns in use
+template <int TYPE, bool PARTIAL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t gsm[];
     uint8_t *a_hi = gsm;                                   // [NSLOT][16 KB]
@@ -336,6 +337,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
         for (int c = 0; c < TN; c++) out[c] = 0.0f;
         RowMeta prev, cur;
         int pb = -1;
+        const int ncols_valid = min(TN, p.M - tok0);
+        const int last_c0 = ((ncols_valid + 31) / 32 - 1) * 32;     // last 32-column chunk of the accumulators that holds real tokens
 
         auto epilogue = [&](int b, const RowMeta &m) {
             const int pr = b & 1;
@@ -346,11 +349,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
             const float dd = m.d, dm = m.dmin;
 #pragma unroll
             for (int c0 = 0; c0 < TN; c0 += 32) {
+                if (PARTIAL && c0 > last_c0) continue;     // token columns beyond M (a 32-slot decode ubatch fills a quarter of the tile)
                 uint32_t hi[32], lo[32];
                 tmem_ld32(tmem + lane_addr + (uint32_t)pr * 256 + c0, hi);
                 tmem_ld32(tmem + lane_addr + (uint32_t)pr * 256 + 128 + c0, lo);
                 tmem_ld_wait();
-                if (c0 == TN - 32) {                       // accumulators are in registers: the tensor core may overwrite them
+                if (PARTIAL ? c0 == last_c0 : c0 == TN - 32) { // accumulators are in registers: the tensor core may overwrite them
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S->acc_empty[pr]);
@@ -429,9 +433,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
 }
 
 
-template <int TYPE>
-int launch_gemm(b200_ctx *ctx, const GemmParams &p, dim3 grid, size_t smem) {
-    auto kern = b200_gemm_i8_kernel<TYPE>;
+template <int TYPE, bool PARTIAL>
+int launch_gemm_t(b200_ctx *ctx, const GemmParams &p, dim3 grid, size_t smem) {
+    auto kern = b200_gemm_i8_kernel<TYPE, PARTIAL>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -441,6 +445,11 @@ int launch_gemm(b200_ctx *ctx, const GemmParams &p, dim3 grid, size_t smem) {
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
+}
+
+template <int TYPE>
+int launch_gemm(b200_ctx *ctx, const GemmParams &p, dim3 grid, size_t smem) {
+    return p.M % TN ? launch_gemm_t<TYPE, true>(ctx, p, grid, smem) : launch_gemm_t<TYPE, false>(ctx, p, grid, smem);
 }
 
 }  // namespace

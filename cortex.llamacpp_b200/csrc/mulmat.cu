@@ -118,7 +118,10 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     const size_t rb = b200_row_bytes(w.type, K);
     const bool w_const = (w.flags & B200_TENSOR_FLAG_WEIGHT) != 0;
     const int64_t nbatch = x.ne[2] * x.ne[3];
-    if (M <= 8) {
+    // up to this many columns the streaming GEMV (4 columns per launch, weights re-streamed per chunk) beats the tensor-core
+    // GEMM, whose per-super-block drain costs the same for 8 tokens as for 128 (measured: profiles/r1_batched.md)
+    static const int64_t gemv_max_m = getenv("GGML_B200_GEMV_MAX_M") ? atoi(getenv("GGML_B200_GEMV_MAX_M")) : 8;
+    if (M <= gemv_max_m) {
         // decode path: one fused launch per (batch) matmul -- activation quantisation happens in the GEMV prologue
         for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
             for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {

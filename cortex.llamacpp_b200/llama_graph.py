@@ -204,8 +204,10 @@ class LlamaGraph:
                     c[:n_cells * row_size(self.kv_type, HD)] = blk[:n_cells * row_size(self.kv_type, HD)]
         torch.cuda.synchronize(self.dev)
 
-    def build(self, n_tok, kv_head, n_kv):
-        """op list of ONE ubatch: n_tok tokens written at cell kv_head, attending over cells [0, n_kv)"""
+    def build(self, n_tok, kv_head, n_kv, n_outputs=None):
+        """op list of ONE ubatch: n_tok tokens written at cell kv_head, attending over cells [0, n_kv).  n_outputs: logits
+        are computed for the LAST n_outputs tokens only (llama.cpp's inp_out_ids: a prompt ubatch asks for one row,
+        llama-model.cpp:4196-4201; we apply the selection before the final norm); default all tokens -> self.logits[:n_out*V]"""
         b, T = self.b200, n_tok
         assert T <= self.max_tokens and n_kv <= self.n_ctx and kv_head + T <= self.n_ctx
         E, H, Hkv, D, FF, V = self.E, self.H, self.Hkv, self.D, self.FF, self.V
@@ -264,9 +266,11 @@ class LlamaGraph:
             else:
                 ops.append(b.make_op(b.OP_ADD, t(p(nxt), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), ffn_inp]))
             inp, other = nxt, (self.resid if nxt is self.resid2 else self.resid2)
-        ops.append(b.make_op(b.OP_RMS_NORM, t(p(self.cur), F32, [E, T]), [t(p(inp), F32, [E, T])], [1e-5]))
-        ops.append(b.make_op(b.OP_MUL, t(p(self.cur2), F32, [E, T]), [t(p(self.cur), F32, [E, T]), self.output_norm]))
-        ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.logits), F32, [V, T]), [self.output, t(p(self.cur2), F32, [E, T])]))
+        To = T if n_outputs is None else min(T, n_outputs)
+        off = (T - To) * E * 4
+        ops.append(b.make_op(b.OP_RMS_NORM, t(p(self.cur), F32, [E, To]), [t(p(inp) + off, F32, [E, To])], [1e-5]))
+        ops.append(b.make_op(b.OP_MUL, t(p(self.cur2), F32, [E, To]), [t(p(self.cur), F32, [E, To]), self.output_norm]))
+        ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.logits), F32, [V, To]), [self.output, t(p(self.cur2), F32, [E, To])]))
         return ops
 
     # ------------------------------------------------------------------------------------------------------------
@@ -279,6 +283,21 @@ class LlamaGraph:
         act = 4 * n_tok * (self.L * ((E + HD) + 2 * (E + KD) + (HD + E) + 2 * (E + FF) + (FF + E)) + (E + V))
         return dict(weights=self.weight_bytes, kv_read=kv_read, kv_write=kv_write, act=act,
                     total=self.weight_bytes + kv_read + kv_write + act)
+
+    def set_inputs_slots_host(self, n_slots, depth, n_kv, rng):
+        """continuous batching (n_parallel slots, one new token each): slot s owns cells [s*depth, (s+1)*depth) of the unified
+        cache (llama_kv_cache_unified keeps a sequence's prompt contiguous), the n_slots new tokens go to cells
+        [n_slots*depth, n_slots*depth + n_slots); mask row s allows its own cells and itself (llama-graph.cpp:1325 semantics)"""
+        T = n_slots
+        Tp = (T + 63) // 64 * 64
+        kv_head = n_slots * depth
+        emb = rng.standard_normal((T, self.E)).astype(np.float32)
+        pos = np.full(T, depth, np.int32)
+        mask = np.full((Tp, n_kv), -np.inf, np.float32)
+        for s_ in range(T):
+            mask[s_, s_ * depth:(s_ + 1) * depth] = 0.0
+            mask[s_, kv_head + s_] = 0.0
+        return emb, pos, mask, kv_head
 
     def set_inputs_host(self, n_tok, kv_head, n_kv, rng):
         """host-side inputs of one ubatch, as llama_context::set_inputs would produce: embeddings of the tokens
