@@ -44,6 +44,8 @@ struct GemmParams {
     float *dst; size_t dst_stride; // dst[tok * dst_stride + row]
     int raw_slots; uint32_t raw_row_bytes;     // per-row slot in the raw ring
     int swap_lbo_sbo;
+    int sb_per_split;              // split-K: blockIdx.z covers super-blocks [z*sb_per_split, ...); partial results go to dst_partial
+    float *dst_partial;            // [ksplit][M][N] (row stride N) when gridDim.z > 1
 };
 
 // ---- tcgen05 / TMEM primitives (inline PTX; SASS: UTCIMMA, LDTM, UTCBAR, ...) ------------------------------------
@@ -249,8 +251,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TM, tok0 = blockIdx.y * TN;
-    const int nsb = p.K / 256;
     constexpr int BLK = TYPE == B200_TYPE_Q4_K ? 144 : TYPE == B200_TYPE_Q5_K ? 176 : 210;
+    // split-K (small token counts leave most SMs idle otherwise): this CTA sees a K-slice as a GEMM of its own over shifted views
+    const int sb0 = (int)blockIdx.z * p.sb_per_split;
+    const int nsb = min(p.sb_per_split, p.K / 256 - sb0);
+    const uint8_t *const Wv = p.W + (size_t)sb0 * BLK;
+    const uint8_t *const Bqv = p.Bq + (size_t)(2 * sb0) * HALF_BYTES;
+    const float *const Bdv = p.Bd + (size_t)sb0 * p.Mpad;
+    const int16_t *const Bs32v = p.Bs32 + (size_t)sb0 * p.Mpad * 8;
+    const int16_t *const Bs16v = p.Bs16 + (size_t)sb0 * p.Mpad * 16;
+    float *const dstv = gridDim.z > 1 ? p.dst_partial + (size_t)blockIdx.z * p.M * p.N : p.dst;
+    const size_t dst_stride = gridDim.z > 1 ? (size_t)p.N : p.dst_stride;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; i++) { mbar_init(&S->raw_full[i], 1); mbar_init(&S->raw_empty[i], 4); }
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int r = lane + 32 * i;
-                const uint8_t *src = p.W + (size_t)(row0 + r) * p.rb + (size_t)b * BLK;
+                const uint8_t *src = Wv + (size_t)(row0 + r) * p.rb + (size_t)b * BLK;
                 const uint32_t extra = (uint32_t)((uintptr_t)src & 15);
                 mybytes += (extra + BLK + 15u) & ~15u;
             }
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int r = lane + 32 * i;
-                const uint8_t *src = p.W + (size_t)(row0 + r) * p.rb + (size_t)b * BLK;
+                const uint8_t *src = Wv + (size_t)(row0 + r) * p.rb + (size_t)b * BLK;
                 const uint32_t extra = (uint32_t)((uintptr_t)src & 15);
                 const uint32_t bytes = (extra + BLK + 15u) & ~15u;
                 bulk_g2s(raw + ((size_t)rs * TM + r) * p.raw_row_bytes, src - extra, bytes, &S->raw_full[rs]);
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
     } else if (warp == 3) {
         // ------------------------------------------------------------ producer: activation tiles (one 16 KB bulk copy per half-stage)
         if (lane == 0) {
-            const uint8_t *src = p.Bq + (size_t)blockIdx.y * (p.K / KH) * HALF_BYTES;
+            const uint8_t *src = Bqv + (size_t)blockIdx.y * (p.K / KH) * HALF_BYTES;
             for (int g = 0; g < 2 * nsb; g++) {
                 const int slot = g % NSLOT;
                 if (g >= NSLOT) mbar_wait(&S->ab_empty[slot], ((g / NSLOT) - 1) & 1);
@@ -363,9 +374,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
                 for (int j = 0; j < 32; j++) {
                     const int c = c0 + j;
                     int P = ((int)hi[j] << 7) + (int)lo[j];
-                    const float da = __ldg(p.Bd + rowb + c);
+                    const float da = __ldg(Bdv + rowb + c);
                     if (TYPE == B200_TYPE_Q6_K) {
-                        const uint4 s0 = __ldg((const uint4 *)(p.Bs16 + (rowb + c) * 16)), s1 = __ldg((const uint4 *)(p.Bs16 + (rowb + c) * 16 + 8));
+                        const uint4 s0 = __ldg((const uint4 *)(Bs16v + (rowb + c) * 16)), s1 = __ldg((const uint4 *)(Bs16v + (rowb + c) * 16 + 8));
                         int off = 0;
                         off = dp2a_lo_(s0.x, m.sc[0], off); off = dp2a_hi_(s0.y, m.sc[0], off);
                         off = dp2a_lo_(s0.z, m.sc[1], off); off = dp2a_hi_(s0.w, m.sc[1], off);
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
                         P -= 32 * off;                      // sum scale_j * sum (q-32) a  ==  sum scale_j q a - 32 sum scale_j bsum_j
                         out[c] += (dd * da) * (float)P;
                     } else {
-                        const uint4 s = __ldg((const uint4 *)(p.Bs32 + (rowb + c) * 8));
+                        const uint4 s = __ldg((const uint4 *)(Bs32v + (rowb + c) * 8));
                         int Mv = 0;
                         Mv = dp2a_lo_(s.x, m.m0123, Mv); Mv = dp2a_hi_(s.y, m.m0123, Mv);
                         Mv = dp2a_lo_(s.z, m.m4567, Mv); Mv = dp2a_hi_(s.w, m.m4567, Mv);
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
                 const int rs = b % p.raw_slots;
                 mbar_wait(&S->raw_full[rs], (b / p.raw_slots) & 1);
                 const uint8_t *slotp = raw + ((size_t)rs * TM + r) * p.raw_row_bytes;
-                const uint8_t *blk = slotp + (uint32_t)((uintptr_t)(p.W + (size_t)(row0 + r) * p.rb + (size_t)b * BLK) & 15);
+                const uint8_t *blk = slotp + (uint32_t)((uintptr_t)(Wv + (size_t)(row0 + r) * p.rb + (size_t)b * BLK) & 15);
                 read_meta<TYPE>(blk, cur);
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
 #pragma unroll
             for (int c = 0; c < TN; c++) {
                 const int tok = tok0 + c;
-                if (tok < p.M) p.dst[(size_t)tok * p.dst_stride + row0 + r] = out[c] + xch[c * TM + r];
+                if (tok < p.M) dstv[(size_t)tok * dst_stride + row0 + r] = out[c] + xch[c * TM + r];
             }
         }
     }
@@ -432,6 +443,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+
+// dst[tok][n] = sum over the K-slices in slice order (deterministic)
+__global__ void b200_gemm_splitk_reduce_kernel(const float *__restrict__ part, int ksplit, int N, int M, float *__restrict__ dst, size_t dst_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * N) return;
+    const int tok = (int)(i / N), n = (int)(i % N);
+    float a = part[i];
+    for (int z = 1; z < ksplit; z++) a += part[(size_t)z * M * N + i];
+    dst[(size_t)tok * dst_stride + n] = a;
+}
 
 template <int TYPE, bool PARTIAL>
 int launch_gemm_t(b200_ctx *ctx, const GemmParams &p, dim3 grid, size_t smem) {
@@ -498,10 +519,28 @@ int gemm_i8_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N,
     if (rs < 1) { b200_set_error("gemm_i8: shared memory"); return B200_ERR_FAILED; }
     p.raw_slots = rs;
     const size_t smem = (size_t)3 * NSLOT * HALF_BYTES + (size_t)rs * TM * p.raw_row_bytes + sizeof(SmemLayout);
-    const dim3 grid((unsigned)(N / TM), (unsigned)ntile);
-    switch (type) {
-        case B200_TYPE_Q4_K: return launch_gemm<B200_TYPE_Q4_K>(ctx, p, grid, smem);
-        case B200_TYPE_Q5_K: return launch_gemm<B200_TYPE_Q5_K>(ctx, p, grid, smem);
-        default:             return launch_gemm<B200_TYPE_Q6_K>(ctx, p, grid, smem);
+    // split-K when the (row tile x token tile) grid leaves most of the machine idle; slices of >= 4 super-blocks
+    static const int max_split = getenv("GGML_B200_GEMM_KSPLIT") ? atoi(getenv("GGML_B200_GEMM_KSPLIT")) : 8;
+    const int64_t ctas = (N / TM) * ntile;
+    int ksplit = 1;
+    while (ksplit < max_split && ctas * ksplit * 2 <= ctx->sm_count && nsb / (ksplit * 2) >= 4) ksplit *= 2;
+    p.sb_per_split = (nsb + ksplit - 1) / ksplit;
+    ksplit = (nsb + p.sb_per_split - 1) / p.sb_per_split;
+    if (ksplit > 1) {
+        p.dst_partial = (float *)ctx->get_scratch(SCRATCH_MISC, (size_t)ksplit * M * N * 4);
+        if (!p.dst_partial) return B200_ERR_ALLOC;
     }
+    const dim3 grid((unsigned)(N / TM), (unsigned)ntile, (unsigned)ksplit);
+    int rc;
+    switch (type) {
+        case B200_TYPE_Q4_K: rc = launch_gemm<B200_TYPE_Q4_K>(ctx, p, grid, smem); break;
+        case B200_TYPE_Q5_K: rc = launch_gemm<B200_TYPE_Q5_K>(ctx, p, grid, smem); break;
+        default:             rc = launch_gemm<B200_TYPE_Q6_K>(ctx, p, grid, smem); break;
+    }
+    if (rc || ksplit == 1) return rc;
+    const int64_t total = M * N;
+    b200_gemm_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p.dst_partial, ksplit, (int)N, (int)M, dst, dst_stride);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
 }
