@@ -465,27 +465,30 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
             mbar_wait(&full[st], use & 1);
             if (i == 0) PROF(6);
             if ((TYPES & (TB_Q4_K | TB_Q5_K)) && ((TYPES & TB_Q6_K) == 0 || ty != B200_TYPE_Q6_K)) {
-                // Q4_K / Q5_K: two rows per pass, one per half-warp, a whole block per lane
+                // Q4_K / Q5_K: a whole block per lane.  Short rows (< 32 blocks): two rows per pass, one per half-warp;
+                // long rows (K >= 8192): all 32 lanes on one row, so a row costs ceil(nblk / 32) block decodes of latency
                 const bool q5 = (TYPES & TB_Q5_K) && (TYPES == TB_Q5_K || ty == B200_TYPE_Q5_K);
-                const int sub = lane >> 4, bl = lane & 15;
+                const int lpr = nblk >= 32 ? 32 : 16, rpp = 32 / lpr;          // lanes per row, rows per pass
+                const int sub = lane / lpr, bl = lane % lpr;
                 const uint4 *sums4 = (const uint4 *)s32;
                 const uint32_t bbytes = q5 ? 176u : 144u;
 #pragma unroll 1
-                for (int r = 0; r < nr; r += 2) {
+                for (int r = 0; r < nr; r += rpp) {
                     const bool mine = r + sub < nr;
                     const uint8_t *rp = rowp + (size_t)(r + (mine ? sub : 0)) * sg.rb;
                     float acc = 0.0f;
 #pragma unroll 1
-                    for (int blk = bl; blk < nblk; blk += 16) {
+                    for (int blk = bl; blk < nblk; blk += lpr) {
                         const uint8_t *b = rp + blk * bbytes;
                         const uint8_t *ap = aq64 + blk * 272;
                         if ((TYPES & TB_Q5_K) && q5) acc += block_q45k<true>(b, ap, sums4[blk], ad[blk]);
                         else if (TYPES & TB_Q4_K) acc += block_q45k<false>(b, ap, sums4[blk], ad[blk]);
                     }
-                    if (r + 2 >= nr) {                   // stage bytes consumed: hand it back before the reduction
+                    if (r + rpp >= nr) {                 // stage bytes consumed: hand it back before the reduction
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[st]);
                     }
+                    if (lpr == 32) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     if (bl == 0 && mine) {
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
             if (i == 0) PROF(7);
         }
     }
-    PROF(8 + warp);                      // each consumer warp's finish time
+    PROF(8 + (warp & 15));               // consumer warps' finish times (two warps share a slot: the later one wins)
 #undef PROF
 }
 
@@ -601,7 +604,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         g.rb = (uint32_t)segs[s].rb; g.type = segs[s].type; g.N = (int)segs[s].N;
         int R = (int)(target / g.rb);
         R = R < 1 ? 1 : (R > 8 ? 8 : R);
-        if (g.type != B200_TYPE_Q6_K && R < 2 && 2 * (size_t)g.rb <= 16384) R = 2;      // pair decoder: two rows per stage while they stay <= 16 KB
+        if (g.type != B200_TYPE_Q6_K && R < 2 && K < 8192) R = 2;      // pair decoder (rows shorter than 32 blocks): two rows per stage
         int lg = 0;
         while ((2 << lg) <= R) lg++;
         g.R = 1 << lg; g.lgR = lg;

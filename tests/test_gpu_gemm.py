@@ -25,7 +25,7 @@ def gpu_mul_mat(b200, ctx, t, W, x, N, K):
 
 
 @pytest.mark.parametrize("N,K,M", [(128, 256, 16), (128, 512, 128), (256, 1024, 130), (128, 4096, 9), (384, 2048, 300), (1024, 4096, 512),
-                                   (256, 5632, 32), (1024, 14336, 32)]      # the last two: split-K with uneven / 8 slices, a quarter-full token tile)
+                                   (256, 5632, 32), (1024, 14336, 32)])      # the last two: split-K with uneven / 8 slices, a quarter-full token tile
 @pytest.mark.parametrize("t", [R.Q4_K, R.Q5_K, R.Q6_K])
 def test_gemm_i8_vs_oracle(b200, ctx, t, N, K, M):
     rng = np.random.default_rng(N + K + M + t)
