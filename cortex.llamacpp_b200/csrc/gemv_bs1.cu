@@ -49,6 +49,7 @@ struct Bs1Params {
     int            nstages;
     uint32_t       stage_bytes;
     int            w_const, use_pdl, ncw;      // ncw: consumer warps (blockDim / 32 - 1)
+    int            cs;                         // thread-block cluster size sharing the activation prologue (1 = none)
     uint32_t       off_aq64, off_aq128, off_ad, off_s32, off_s16, off_ring;   // 0 = layout not needed (aq*, s*)
     const uint8_t *pf_ptr;
     unsigned long long pf_bytes;
@@ -253,19 +254,45 @@ __device__ __forceinline__ float item_q6k(const uint8_t *row, int it, const uint
 // ---------------------------------------------------------------------------------------------- prologue
 // f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref
 #define PROFQ(slot) do { if (p.prof && lane == 0 && warp == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[(size_t)blockIdx.x * 32 + (slot)] = t_; } } while (0)
-// one warp: 256 activations (lane owns v[0..7]) -> q8_K block b in the shared-memory layouts
+// ---- thread-block cluster helpers: the CTAs of a cluster split the activation prologue and write each quantised block into
+//      every member's shared memory (distributed shared memory), so a long activation vector is read and quantised once per
+//      cluster instead of once per CTA ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint2 v) { asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint16_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// one warp: 256 activations (lane owns v[0..7]) -> q8_K block b in the shared-memory layouts (of every CTA of the cluster)
 __device__ __forceinline__ void bs1_quant_chunk(const Bs1Params &p, uint8_t *smem, int b, int lane, const float (&v)[8]) {
-    float *s_ad = (float *)(smem + p.off_ad);
-    int16_t *s_s32 = (int16_t *)(smem + p.off_s32), *s_s16 = (int16_t *)(smem + p.off_s16);
     const int e0 = b * 256 + lane * 8;
     uint2 qp; float d; int pair;
     warp_quant_q8k(v, lane, qp, d, pair);                // pair: 16-element sum, valid in even lanes
     const int quad = pair + __shfl_xor_sync(0xffffffffu, pair, 2);
-    if (p.off_s16 && (lane & 1) == 0) s_s16[b * 16 + (lane >> 1)] = (int16_t)pair;
-    if (p.off_s32 && (lane & 3) == 0) s_s32[b * 8 + (lane >> 2)] = (int16_t)quad;
-    if (lane == 0) s_ad[b] = d;
-    if (p.off_aq64)  *(uint2 *)(smem + p.off_aq64 + (e0 >> 8) * 272 + (e0 & 255)) = qp;
-    if (p.off_aq128) *(uint2 *)(smem + p.off_aq128 + (e0 >> 7) * 144 + (e0 & 127)) = qp;
+    const uint32_t o_s16 = p.off_s16 + (uint32_t)(b * 16 + (lane >> 1)) * 2, o_s32 = p.off_s32 + (uint32_t)(b * 8 + (lane >> 2)) * 2;
+    const uint32_t o_d = p.off_ad + (uint32_t)b * 4;
+    const uint32_t o_q64 = p.off_aq64 + (uint32_t)((e0 >> 8) * 272 + (e0 & 255)), o_q128 = p.off_aq128 + (uint32_t)((e0 >> 7) * 144 + (e0 & 127));
+    if (p.cs <= 1) {
+        if (p.off_s16 && (lane & 1) == 0) *(int16_t *)(smem + o_s16) = (int16_t)pair;
+        if (p.off_s32 && (lane & 3) == 0) *(int16_t *)(smem + o_s32) = (int16_t)quad;
+        if (lane == 0) *(float *)(smem + o_d) = d;
+        if (p.off_aq64)  *(uint2 *)(smem + o_q64) = qp;
+        if (p.off_aq128) *(uint2 *)(smem + o_q128) = qp;
+    } else {
+        const uint32_t base = smem_u32(smem);
+        for (int r = 0; r < p.cs; r++) {
+            const uint32_t rb = mapa_shared(base, (uint32_t)r);
+            if (p.off_s16 && (lane & 1) == 0) st_cluster_u16(rb + o_s16, (uint16_t)(int16_t)pair);
+            if (p.off_s32 && (lane & 3) == 0) st_cluster_u16(rb + o_s32, (uint16_t)(int16_t)quad);
+            if (lane == 0) st_cluster_u32(rb + o_d, __float_as_uint(d));
+            if (p.off_aq64)  st_cluster_v2(rb + o_q64, qp);
+            if (p.off_aq128) st_cluster_v2(rb + o_q128, qp);
+        }
+    }
 }
 __device__ __forceinline__ void bs1_apply_mode(const Bs1Params &p, float (&v)[8], const float4 &w0, const float4 &w1, float norm_scale) {
     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -294,11 +321,12 @@ __device__ __forceinline__ float bs1_norm_scale(const Bs1Params &p, double *s_re
 // when the rms_norm needs the sum of squares of the whole vector first.
 __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, double *s_red, int warp, int lane) {
     const int nchunk = p.K >> 8, ncw = p.ncw;
-    if (nchunk <= 2 * ncw) {
+    const int cs = p.cs, crank = cs > 1 ? (int)cluster_ctarank() : 0;        // cluster mode: CTA `crank` takes blocks b = cs * j + crank
+    if (nchunk <= 2 * ncw * cs) {
         float4 xa[2][2], xb[2][2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int b = warp + u * ncw;
+            const int b = (warp + u * ncw) * cs + crank;
             xa[u][0] = xa[u][1] = xb[u][0] = xb[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (b < nchunk) {
                 const int e0 = b * 256 + lane * 8;
@@ -319,7 +347,7 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
         }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int b = warp + u * ncw;
+            const int b = (warp + u * ncw) * cs + crank;
             if (b < nchunk) {
                 float v[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
                 if (p.prof) { asm volatile("" : "+f"(v[0])); if (u == 0) PROFQ(24); }
@@ -385,7 +413,8 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
         if (lane < ns) { mbar_init(&full[lane], 1); mbar_init(&empty[lane], 1); }
         mbar_fence_init();
         __syncwarp();
-        asm volatile("bar.arrive 1, %0;" ::"r"(BS1_THREADS) : "memory");       // consumers learn about the barriers at the end of their prologue
+        if (p.cs > 1) cluster_arrive();      // cluster mode: one cluster-wide barrier covers the mbarrier init and every member's activation stores
+        else asm volatile("bar.arrive 1, %0;" ::"r"(BS1_THREADS) : "memory");       // consumers learn about the barriers at the end of their prologue
         bool any_expert = false;
 #pragma unroll
         for (int s = 0; s < GEMV_MAX_SEG; s++) any_expert |= s < p.nseg && p.seg[s].expert_id != nullptr;
@@ -436,7 +465,8 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
     if (p.use_pdl) pdl_wait();          // the activations belong to the previous kernels
     if (warp == 0) PROF(4);
     bs1_prologue(p, smem, s_red, warp, lane);
-    named_bar_sync(1, BS1_THREADS);     // activations complete + mbarriers initialised (producer arrived long ago)
+    if (p.cs > 1) { cluster_arrive(); cluster_wait(); }       // every member's blocks have landed in this CTA's shared memory
+    else named_bar_sync(1, BS1_THREADS);     // activations complete + mbarriers initialised (producer arrived long ago)
     if (warp == 0) PROF(5);
     if (nchunks == 0) return;
 
@@ -468,7 +498,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
                 // Q4_K / Q5_K: a whole block per lane.  Short rows (< 32 blocks): two rows per pass, one per half-warp;
                 // long rows (K >= 8192): all 32 lanes on one row, so a row costs ceil(nblk / 32) block decodes of latency
                 const bool q5 = (TYPES & TB_Q5_K) && (TYPES == TB_Q5_K || ty == B200_TYPE_Q5_K);
-                const int lpr = nblk >= 32 ? 32 : 16, rpp = 32 / lpr;          // lanes per row, rows per pass
+                const int lpr = (nblk >= 32 && sg.R == 1) ? 32 : 16, rpp = 32 / lpr;          // lanes per row, rows per pass
                 const int sub = lane / lpr, bl = lane % lpr;
                 const uint4 *sums4 = (const uint4 *)s32;
                 const uint32_t bbytes = q5 ? 176u : 144u;
@@ -522,7 +552,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
 #undef PROF
 }
 
-int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0, g_bs1_warps = 0;
+int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0, g_bs1_warps = 0, g_bs1_cluster = 4, g_bs1_lpr32 = 1;
 bool g_bs1_env = false;
 
 template <int TYPES>
@@ -538,11 +568,16 @@ int bs1_launch_t(b200_ctx *ctx, const Bs1Params &p, int grid, size_t smem_bytes)
     cfg.blockDim = dim3((unsigned)(p.ncw + 1) * 32);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     int nattr = 0;
     if (p.use_pdl) {
         attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        nattr++;
+    }
+    if (p.cs > 1) {
+        attr[nattr].id = cudaLaunchAttributeClusterDimension;
+        attr[nattr].val.clusterDim.x = (unsigned)p.cs; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
         nattr++;
     }
     cfg.attrs = attr;
@@ -550,6 +585,22 @@ int bs1_launch_t(b200_ctx *ctx, const Bs1Params &p, int grid, size_t smem_bytes)
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ctx->launches++;
     return B200_OK;
+}
+
+// how many clusters of `cs` CTAs with this shared-memory size can be resident at once (GPC packing decides); cached per size
+template <int TYPES>
+int bs1_max_clusters(b200_ctx *ctx, int cs, int threads, size_t smem_bytes) {
+    auto kern = b200_gemv_bs1_kernel<TYPES>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->sm_count / cs * cs)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 }  // namespace
@@ -561,6 +612,8 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         if (const char *e = getenv("GGML_B200_BS1_CTAS")) g_bs1_ctas = atoi(e);          // CTAs per SM (1 or 2; default 2)
         if (const char *e = getenv("GGML_B200_BS1_SMEM_KB")) g_bs1_smem_kb = atoi(e);    // shared memory per CTA
         if (const char *e = getenv("GGML_B200_BS1_OFF")) g_bs1_off = atoi(e);
+        if (const char *e = getenv("GGML_B200_BS1_CLUSTER")) g_bs1_cluster = atoi(e);   // 1 = off, 2 or 4 CTAs share the prologue of long vectors
+        if (const char *e = getenv("GGML_B200_BS1_LPR32")) g_bs1_lpr32 = atoi(e);
         if (const char *e = getenv("GGML_B200_BS1_WARPS")) g_bs1_warps = atoi(e);       // 16 or 32 warps per CTA (default 32)
         g_bs1_env = true;
     }
@@ -604,7 +657,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         g.rb = (uint32_t)segs[s].rb; g.type = segs[s].type; g.N = (int)segs[s].N;
         int R = (int)(target / g.rb);
         R = R < 1 ? 1 : (R > 8 ? 8 : R);
-        if (g.type != B200_TYPE_Q6_K && R < 2 && K < 8192) R = 2;      // pair decoder (rows shorter than 32 blocks): two rows per stage
+        if (g.type != B200_TYPE_Q6_K && R < 2 && (K < 8192 || g_bs1_lpr32 == 0) && 2 * (size_t)g.rb <= 16384) R = 2;      // pair decoder (rows shorter than 32 blocks): two rows per stage
         int lg = 0;
         while ((2 << lg) <= R) lg++;
         g.R = 1 << lg; g.lgR = lg;
@@ -633,6 +686,21 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     for (int s = 1; s < nseg; s++) min_rows = segs[s].N < min_rows ? segs[s].N : min_rows;
     int64_t grid = (int64_t)ctx->sm_count * cps;
     if (grid > min_rows) grid = min_rows;                // every CTA gets at least one row of every segment
+    // long activation vectors (a warp would quantise two blocks, every CTA would re-read 50+ KB): share the prologue in a cluster
+    p.cs = 1;
+    if (g_bs1_cluster > 1 && ga.mode != ACT_F32_NORM && (K >> 8) > ncw && grid >= ctx->sm_count / 2) {
+        const int cs = g_bs1_cluster >= 4 ? 4 : 2;
+        static int max_cl[5] = {0, 0, -1, 0, -1};
+        if (max_cl[cs] < 0) {
+            switch (mask) {
+                case TB_Q4_K: max_cl[cs] = bs1_max_clusters<TB_Q4_K>(ctx, cs, (ncw + 1) * 32, (size_t)220 * 1024); break;
+                default:      max_cl[cs] = bs1_max_clusters<TB_Q6_K>(ctx, cs, (ncw + 1) * 32, (size_t)220 * 1024); break;
+            }
+        }
+        int64_t gcl = grid / cs * cs;
+        if (max_cl[cs] > 0 && gcl > (int64_t)max_cl[cs] * cs) gcl = (int64_t)max_cl[cs] * cs;      // one wave of co-resident clusters
+        if (max_cl[cs] > 0 && gcl >= ctx->sm_count * 3 / 4) { p.cs = cs; grid = gcl; }
+    }
     for (int s = 0; s < nseg; s++) { p.seg[s].q = (int)(segs[s].N / grid); p.seg[s].rem = (int)(segs[s].N % grid); }
     int rc;
     switch (mask) {
