@@ -305,7 +305,11 @@ ggml_backend_t dev_init_backend(ggml_backend_dev_t dev, const char *) {
         GGML_LOG_ERROR("ggml-b200: failed to create a context on device %d: %s\n", d->device, b200_last_error());
         return NULL;
     }
-    if (const char *e = getenv("GGML_B200_GRAPHS")) b200_set_option(ctx, "cuda_graphs", atoi(e));
+    // decode steps replay a captured CUDA graph (the KV-store destinations are patched through a device table, graph.cu) and
+    // kernels use programmatic dependent launch; both can be switched off for debugging
+    const char *eg = getenv("GGML_B200_GRAPHS"), *ep = getenv("GGML_B200_PDL");
+    b200_set_option(ctx, "cuda_graphs", eg ? atoi(eg) : 1);
+    b200_set_option(ctx, "pdl", ep ? atoi(ep) : 1);
     ggml_backend_t backend = new ggml_backend{backend_guid(), backend_iface, dev, new backend_ctx{d->device, d->name, ctx, {}}};
     return backend;
 }

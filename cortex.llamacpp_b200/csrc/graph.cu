@@ -12,18 +12,29 @@
 #include <string.h>
 #include <algorithm>
 
+// A decode step of llama.cpp differs from the previous one ONLY in where the new K/V rows are stored (the CPY destinations are
+// views of the cache at kv_head, llama-graph.cpp:1375-1397).  The reference patches those kernel parameters into its captured
+// graph every token (maintain_cuda_graph, ggml-cuda.cu:2544-2587); here the cache key ignores them and the captured rope+store
+// kernels read their destinations from a small device table that is refreshed with one 16 B/layer copy before each replay.
 struct GraphCacheEntry {
-    std::vector<b200_op> ops;
+    std::vector<b200_op> key;                       // op list with the KV-store destinations zeroed
+    std::vector<int> kv_idx;                        // op indices of the KV-store candidates (CPY f32 -> 1-D cache view)
+    std::vector<void *> kv_ptrs;                    // their destinations at first sighting (exact-match fallback)
+    bool indirect = false;                          // every candidate is absorbed by a fused rope+store node: table indirection
+    std::vector<std::pair<int, int>> node_kv;       // per rope+store node: op indices of its K and V store
+    void **dev_table = nullptr;                     // [2 * nodes] device pointers
     cudaGraphExec_t exec = nullptr;
     int hits = 0;
 };
 struct GraphCache {
     std::vector<GraphCacheEntry> entries;
+    std::vector<b200_op> scratch_key;               // reused per call
+    std::vector<int> scratch_idx;
 };
 
 void graph_cache_free(b200_ctx *ctx) {
     if (!ctx->graph_cache) return;
-    for (auto &e : ctx->graph_cache->entries) if (e.exec) cudaGraphExecDestroy(e.exec);
+    for (auto &e : ctx->graph_cache->entries) { if (e.exec) cudaGraphExecDestroy(e.exec); if (e.dev_table) cudaFree(e.dev_table); }
     delete ctx->graph_cache;
     ctx->graph_cache = nullptr;
 }
@@ -69,6 +80,7 @@ extern "C" int b200_op_compute(b200_ctx *ctx, const b200_op *op) {
 // Intermediates that only lived between the fused ops are never materialised; the matcher proves with a liveness scan
 // over the op list (address ranges, first access after the pattern) that nobody else reads them.
 enum { EX_OP = 0, EX_GEMV = 1, EX_ROPE_STORE = 2 };
+static const int g_fuse_debug = getenv("GGML_B200_FUSE_DEBUG") ? atoi(getenv("GGML_B200_FUSE_DEBUG")) : 0;
 struct ExecNode {
     int kind = EX_OP;
     b200_op op;                                  // EX_OP
@@ -150,38 +162,52 @@ static bool match_norm_mul(const b200_op *ops, int n, int i, const b200_tensor *
 struct FuseScratch { float *q, *k, *v, *g, *u; };
 
 // attention block: NORM MUL {MMq MMk MMv ROPEq ROPEk CPYk CPYv in any dependency-respecting order} FA
+#define MA_FAIL(code) do { if (g_fuse_debug) fprintf(stderr, "[b200 fuse] attention pattern at op %d rejected: check %d\n", i, code); return 0; } while (0)
 static int match_attention(b200_ctx *ctx, const b200_op *ops, int n, int i, const FuseScratch &fs, std::vector<ExecNode> &out) {
     const b200_tensor *xin; const float *nw; float eps;
-    if (i + 9 >= n || !match_norm_mul(ops, n, i, xin, nw, eps)) return 0;
-    const b200_op &fa = ops[i + 9];
-    if (fa.op != B200_OP_FLASH_ATTN_EXT) return 0;
-    const b200_op *mm[3], *rope[2], *cpy[2];
-    int nmm = 0, nrope = 0, ncpy = 0;
-    for (int j = i + 2; j < i + 9; j++) {
+    if (i + 9 >= n || !match_norm_mul(ops, n, i, xin, nw, eps)) MA_FAIL(1);
+    // the FLASH_ATTN_EXT that closes the block: 7 ops after NORM MUL, plus (first layer of a llama.cpp graph) the f32 -> f16
+    // conversion of the KQ mask, which llama.cpp schedules right before its first consumer
+    int fa_idx = -1;
+    for (int j = i + 9; j < n && j <= i + 11; j++) if (ops[j].op == B200_OP_FLASH_ATTN_EXT) { fa_idx = j; break; }
+    if (fa_idx < 0) MA_FAIL(2);
+    const b200_op &fa = ops[fa_idx];
+    const b200_op *mm[3], *rope[2], *cpy[2], *extra[2];
+    int nmm = 0, nrope = 0, ncpy = 0, nextra = 0;
+    for (int j = i + 2; j < fa_idx; j++) {
         const b200_op &o = ops[j];
         if (o.op == B200_OP_MUL_MAT && nmm < 3) mm[nmm++] = &o;
         else if (o.op == B200_OP_ROPE && nrope < 2) rope[nrope++] = &o;
+        else if (o.op == B200_OP_CPY && fa.n_src > 3 && o.dst.data == fa.src[3].data && nextra < 2) extra[nextra++] = &o;     // mask conversion
         else if (o.op == B200_OP_CPY && ncpy < 2) cpy[ncpy++] = &o;
-        else return 0;
+        else MA_FAIL(3);
     }
-    if (nmm != 3 || nrope != 2 || ncpy != 2) return 0;
+    if (nmm != 3 || nrope != 2 || ncpy != 2) MA_FAIL(4);
     const b200_tensor &B = ops[i + 1].dst;
-    for (int j = 0; j < 3; j++) if (!is_decode_mm(*mm[j]) || !same_tensor(mm[j]->src[1], B)) return 0;
-    if (!all_weights(mm, 3)) return 0;
-    // roles: q = the matmul whose rope feeds FA; k = the matmul whose rope feeds a CPY; v = the matmul feeding a CPY directly
+    for (int j = 0; j < 3; j++) if (!is_decode_mm(*mm[j]) || !same_tensor(mm[j]->src[1], B)) MA_FAIL(5);
+    if (!all_weights(mm, 3)) MA_FAIL(6);
+    for (int x = 0; x < nextra; x++) if (overlaps(extra[x]->src[0], ops[i].dst) || overlaps(extra[x]->src[0], B)) MA_FAIL(17);
+    // roles: q = the matmul whose rope feeds FA; k = the matmul whose rope feeds a CPY; v = the matmul feeding a CPY directly.
+    // ggml-alloc hands the SAME buffer to the three matmul outputs one after the other (each dies at its rope / store), so a
+    // consumer is paired with the LATEST matmul before it that wrote its source address, not with "the" matmul at that address
     const b200_op *mq = nullptr, *mk = nullptr, *mv = nullptr, *rq = nullptr, *rk = nullptr, *ck = nullptr, *cv = nullptr;
     for (int r = 0; r < 2; r++) {
         if (rope[r]->dst.data == fa.src[0].data) rq = rope[r];
-        for (int c = 0; c < 2; c++) if (cpy[c]->src[0].data == rope[r]->dst.data) { rk = rope[r]; ck = cpy[c]; }
+        else for (int c = 0; c < 2; c++) if (cpy[c]->src[0].data == rope[r]->dst.data && cpy[c] > rope[r]) { rk = rope[r]; ck = cpy[c]; }
     }
-    if (!rq || !rk || rq == rk) return 0;
+    if (!rq || !rk || rq == rk) MA_FAIL(7);
     cv = ck == cpy[0] ? cpy[1] : cpy[0];
-    for (int j = 0; j < 3; j++) {
-        if (mm[j]->dst.data == rq->src[0].data) mq = mm[j];
-        else if (mm[j]->dst.data == rk->src[0].data) mk = mm[j];
-        else if (mm[j]->dst.data == cv->src[0].data) mv = mm[j];
-    }
-    if (!mq || !mk || !mv) return 0;
+    auto producer = [&](const b200_op *consumer) -> const b200_op * {
+        const b200_op *best = nullptr;
+        for (int j = 0; j < 3; j++) if (mm[j] < consumer && mm[j]->dst.data == consumer->src[0].data && (!best || mm[j] > best)) best = mm[j];
+        return best;
+    };
+    mq = producer(rq); mk = producer(rk); mv = producer(cv);
+    if (!mq || !mk || !mv || mq == mk || mq == mv || mk == mv) MA_FAIL(8);
+    // a matmul output that shares its buffer with a later one must be consumed before that one is produced
+    const b200_op *cons[3] = {rq, rk, cv}, *prod[3] = {mq, mk, mv};
+    for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++)
+        if (a_ != b_ && prod[a_]->dst.data == prod[b_]->dst.data && prod[a_] < prod[b_] && cons[a_] > prod[b_]) MA_FAIL(18);
     // shapes: rope over [D, heads, T] f32 dense views of the matmul outputs, identical rope parameters and positions
     const int64_t T = B.ne[1], D = rq->src[0].ne[0], H = rq->src[0].ne[1], Hkv = rk->src[0].ne[1];
     auto rope_ok = [&](const b200_op *r, int64_t heads) {
@@ -190,21 +216,28 @@ static int match_attention(b200_ctx *ctx, const b200_op *ops, int n, int i, cons
                a.nb[0] == 4 && a.nb[1] == (uint64_t)D * 4 && a.nb[2] == (uint64_t)D * heads * 4 && r->src[1].type == B200_TYPE_I32 &&
                r->src[1].ne[0] == T && supports_glue(r);
     };
-    if (D > 512 || D % 32 || !rope_ok(rq, H) || !rope_ok(rk, Hkv)) return 0;
-    if (memcmp(rq->params, rk->params, sizeof(rq->params)) || rq->src[1].data != rk->src[1].data || rq->src[2].data != rk->src[2].data) return 0;
-    if (mq->src[0].ne[1] != H * D || mk->src[0].ne[1] != Hkv * D || mv->src[0].ne[1] != Hkv * D) return 0;
+    if (D > 512 || D % 32 || !rope_ok(rq, H) || !rope_ok(rk, Hkv)) MA_FAIL(9);
+    if (memcmp(rq->params, rk->params, sizeof(rq->params)) || rq->src[1].data != rk->src[1].data || rq->src[2].data != rk->src[2].data) MA_FAIL(10);
+    if (mq->src[0].ne[1] != H * D || mk->src[0].ne[1] != Hkv * D || mv->src[0].ne[1] != Hkv * D) MA_FAIL(11);
     const b200_tensor &qd = rq->dst;
-    if (qd.nb[0] != 4 || qd.ne[0] != D || qd.ne[1] != H || qd.ne[2] != T) return 0;
+    if (qd.nb[0] != 4 || qd.ne[0] != D || qd.ne[1] != H || qd.ne[2] != T) MA_FAIL(12);
     // KV store destinations: contiguous runs of T rows of Hkv*D elements in the cache type
     const int kvt = ck->dst.type;
-    if (kvt != cv->dst.type || (kvt != B200_TYPE_F16 && kvt != B200_TYPE_Q8_0 && kvt != B200_TYPE_Q4_0)) return 0;
+    if (kvt != cv->dst.type || (kvt != B200_TYPE_F16 && kvt != B200_TYPE_Q8_0 && kvt != B200_TYPE_Q4_0)) MA_FAIL(13);
     if (!tensor_is_contiguous(ck->dst) || !tensor_is_contiguous(cv->dst) || tensor_nelements(ck->dst) != Hkv * D * T ||
-        tensor_nelements(cv->dst) != Hkv * D * T) return 0;
-    if (ck->src[0].type != B200_TYPE_F32 || cv->src[0].type != B200_TYPE_F32 || !tensor_is_contiguous(ck->src[0]) || !tensor_is_contiguous(cv->src[0])) return 0;
+        tensor_nelements(cv->dst) != Hkv * D * T) MA_FAIL(14);
+    if (ck->src[0].type != B200_TYPE_F32 || cv->src[0].type != B200_TYPE_F32 || !tensor_is_contiguous(ck->src[0]) || !tensor_is_contiguous(cv->src[0])) MA_FAIL(15);
     // nobody else may need the intermediates we never write
     const b200_tensor *dead[] = {&ops[i].dst, &B, &mq->dst, &mk->dst, &mv->dst, &rk->dst};
-    for (const b200_tensor *t : dead) if (live_after(ops, n, i + 9, *t)) return 0;
+    // (memory of a dead intermediate that ggml-alloc re-used for the mask conversion inside the block is read later as the MASK,
+    //  which we do write: not a use of the intermediate)
+    for (const b200_tensor *t : dead) if (live_after(ops, n, fa_idx, *t)) {
+        bool reused = false;
+        for (int x = 0; x < nextra; x++) reused |= overlaps(*t, extra[x]->dst);
+        if (!reused) MA_FAIL(16);
+    }
     (void)ctx;
+    for (int x = 0; x < nextra; x++) { ExecNode m; m.kind = EX_OP; m.op = *extra[x]; out.push_back(m); }
     ExecNode g;
     g.kind = EX_GEMV; g.nseg = 3; g.K = xin->ne[0]; g.ncols = (int)T; g.w_const = true;
     g.seg[0] = seg_of(*mq, fs.q, (size_t)(H * D), nullptr);
@@ -229,7 +262,7 @@ static int match_attention(b200_ctx *ctx, const b200_op *ops, int n, int i, cons
     ExecNode f;
     f.kind = EX_OP; f.op = fa;
     out.push_back(f);
-    return 10;
+    return fa_idx - i + 1;
 }
 
 // FFN block: NORM MUL {MMgate SILU MMup MUL MMdown} ADD
@@ -418,9 +451,42 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
     return B200_OK;
 }
 
-static bool ops_equal(const std::vector<b200_op> &a, const b200_op *b, int n) {
-    if ((int)a.size() != n) return false;
-    return memcmp(a.data(), b, sizeof(b200_op) * (size_t)n) == 0;
+static bool is_kv_store(const b200_op &o) {
+    if (o.op != B200_OP_CPY || o.src[0].type != B200_TYPE_F32) return false;
+    const b200_tensor &d = o.dst;
+    if (d.type != B200_TYPE_F16 && d.type != B200_TYPE_Q8_0 && d.type != B200_TYPE_Q4_0) return false;
+    return d.ne[1] == 1 && d.ne[2] == 1 && d.ne[3] == 1 && !(d.flags & B200_TENSOR_FLAG_WEIGHT);
+}
+
+// point every fused rope+store node at its slots of the entry's device table; false if a KV store is not inside such a node
+static bool bind_kv_table(GraphCacheEntry &e, const b200_op *ops, std::vector<ExecNode> &list, bool assign) {
+    e.node_kv.clear();
+    size_t covered = 0;
+    int j = 0;
+    for (ExecNode &x : list) {
+        if (x.kind != EX_ROPE_STORE) continue;
+        int ki = -1, vi = -1;
+        for (int idx : e.kv_idx) {
+            if (ops[idx].dst.data == x.rs.k_dst && ki < 0) ki = idx;
+            else if (ops[idx].dst.data == x.rs.v_dst && vi < 0) vi = idx;
+        }
+        if (ki < 0 || vi < 0) return false;
+        e.node_kv.push_back({ki, vi});
+        covered += 2;
+        if (assign) { x.rs.k_dst_ind = (void *const *)(e.dev_table + 2 * j); x.rs.v_dst_ind = (void *const *)(e.dev_table + 2 * j + 1); }
+        j++;
+    }
+    return covered == e.kv_idx.size();
+}
+
+static int upload_kv_table(b200_ctx *ctx, const GraphCacheEntry &e, const b200_op *ops) {
+    if (e.node_kv.empty()) return B200_OK;
+    void *host[2 * 512];
+    const size_t n = e.node_kv.size() > 512 ? 512 : e.node_kv.size();
+    for (size_t j = 0; j < n; j++) { host[2 * j] = ops[e.node_kv[j].first].dst.data; host[2 * j + 1] = ops[e.node_kv[j].second].dst.data; }
+    // pageable source: the driver stages it before returning, so `host` may die right away; ordered before the replay on the stream
+    CUDA_TRY(cudaMemcpyAsync(e.dev_table, host, 2 * n * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+    return B200_OK;
 }
 
 extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) {
@@ -437,42 +503,93 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
 
     if (!ctx->opt_cuda_graphs || n_ops < 8) return run_list(ctx, list);
 
-    // ---- CUDA graph replay keyed on the exact op list ----
+    // only decode-sized steps repeat (a prompt ubatch is seen once, and capturing its ~1000 big launches costs more than it saves)
+    {
+        bool decode_like = false;
+        for (const ExecNode &x : list) decode_like |= x.kind == EX_GEMV;
+        if (!decode_like && ctx->opt_fusion >= 2) return run_list(ctx, list);
+    }
+    // ---- CUDA graph replay keyed on the op list modulo the KV-store destinations ----
     if (!ctx->graph_cache) ctx->graph_cache = new GraphCache();
     GraphCache &gc = *ctx->graph_cache;
+    std::vector<b200_op> &key = gc.scratch_key;
+    key.assign(ops, ops + n_ops);
+    std::vector<int> &kv_idx = gc.scratch_idx;
+    kv_idx.clear();
+    for (int i = 0; i < n_ops; i++) if (is_kv_store(ops[i])) { kv_idx.push_back(i); key[i].dst.data = nullptr; }
     for (auto &e : gc.entries) {
-        if (ops_equal(e.ops, ops, n_ops)) {
-            if (e.exec) {
-                CUDA_TRY(cudaGraphLaunch(e.exec, ctx->stream));
-                ctx->launches += 1;
-                e.hits++;
-                return B200_OK;
-            }
-            // second sighting: capture now.  Scratch must already be large enough (first run grew it).
-            cudaGraph_t g = nullptr;
-            ctx->capturing = true;
-            CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = run_list(ctx, list);
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-            ctx->capturing = false;
-            if (rc || ce != cudaSuccess || !g) {
-                cudaGetLastError();
-                if (g) cudaGraphDestroy(g);
-                return run_list(ctx, list);          // fall back to eager launches
-            }
-            if (cudaGraphInstantiate(&e.exec, g, 0) != cudaSuccess) { cudaGetLastError(); e.exec = nullptr; cudaGraphDestroy(g); return run_list(ctx, list); }
-            cudaGraphDestroy(g);
+        if ((int)e.key.size() != n_ops || memcmp(e.key.data(), key.data(), sizeof(b200_op) * (size_t)n_ops) != 0) continue;
+        if (!e.indirect) {                           // exact pointers required
+            bool same = e.kv_ptrs.size() == kv_idx.size();
+            for (size_t j = 0; same && j < kv_idx.size(); j++) same = e.kv_ptrs[j] == ops[kv_idx[j]].dst.data;
+            if (!same) continue;
+        }
+        if (e.exec) {
+            if (e.indirect) { int rc = upload_kv_table(ctx, e, ops); if (rc) return rc; }
             CUDA_TRY(cudaGraphLaunch(e.exec, ctx->stream));
             ctx->launches += 1;
+            e.hits++;
+            if (getenv("GGML_B200_GRAPH_DEBUG") && (e.hits & 15) == 1) fprintf(stderr, "[b200 graph] replay hit %d (indirect %d, %zu kv nodes)\n", e.hits, (int)e.indirect, e.node_kv.size());
             return B200_OK;
         }
+        // second sighting: capture now.  Scratch must already be large enough (first run grew it).
+        if (e.indirect) {
+            if (!e.dev_table && cudaMalloc((void **)&e.dev_table, 2 * 512 * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); e.dev_table = nullptr; e.indirect = false; }
+            if (e.indirect && (e.node_kv.size() > 512 || !bind_kv_table(e, ops, list, true))) e.indirect = false;
+            if (e.indirect) { int rc = upload_kv_table(ctx, e, ops); if (rc) return rc; }
+            else { e.kv_ptrs.clear(); for (int idx : kv_idx) e.kv_ptrs.push_back(ops[idx].dst.data); for (ExecNode &x : list) if (x.kind == EX_ROPE_STORE) x.rs.k_dst_ind = x.rs.v_dst_ind = nullptr; }
+        }
+        cudaGraph_t g = nullptr;
+        ctx->capturing = true;
+        CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_list(ctx, list);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        ctx->capturing = false;
+        if (rc || ce != cudaSuccess || !g) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            for (ExecNode &x : list) if (x.kind == EX_ROPE_STORE) x.rs.k_dst_ind = x.rs.v_dst_ind = nullptr;
+            return run_list(ctx, list);          // fall back to eager launches
+        }
+        if (cudaGraphInstantiate(&e.exec, g, 0) != cudaSuccess) {
+            cudaGetLastError(); e.exec = nullptr; cudaGraphDestroy(g);
+            for (ExecNode &x : list) if (x.kind == EX_ROPE_STORE) x.rs.k_dst_ind = x.rs.v_dst_ind = nullptr;
+            return run_list(ctx, list);
+        }
+        cudaGraphDestroy(g);
+        CUDA_TRY(cudaGraphLaunch(e.exec, ctx->stream));
+        ctx->launches += 1;
+        return B200_OK;
     }
     if (gc.entries.size() >= 64) {           // bounded cache: drop the oldest
         if (gc.entries.front().exec) cudaGraphExecDestroy(gc.entries.front().exec);
+        if (gc.entries.front().dev_table) cudaFree(gc.entries.front().dev_table);
         gc.entries.erase(gc.entries.begin());
     }
+    static const int gdebug = getenv("GGML_B200_GRAPH_DEBUG") ? atoi(getenv("GGML_B200_GRAPH_DEBUG")) : 0;
+    if (gdebug && !gc.entries.empty()) {          // why did this list miss?  first difference against the newest entry
+        const GraphCacheEntry &le = gc.entries.back();
+        if ((int)le.key.size() != n_ops) fprintf(stderr, "[b200 graph] miss: %d ops vs %zu\n", n_ops, le.key.size());
+        else for (int i = 0; i < n_ops; i++) if (memcmp(&le.key[i], &key[i], sizeof(b200_op))) {
+            const b200_op &a = le.key[i], &b = key[i];
+            fprintf(stderr, "[b200 graph] miss at op %d/%d (id %d): dst %p/%p ne %lld,%lld/%lld,%lld src0 %p/%p ne1 %lld/%lld src1 %p/%p src3 %p/%p params0 %d/%d\n", i, n_ops, b.op,
+                    a.dst.data, b.dst.data, (long long)a.dst.ne[0], (long long)a.dst.ne[1], (long long)b.dst.ne[0], (long long)b.dst.ne[1], a.src[0].data, b.src[0].data,
+                    (long long)a.src[0].ne[1], (long long)b.src[0].ne[1], a.src[1].data, b.src[1].data, a.src[3].data, b.src[3].data, a.params[0], b.params[0]);
+            break;
+        }
+    }
+    if (gdebug) {
+        int ng = 0, nr = 0;
+        for (const ExecNode &x : list) { ng += x.kind == EX_GEMV; nr += x.kind == EX_ROPE_STORE; }
+        fprintf(stderr, "[b200 graph] new list: %d ops -> %zu nodes (%d fused gemv, %d rope+store), %zu kv stores; op ids:", n_ops, list.size(), ng, nr, kv_idx.size());
+        for (int i = 0; i < n_ops && i < 64; i++) fprintf(stderr, " %d", ops[i].op);
+        fprintf(stderr, "\n");
+    }
     GraphCacheEntry ne;
-    ne.ops.assign(ops, ops + n_ops);
+    ne.key = key;
+    ne.kv_idx = kv_idx;
+    for (int idx : kv_idx) ne.kv_ptrs.push_back(ops[idx].dst.data);
+    ne.indirect = !kv_idx.empty() && bind_kv_table(ne, ops, list, false);
     gc.entries.push_back(std::move(ne));
     return run_list(ctx, list);
 }
