@@ -109,3 +109,40 @@ def test_llama_decode_cuda_graph_replay(b200, ctx):
         assert launches[-1] == 1 and launches[0] > 1, launches
     ctx.set_option("pdl", 0)
     ctx.set_option("cuda_graphs", 0)
+
+
+@pytest.mark.parametrize("kv", ["f16", "q8_0"])
+def test_llama_decode_graph_replay_follows_kv_head(b200, ctx, kv):
+    """a real decode loop: every step stores its K/V rows one cell further (the only thing that changes in llama.cpp's
+    graph from token to token).  The captured graph must be REPLAYED (1 launch per step) with the new destinations patched
+    in, and every step's logits must equal the eager run bit for bit -- a stale destination would corrupt the cache."""
+    import torch
+    from __graft_entry__ import load_llama_graph
+    lg = load_llama_graph()
+    g = lg.LlamaGraph(b200, model="tiny-d128", ftype="q4_k_m", kv=kv, n_ctx=256, max_tokens=4)
+    ctx.set_option("fusion", 2)
+    ctx.set_option("pdl", 1)
+    outs = {}
+    for graphs in (0, 1):
+        ctx.set_option("cuda_graphs", graphs)
+        for lw in g.layers:
+            lw["k_cache"].zero_(); lw["v_cache"].zero_()
+        rng = np.random.default_rng(3)
+        seq, launches = [], []
+        for step, (T, kv_head) in enumerate([(4, 0)] + [(1, 4 + i) for i in range(10)]):
+            emb, pos, mask = g.set_inputs_host(T, kv_head, 256, rng)
+            g.inp_embd[:T * g.E] = torch.from_numpy(emb.reshape(-1)).cuda()
+            g.pos[:T] = torch.from_numpy(pos).cuda()
+            g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda()
+            torch.cuda.synchronize()
+            n0 = ctx.launches()
+            ctx.compute(g.build(T, kv_head, 256)); ctx.sync()
+            launches.append(ctx.launches() - n0)
+            seq.append(g.logits[:T * g.V].cpu().numpy().copy())
+        outs[graphs] = (seq, launches)
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+    assert all(n == 1 for n in outs[1][1][3:]), outs[1][1]          # prompt, first decode (eager), second (capture), then replays
+    assert all(n > 1 for n in outs[0][1])
+    ctx.set_option("pdl", 0)
+    ctx.set_option("cuda_graphs", 0)
