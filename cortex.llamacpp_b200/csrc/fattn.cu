@@ -355,6 +355,10 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
     const int tile_id = blockIdx.y;
     for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
         const int r = e / D, d = e % D;
+        {   // rows of the 16-row tile that hold no query (a bs1 decode step fills 4 of 16): nothing to merge or store
+            const int hin_ = ht * p.HG + r % p.HG, col_ = c0 + r / p.HG;
+            if (!((r / p.HG) < p.QC && col_ < p.n_q && hin_ < p.gq)) continue;
+        }
         float M = -INFINITY;
 #pragma unroll
         for (int w = 0; w < NWARP; w++) M = fmaxf(M, cm[w * 16 + r]);
