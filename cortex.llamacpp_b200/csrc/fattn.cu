@@ -417,6 +417,109 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-token decode over an f16 cache: a vector kernel (replaces flash_attn_vec_ext_f32, fattn-vec-f32.cuh:4-282, for the
+// bs1 step, where the 16-row mma tile above is a quarter full and its fixed costs dominate 3 MB of KV).  One WARP = one
+// 32-position tile of one KV head = one KV split; all `gq` query heads of the group share every K/V byte.
+//   S = Q.K : lane j owns position j; Q is rounded to f16 like the CPU does for an f16 K (products exact, f32 accumulate)
+//   softmax : one tile per warp -> plain max / sum over the 32 lanes, no running rescale
+//   O = P.V : lane owns 4 of the 128 dims; p_j of every head is broadcast by shuffle, V rows are read coalesced, f32 accumulate
+// K and V tiles are prefetched into L2 BEFORE griddepcontrol.wait (L2 is coherent with the rope+store kernel's writes).
+// Partials go to the same [tile][split][16][D+2] layout, merged by b200_fattn_combine_kernel.
+template <int GQ>
+__global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaParams p) {
+    constexpr int D = 128;
+    __shared__ __align__(16) float sq[NWARP][GQ][D];      // f16-rounded Q of the group, per warp (no CTA-wide sync needed)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x * NWARP + warp, hk = blockIdx.y;
+    const int p0 = split * BK;
+    const bool active = split < p.n_splits;
+    const char *krow = p.k + (uint64_t)hk * p.k_nb2 + (uint64_t)(p0 + lane) * p.k_nb1;
+    const char *vbase = p.v + (uint64_t)hk * p.v_nb2 + (uint64_t)p0 * p.v_nb1;
+    if (active) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(krow));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(krow + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + (uint64_t)lane * p.v_nb1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + (uint64_t)lane * p.v_nb1 + 128));
+    }
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
+    if (!active) return;
+    float *pp = p.part + (((uint64_t)hk * p.n_splits + split) * 16) * (D + 2);
+    // mask of my position (query column 0); a fully masked tile contributes nothing
+    const __half mh = *(const __half *)(p.mask + (uint64_t)(p0 + lane) * 2);
+    const float mval = __half2float(mh);
+    const bool masked = __hisinf(mh) && mval < 0.0f;
+    if (__all_sync(0xffffffffu, masked)) {
+        if (lane < p.gq) { pp[(uint64_t)lane * (D + 2) + D] = -INFINITY; pp[(uint64_t)lane * (D + 2) + D + 1] = 0.0f; }
+        return;
+    }
+    // Q -> f16-rounded f32 in shared memory
+#pragma unroll
+    for (int h = 0; h < GQ; h++) {
+        if (h < p.gq) {
+            const float4 q4 = *(const float4 *)(p.q + (uint64_t)(hk * p.gq + h) * p.q_nb2 + (uint64_t)lane * 16);
+            float4 r;
+            r.x = __half2float(__float2half_rn(q4.x)); r.y = __half2float(__float2half_rn(q4.y));
+            r.z = __half2float(__float2half_rn(q4.z)); r.w = __half2float(__float2half_rn(q4.w));
+            *(float4 *)&sq[warp][h][lane * 4] = r;
+        }
+    }
+    __syncwarp();
+    // ---- S = Q.K for my position -------------------------------------------------------------------------------
+    float sc[GQ];
+#pragma unroll
+    for (int h = 0; h < GQ; h++) sc[h] = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < D / 8; c++) {
+        const uint4 kq = *(const uint4 *)(krow + c * 16);
+        const float2 k0 = __half22float2(*(const __half2 *)&kq.x), k1 = __half22float2(*(const __half2 *)&kq.y);
+        const float2 k2 = __half22float2(*(const __half2 *)&kq.z), k3 = __half22float2(*(const __half2 *)&kq.w);
+#pragma unroll
+        for (int h = 0; h < GQ; h++) {
+            if (h < p.gq) {
+                const float4 qa = *(const float4 *)&sq[warp][h][c * 8], qb = *(const float4 *)&sq[warp][h][c * 8 + 4];
+                float a = sc[h];
+                a = fmaf(qa.x, k0.x, a); a = fmaf(qa.y, k0.y, a); a = fmaf(qa.z, k1.x, a); a = fmaf(qa.w, k1.y, a);
+                a = fmaf(qb.x, k2.x, a); a = fmaf(qb.y, k2.y, a); a = fmaf(qb.z, k3.x, a); a = fmaf(qb.w, k3.y, a);
+                sc[h] = a;
+            }
+        }
+    }
+    // ---- softmax over the tile ---------------------------------------------------------------------------------
+    float pj[GQ], Mh[GQ], Lh[GQ];
+#pragma unroll
+    for (int h = 0; h < GQ; h++) {
+        const float sv = masked ? -INFINITY : sc[h] * p.scale + mval;
+        const float M = warp_reduce_max(sv);
+        const float e = (masked || M == -INFINITY) ? 0.0f : expf(sv - M);
+        pj[h] = e; Mh[h] = M; Lh[h] = warp_reduce_sum(e);
+    }
+    // ---- O = P.V : lane owns dims [4*lane, 4*lane+4) -------------------------------------------------------------
+    float o[GQ][4];
+#pragma unroll
+    for (int h = 0; h < GQ; h++) o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.0f;
+#pragma unroll 8
+    for (int j = 0; j < BK; j++) {
+        const uint2 vv = *(const uint2 *)(vbase + (uint64_t)j * p.v_nb1 + lane * 8);
+        const float2 v0 = __half22float2(*(const __half2 *)&vv.x), v1 = __half22float2(*(const __half2 *)&vv.y);
+#pragma unroll
+        for (int h = 0; h < GQ; h++) {
+            if (h < p.gq) {
+                const float w = __shfl_sync(0xffffffffu, pj[h], j);
+                o[h][0] = fmaf(w, v0.x, o[h][0]); o[h][1] = fmaf(w, v0.y, o[h][1]); o[h][2] = fmaf(w, v1.x, o[h][2]); o[h][3] = fmaf(w, v1.y, o[h][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < GQ; h++) {
+        if (h < p.gq) {
+            float *row = pp + (uint64_t)h * (D + 2);
+            *(float4 *)(row + lane * 4) = make_float4(o[h][0], o[h][1], o[h][2], o[h][3]);
+            if (lane == 0) { row[D] = Mh[h]; row[D + 1] = Lh[h]; }
+        }
+    }
+}
+
 // merge of the KV splits: one WARP per (tile, query row); lanes first reduce the per-split (max, sum) pairs, then each lane
 // owns D/32 output dims and walks the splits with independent loads (log-sum-exp merge, fixed split order => deterministic)
 template <int D>
@@ -563,6 +666,32 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     p.m1 = powf(2.0f, -(p.max_bias / 2.0f) / p.n_head_log2);
     const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;
     if (n_tiles == 0 || p.n_q == 0) return B200_OK;
+    // single-token decode over an f16 cache: the vector kernel (one warp per 32 positions, all heads of the group)
+    static const int use_vec = getenv("GGML_B200_FA_VEC") ? atoi(getenv("GGML_B200_FA_VEC")) : 1;
+    if (use_vec && p.n_q == 1 && D == 128 && kv_kind(k.type) == KV_F16 && kv_kind(v.type) == KV_F16 && p.gq <= 8 && has_mask &&
+        p.softcap == 0.0f && p.max_bias == 0.0f && !(q.nb[2] & 15) && !((uintptr_t)q.data & 15) && !(v.nb[1] & 7) && !(k.nb[1] & 15)) {
+        p.n_splits = p.n_kv / BK;
+        p.kv_per_split = BK;
+        p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)n_tiles * p.n_splits * 16 * (D + 2) * 4);
+        if (!p.part) return B200_ERR_ALLOC;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((p.n_splits + NWARP - 1) / NWARP), (unsigned)p.Hkv);
+        cfg.blockDim = dim3(NWARP * 32);
+        cfg.stream = ctx->stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = p.use_pdl ? 1 : 0;
+        if (p.gq <= 4) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_vec_kernel<4>, p));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_vec_kernel<8>, p));
+        ctx->launches++;
+        cfg.gridDim = dim3((unsigned)((n_tiles * 16 + 3) / 4));
+        cfg.blockDim = dim3(128);
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_combine_kernel<128>, p, n_tiles));
+        ctx->launches++;
+        return B200_OK;
+    }
     // split the KV range so the grid covers the machine ~2-3x; each split is a multiple of NWARP*BK positions
     const int unit = NWARP * BK;
     const int max_splits = (p.n_kv + unit - 1) / unit;
