@@ -429,16 +429,20 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
 template <int GQ>
 __global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaParams p) {
     constexpr int D = 128;
-    __shared__ __align__(16) float sq[NWARP][GQ][D];      // f16-rounded Q of the group, per warp (no CTA-wide sync needed)
+    constexpr int KLD = D * 2 + 16;                        // bytes per staged K row: +16 keeps lane-strided 128-bit reads conflict-free
+    extern __shared__ __align__(128) uint8_t vsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wsm = vsm + (size_t)warp * (BK * KLD + BK * D * 2 + GQ * D * 4);
+    uint8_t *sK = wsm, *sV = wsm + BK * KLD;
+    float *sq = (float *)(sV + BK * D * 2);               // f16-rounded Q of the group [GQ][D], per warp (no CTA-wide sync anywhere)
     const int split = blockIdx.x * NWARP + warp, hk = blockIdx.y;
     const int p0 = split * BK;
     const bool active = split < p.n_splits;
-    const char *krow = p.k + (uint64_t)hk * p.k_nb2 + (uint64_t)(p0 + lane) * p.k_nb1;
+    const char *kbase = p.k + (uint64_t)hk * p.k_nb2 + (uint64_t)p0 * p.k_nb1;
     const char *vbase = p.v + (uint64_t)hk * p.v_nb2 + (uint64_t)p0 * p.v_nb1;
-    if (active) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(krow));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(krow + 128));
+    if (active) {      // warm the L2 while the producer kernels are still running
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kbase + (uint64_t)lane * p.k_nb1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kbase + (uint64_t)lane * p.k_nb1 + 128));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + (uint64_t)lane * p.v_nb1));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + (uint64_t)lane * p.v_nb1 + 128));
     }
@@ -453,7 +457,17 @@ __global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaPara
         if (lane < p.gq) { pp[(uint64_t)lane * (D + 2) + D] = -INFINITY; pp[(uint64_t)lane * (D + 2) + D + 1] = 0.0f; }
         return;
     }
-    // Q -> f16-rounded f32 in shared memory
+    // ---- stage the K and V tiles with coalesced 16-byte async copies: every byte of the tile is in flight at once ----
+    {
+        const int half = lane >> 4, c16 = lane & 15;      // two rows per instruction, 16 chunks of 16 bytes per row
+#pragma unroll
+        for (int r = 0; r < BK; r += 2) {
+            const int row = r + half;
+            cp_async16(sK + row * KLD + c16 * 16, kbase + (uint64_t)row * p.k_nb1 + c16 * 16);
+            cp_async16(sV + row * (D * 2) + c16 * 16, vbase + (uint64_t)row * p.v_nb1 + c16 * 16);
+        }
+    }
+    // Q -> f16-rounded f32 in shared memory (overlaps the copies)
 #pragma unroll
     for (int h = 0; h < GQ; h++) {
         if (h < p.gq) {
@@ -461,14 +475,16 @@ __global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaPara
             float4 r;
             r.x = __half2float(__float2half_rn(q4.x)); r.y = __half2float(__float2half_rn(q4.y));
             r.z = __half2float(__float2half_rn(q4.z)); r.w = __half2float(__float2half_rn(q4.w));
-            *(float4 *)&sq[warp][h][lane * 4] = r;
+            *(float4 *)&sq[h * D + lane * 4] = r;
         }
     }
+    cp_async_wait_all();
     __syncwarp();
-    // ---- S = Q.K for my position -------------------------------------------------------------------------------
+    // ---- S = Q.K for my position (lane j owns position j) ------------------------------------------------------
     float sc[GQ];
 #pragma unroll
     for (int h = 0; h < GQ; h++) sc[h] = 0.0f;
+    const uint8_t *krow = sK + lane * KLD;
 #pragma unroll 4
     for (int c = 0; c < D / 8; c++) {
         const uint4 kq = *(const uint4 *)(krow + c * 16);
@@ -477,7 +493,7 @@ __global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaPara
 #pragma unroll
         for (int h = 0; h < GQ; h++) {
             if (h < p.gq) {
-                const float4 qa = *(const float4 *)&sq[warp][h][c * 8], qb = *(const float4 *)&sq[warp][h][c * 8 + 4];
+                const float4 qa = *(const float4 *)&sq[h * D + c * 8], qb = *(const float4 *)&sq[h * D + c * 8 + 4];
                 float a = sc[h];
                 a = fmaf(qa.x, k0.x, a); a = fmaf(qa.y, k0.y, a); a = fmaf(qa.z, k1.x, a); a = fmaf(qa.w, k1.y, a);
                 a = fmaf(qb.x, k2.x, a); a = fmaf(qb.y, k2.y, a); a = fmaf(qb.z, k3.x, a); a = fmaf(qb.w, k3.y, a);
@@ -500,7 +516,7 @@ __global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaPara
     for (int h = 0; h < GQ; h++) o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.0f;
 #pragma unroll 8
     for (int j = 0; j < BK; j++) {
-        const uint2 vv = *(const uint2 *)(vbase + (uint64_t)j * p.v_nb1 + lane * 8);
+        const uint2 vv = *(const uint2 *)(sV + j * (D * 2) + lane * 8);
         const float2 v0 = __half22float2(*(const __half2 *)&vv.x), v1 = __half22float2(*(const __half2 *)&vv.y);
 #pragma unroll
         for (int h = 0; h < GQ; h++) {
@@ -514,7 +530,8 @@ __global__ void __launch_bounds__(NWARP * 32) b200_fattn_vec_kernel(const FaPara
     for (int h = 0; h < GQ; h++) {
         if (h < p.gq) {
             float *row = pp + (uint64_t)h * (D + 2);
-            *(float4 *)(row + lane * 4) = make_float4(o[h][0], o[h][1], o[h][2], o[h][3]);
+            *(float2 *)(row + lane * 4) = make_float2(o[h][0], o[h][1]);          // rows are (D + 2) floats apart: 8-byte aligned only
+            *(float2 *)(row + lane * 4 + 2) = make_float2(o[h][2], o[h][3]);
             if (lane == 0) { row[D] = Mh[h]; row[D + 1] = Lh[h]; }
         }
     }
@@ -666,8 +683,10 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     p.m1 = powf(2.0f, -(p.max_bias / 2.0f) / p.n_head_log2);
     const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;
     if (n_tiles == 0 || p.n_q == 0) return B200_OK;
-    // single-token decode over an f16 cache: the vector kernel (one warp per 32 positions, all heads of the group)
-    static const int use_vec = getenv("GGML_B200_FA_VEC") ? atoi(getenv("GGML_B200_FA_VEC")) : 1;
+    // single-token decode over an f16 cache: the vector kernel (one warp per 32 positions, all heads of the group).  Parity green,
+    // but measured SLOWER than the mma tile kernel in round 1 (10.5 + 9.2 us with 24 splits to merge vs 9.5 + 5.1 us; 499 vs
+    // 536 tok/s on Llama-3-8B bs1), so it is opt-in until its latency chain is understood
+    static const int use_vec = getenv("GGML_B200_FA_VEC") ? atoi(getenv("GGML_B200_FA_VEC")) : 0;
     if (use_vec && p.n_q == 1 && D == 128 && kv_kind(k.type) == KV_F16 && kv_kind(v.type) == KV_F16 && p.gq <= 8 && has_mask &&
         p.softcap == 0.0f && p.max_bias == 0.0f && !(q.nb[2] & 15) && !((uintptr_t)q.data & 15) && !(v.nb[1] & 7) && !(k.nb[1] & 15)) {
         p.n_splits = p.n_kv / BK;
@@ -683,8 +702,17 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
         cfg.stream = ctx->stream;
         cfg.attrs = attr;
         cfg.numAttrs = p.use_pdl ? 1 : 0;
+        const int GQv = p.gq <= 4 ? 4 : 8;
+        cfg.dynamicSmemBytes = (size_t)NWARP * (BK * (128 * 2 + 16) + BK * 128 * 2 + GQv * 128 * 4);
+        static bool vattr[16] = {false};
+        if (!vattr[ctx->device & 15]) {
+            CUDA_TRY(cudaFuncSetAttribute(b200_fattn_vec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(b200_fattn_vec_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            vattr[ctx->device & 15] = true;
+        }
         if (p.gq <= 4) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_vec_kernel<4>, p));
         else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_vec_kernel<8>, p));
+        cfg.dynamicSmemBytes = 0;
         ctx->launches++;
         cfg.gridDim = dim3((unsigned)((n_tiles * 16 + 3) / 4));
         cfg.blockDim = dim3(128);
