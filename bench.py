@@ -444,6 +444,23 @@ def tp_leg(a, b200, lg, L, ctx, rank, world, local, peak):
     t = torch.tensor([ms], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # where the step goes (timing-only replays with kernel classes not launched; results of these replays are discarded)
+    breakdown = {}
+    for name, mask_ in (("no_allreduce", 8), ("no_attention", 3), ("no_gemv", 4)):
+        ctx.set_option("debug_skip", mask_)
+        for _ in range(3):
+            b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step")
+        ctx.sync(); dist.barrier(); torch.cuda.synchronize()
+        L.b200_event_record(ctx.h, e0)
+        for _ in range(8):
+            b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step")
+        L.b200_event_record(ctx.h, e1)
+        L.b200_event_synchronize(e1)
+        tt = torch.tensor([L.b200_event_elapsed_ms(e0, e1) / 8], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        breakdown[name + "_ms"] = float(tt.item())
+    ctx.set_option("debug_skip", 0)
+    b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step"); ctx.sync(); dist.barrier()
     logits = g.logits[:g.V].clone()
     ref = logits.clone()
     dist.broadcast(ref, 0)
@@ -457,7 +474,8 @@ def tp_leg(a, b200, lg, L, ctx, rank, world, local, peak):
            "allreduce": "B200_OP_ALLREDUCE x%d per step: one-shot peer-memory kernel over NVLink (f32 [E] = %d bytes), residual add fused" % (2 * g.L, g.E * 4),
            "gpu_launches_per_step": int(launches), "logits_identical_on_all_ranks": bool(flag.item()),
            "per_gpu_bytes_per_step": sb["total"], "per_gpu_achieved_gbs": sb["total"] * tok_s / 1e9, "per_gpu_hbm_frac": sb["total"] * tok_s / 1e9 / peak,
-           "hbm_roofline_tok_s": peak * 1e9 / sb["total"]}
+           "hbm_roofline_tok_s": peak * 1e9 / sb["total"],
+           "step_ms_with_kernel_classes_not_launched": breakdown}
     if a.tp_layers:
         out["INVALID"] = "--tp-layers override"
     return out

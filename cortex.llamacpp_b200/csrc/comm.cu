@@ -84,6 +84,7 @@ struct OneShotParams {
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // grid = ONESHOT_CTAS; CTA c owns floats [c*per, (c+1)*per) of the vector on every rank
@@ -101,18 +102,19 @@ __global__ void __launch_bounds__(256) b200_allreduce_oneshot_kernel(const OneSh
         float4 *slot = (float4 *)(p.peer[r] + OFF_SLOTS + ((size_t)set * MAX_WORLD + p.rank) * ONESHOT_MAX_BYTES);
         for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) slot[i] = src[i];
     }
-    __threadfence_system();
     __syncthreads();
-    // 2. publish: flag [set][rank][cta] of every rank = epoch
+    // 2. publish: flag [set][rank][cta] of every rank = epoch.  One system-scope fence per publishing thread AFTER the CTA barrier
+    //    (cumulative over the whole CTA's stores, the cooperative-groups grid-sync pattern) instead of one per thread
     if (threadIdx.x < p.world) {
         uint32_t *f = (uint32_t *)(p.peer[threadIdx.x] + OFF_FLAGS) + ((size_t)set * MAX_WORLD + p.rank) * ONESHOT_CTAS + blockIdx.x;
-        st_release_sys(f, epoch);
+        st_release_sys(f, epoch);                 // the release carries the (one) system-scope fence
     }
     // 3. wait for the same slice of every rank (bounded spin: a lost peer must not hang the GPU)
     if (threadIdx.x < p.world) {
         const uint32_t *f = (const uint32_t *)(local + OFF_FLAGS) + ((size_t)set * MAX_WORLD + threadIdx.x) * ONESHOT_CTAS + blockIdx.x;
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - epoch) < 0) { if (clock64() - t0 > (1ll << 32)) break; }
+        while ((int)(ld_relaxed_sys(f) - epoch) < 0) { if (clock64() - t0 > (1ll << 32)) break; }     // plain polls ...
+        (void)ld_acquire_sys(f);                                                                      // ... one acquire once the flag is there
     }
     __syncthreads();
     // 4. sum in fixed rank order (+ residual)

@@ -433,7 +433,7 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
 }
 
 static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
-    // timing experiments only (results are then wrong): option "debug_skip" / GGML_B200_DEBUG_SKIP bit 0 flash_attn, 1 rope+store, 2 GEMV
+    // timing experiments only (results are then wrong): option "debug_skip" / GGML_B200_DEBUG_SKIP bit 0 flash_attn, 1 rope+store, 2 GEMV, 3 all-reduce
     static const int env_skip = getenv("GGML_B200_DEBUG_SKIP") ? atoi(getenv("GGML_B200_DEBUG_SKIP")) : 0;
     const int dbg_skip = env_skip | ctx->opt_debug_skip;
     for (const ExecNode &e : list) {
@@ -442,6 +442,7 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
             if ((dbg_skip & 1) && e.kind == EX_OP && e.op.op == B200_OP_FLASH_ATTN_EXT) continue;
             if ((dbg_skip & 2) && e.kind == EX_ROPE_STORE) continue;
             if ((dbg_skip & 4) && e.kind == EX_GEMV) continue;
+            if ((dbg_skip & 8) && e.kind == EX_OP && e.op.op == B200_OP_ALLREDUCE) continue;
         }
         if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf_ptr, e.pf_bytes);
         else if (e.kind == EX_ROPE_STORE) rc = launch_rope_store(ctx, e.rs);
