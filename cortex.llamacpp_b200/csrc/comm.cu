@@ -74,7 +74,9 @@ namespace {
 constexpr size_t OFF_FLAGS = 128;
 constexpr size_t FLAGS_BYTES = 2 * MAX_WORLD * ONESHOT_CTAS * 4;
 constexpr size_t OFF_SLOTS = (OFF_FLAGS + FLAGS_BYTES + 127) & ~(size_t)127;
-constexpr size_t EXCH_BYTES = OFF_SLOTS + 2 * MAX_WORLD * ONESHOT_MAX_BYTES;
+constexpr size_t LL_MAX_BYTES = 64 * 1024;                   // payload per rank served by the flag-in-data (LL) kernel
+constexpr size_t OFF_LL = OFF_SLOTS + 2 * MAX_WORLD * ONESHOT_MAX_BYTES;
+constexpr size_t EXCH_BYTES = OFF_LL + 2 * MAX_WORLD * 2 * LL_MAX_BYTES;
 
 struct OneShotParams {
     uint8_t *peer[MAX_WORLD];
@@ -138,6 +140,56 @@ __global__ void __launch_bounds__(256) b200_allreduce_oneshot_kernel(const OneSh
     }
 }
 
+// Low-latency variant for decode-sized vectors (<= 64 KB): every 8-byte store carries 4 bytes of payload and the 4-byte epoch
+// (the "LL" idea of NCCL's small-message protocol), so a receiver that sees the epoch in a word also sees its payload:
+// no fence, no separate flag, no CTA barrier -- one NVLink traversal plus rank skew.  Slots: [2 sets][MAX_WORLD][2 x payload].
+__device__ __forceinline__ void st_v4_sys(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_v4_sys(const void *p) {
+    uint4 v; asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
+}
+__global__ void __launch_bounds__(256) b200_allreduce_ll_kernel(const OneShotParams p) {
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
+    uint8_t *local = p.peer[p.rank];
+    const uint32_t epoch = *(volatile uint32_t *)local + 1;
+    const int set = epoch & 1;
+    const int n4 = p.n >> 2;
+    const float4 *src = (const float4 *)p.src;
+    const float4 *res = (const float4 *)p.residual;
+    float4 *dst = (float4 *)p.dst;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        const uint32_t x = __float_as_uint(v.x), y = __float_as_uint(v.y), z = __float_as_uint(v.z), w = __float_as_uint(v.w);
+        for (int r = 0; r < p.world; r++) {
+            uint8_t *slot = p.peer[r] + OFF_LL + ((size_t)set * MAX_WORLD + p.rank) * 2 * LL_MAX_BYTES + (size_t)i * 32;
+            st_v4_sys(slot, x, epoch, y, epoch);
+            st_v4_sys(slot + 16, z, epoch, w, epoch);
+        }
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long t0 = clock64();
+        for (int r = 0; r < p.world; r++) {                      // fixed rank order => bit-identical sums on every rank
+            const uint8_t *slot = local + OFF_LL + ((size_t)set * MAX_WORLD + r) * 2 * LL_MAX_BYTES + (size_t)i * 32;
+            uint4 lo, hi;
+            do {
+                lo = ld_v4_sys(slot); hi = ld_v4_sys(slot + 16);
+                if (clock64() - t0 > (1ll << 32)) break;           // a lost peer must not hang the GPU
+            } while (lo.y != epoch || lo.w != epoch || hi.y != epoch || hi.w != epoch);
+            const float bx = __uint_as_float(lo.x), by = __uint_as_float(lo.z), bz = __uint_as_float(hi.x), bw = __uint_as_float(hi.z);
+            if (r == 0) a = make_float4(bx, by, bz, bw);
+            else { a.x = __fadd_rn(a.x, bx); a.y = __fadd_rn(a.y, by); a.z = __fadd_rn(a.z, bz); a.w = __fadd_rn(a.w, bw); }
+        }
+        if (res) { const float4 b = res[i]; a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w); }
+        dst[i] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t *done = (uint32_t *)(local + 4);
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) { *done = 0; __threadfence(); *(volatile uint32_t *)local = epoch; }
+    }
+}
+
 __global__ void b200_add_f32_kernel(const float *a, const float *b, float *d, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __fadd_rn(a[i], b[i]);
@@ -172,6 +224,7 @@ int b200_comm_init(b200_ctx *ctx, const void *id128, int rank, int world) {
     void *buf = nullptr;
     if (cudaMalloc(&buf, EXCH_BYTES) != cudaSuccess) { cudaGetLastError(); delete c; b200_set_error("comm_init: exchange buffer"); return B200_ERR_ALLOC; }
     CUDA_TRY(cudaMemset(buf, 0, OFF_SLOTS));
+    CUDA_TRY(cudaMemset((uint8_t *)buf + OFF_LL, 0, EXCH_BYTES - OFF_LL));      // LL words must not hold a stale epoch
     c->local = (uint8_t *)buf;
     c->peer[rank] = c->local;
     ctx->comm = c;
@@ -249,6 +302,8 @@ int op_allreduce(b200_ctx *ctx, const b200_op *op) {
         OneShotParams p = {};
         for (int r = 0; r < world; r++) p.peer[r] = c->peer[r];
         p.src = src; p.residual = res; p.dst = dst; p.n = (int)n; p.rank = c->rank; p.world = world; p.use_pdl = ctx->opt_pdl;
+        static const int use_ll = getenv("GGML_B200_ALLREDUCE_LL") ? atoi(getenv("GGML_B200_ALLREDUCE_LL")) : 1;
+        const bool ll = use_ll && (size_t)n * 4 <= LL_MAX_BYTES;
         int ctas = (int)((n / 4 + 255) / 256);
         if (ctas > ONESHOT_CTAS) ctas = ONESHOT_CTAS;
         cudaLaunchConfig_t cfg = {};
@@ -257,7 +312,8 @@ int op_allreduce(b200_ctx *ctx, const b200_op *op) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = p.use_pdl ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_allreduce_oneshot_kernel, p));
+        if (ll) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_allreduce_ll_kernel, p));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_allreduce_oneshot_kernel, p));
         ctx->launches++;
         return B200_OK;
     }
