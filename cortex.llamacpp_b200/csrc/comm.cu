@@ -302,8 +302,10 @@ int op_allreduce(b200_ctx *ctx, const b200_op *op) {
         OneShotParams p = {};
         for (int r = 0; r < world; r++) p.peer[r] = c->peer[r];
         p.src = src; p.residual = res; p.dst = dst; p.n = (int)n; p.rank = c->rank; p.world = world; p.use_pdl = ctx->opt_pdl;
-        static const int use_ll = getenv("GGML_B200_ALLREDUCE_LL") ? atoi(getenv("GGML_B200_ALLREDUCE_LL")) : 1;
-        const bool ll = use_ll && (size_t)n * 4 <= LL_MAX_BYTES;
+        // measured on Llama-3-70B decode (profiles/r1_scale.md): flag-in-data wins at 2 ranks (6.3 vs 8.9 us per all-reduce) and loses
+        // at 8 (22 vs 15.9 us: twice the NVLink bytes and world x polling per element), so it is the default for 2 ranks only
+        static const int use_ll = getenv("GGML_B200_ALLREDUCE_LL") ? atoi(getenv("GGML_B200_ALLREDUCE_LL")) : -1;
+        const bool ll = (use_ll < 0 ? world <= 2 : use_ll != 0) && (size_t)n * 4 <= LL_MAX_BYTES;
         int ctas = (int)((n / 4 + 255) / 256);
         if (ctas > ONESHOT_CTAS) ctas = ONESHOT_CTAS;
         cudaLaunchConfig_t cfg = {};
