@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "quant_warp.cuh"
 #include "gemv.h"
+#include "gemv_bs1_items.cuh"
 
 namespace {
 
@@ -64,192 +65,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // unsigned bytes x signed bytes
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp2a_lo_su(uint32_t a16x2, uint32_t b8, int c) {   // a.lo16*b.byte0 + a.hi16*b.byte1 (signed x unsigned)
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8), "r"(c));
-    return d;
-}
-
-// ---------------------------------------------------------------------------------------------- Q4_K / Q5_K
-// item = 64 weights (one 32-byte qs group g of a 144/176-byte block): low nibbles -> sub-block 2g, high -> 2g+1
-template <bool Q5>
-__device__ __forceinline__ float item_q45k(const uint8_t *row, int it, const uint8_t *aq, const uint32_t *s32, const float *ad) {
-    constexpr int BYTES = Q5 ? 176 : 144;
-    const uint8_t *b = row + (it >> 2) * BYTES;
-    const int g = it & 3;
-    const uint4 hdr = *(const uint4 *)b;
-    const uint8_t *qp = b + (Q5 ? 48 : 16) + g * 32;
-    const uint4 qa = *(const uint4 *)qp, qb = *(const uint4 *)(qp + 16);
-    const uint8_t *ap = aq + it * 80;
-    // all eight 6-bit (scale, min) pairs as packed bytes (get_scale_min_k4, ggml-quants.c:631), then bytes 2g, 2g+1
-    const uint32_t sc_lo = hdr.y & 0x3f3f3f3fu, mn_lo = hdr.z & 0x3f3f3f3fu;
-    const uint32_t sc_hi = (hdr.w & 0x0f0f0f0fu) | ((hdr.y >> 2) & 0x30303030u);
-    const uint32_t mn_hi = ((hdr.w >> 4) & 0x0f0f0f0fu) | ((hdr.z >> 2) & 0x30303030u);
-    const uint32_t sel = 0x7710u + 0x22u * (uint32_t)g;            // result bytes: [2g], [2g+1], x, x
-    const uint32_t scp = __byte_perm(sc_lo, sc_hi, sel), mnp = __byte_perm(mn_lo, mn_hi, sel);
-    int sA, sB;
-    if (!Q5) {
-        const uint4 a0 = *(const uint4 *)ap, a1 = *(const uint4 *)(ap + 16);
-        int s0 = __dp4a((int)(qa.x & 0x0f0f0f0fu), (int)a0.x, 0), s1 = __dp4a((int)(qa.y & 0x0f0f0f0fu), (int)a0.y, 0);
-        s0 = __dp4a((int)(qa.z & 0x0f0f0f0fu), (int)a0.z, s0); s1 = __dp4a((int)(qa.w & 0x0f0f0f0fu), (int)a0.w, s1);
-        s0 = __dp4a((int)(qb.x & 0x0f0f0f0fu), (int)a1.x, s0); s1 = __dp4a((int)(qb.y & 0x0f0f0f0fu), (int)a1.y, s1);
-        s0 = __dp4a((int)(qb.z & 0x0f0f0f0fu), (int)a1.z, s0); s1 = __dp4a((int)(qb.w & 0x0f0f0f0fu), (int)a1.w, s1);
-        sA = s0 + s1;
-        const uint4 a2 = *(const uint4 *)(ap + 32), a3 = *(const uint4 *)(ap + 48);
-        // high nibbles stay in place: sum (16 q) a = 16 sum q a, exact in int32 (|sum| < 2^20)
-        int t0 = dp4a_us(qa.x & 0xf0f0f0f0u, a2.x, 0), t1 = dp4a_us(qa.y & 0xf0f0f0f0u, a2.y, 0);
-        t0 = dp4a_us(qa.z & 0xf0f0f0f0u, a2.z, t0); t1 = dp4a_us(qa.w & 0xf0f0f0f0u, a2.w, t1);
-        t0 = dp4a_us(qb.x & 0xf0f0f0f0u, a3.x, t0); t1 = dp4a_us(qb.y & 0xf0f0f0f0u, a3.y, t1);
-        t0 = dp4a_us(qb.z & 0xf0f0f0f0u, a3.z, t0); t1 = dp4a_us(qb.w & 0xf0f0f0f0u, a3.w, t1);
-        sB = (t0 + t1) >> 4;
-    } else {
-        const uint4 ha = *(const uint4 *)(b + 16), hb = *(const uint4 *)(b + 32);
-        const uint4 a0 = *(const uint4 *)ap, a1 = *(const uint4 *)(ap + 16), a2 = *(const uint4 *)(ap + 32), a3 = *(const uint4 *)(ap + 48);
-        const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-        const uint32_t hw[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-        const uint32_t al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const uint32_t ah[8] = {a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
-        int s0 = 0, s1 = 0, t0 = 0, t1 = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t hsh = hw[i] >> (2 * g);
-            const uint32_t lo = (qw[i] & 0x0f0f0f0fu) | ((hsh << 4) & 0x10101010u);
-            const uint32_t hi = ((qw[i] >> 4) & 0x0f0f0f0fu) | ((hsh << 3) & 0x10101010u);
-            if (i & 1) { s1 = __dp4a((int)lo, (int)al[i], s1); t1 = __dp4a((int)hi, (int)ah[i], t1); }
-            else       { s0 = __dp4a((int)lo, (int)al[i], s0); t0 = __dp4a((int)hi, (int)ah[i], t0); }
-        }
-        sA = s0 + s1; sB = t0 + t1;
-    }
-    const int P = (int)(scp & 0xffu) * sA + (int)((scp >> 8) & 0xffu) * sB;
-    const int M = dp2a_lo_su(s32[it], mnp, 0);
-    const float da = ad[it >> 2];
-    const float d = half_bits_to_float(hdr.x), dmin = half_bits_to_float(hdr.x >> 16);
-    return (d * da) * (float)P - (dmin * da) * (float)M;
-}
-
-// Whole 256-weight block per lane (16 lanes walk one row, the two half-warps take two rows of the stage at once): the 16-byte
-// header, the 6-bit scale unpack, d/dmin and the activation scale are paid once per 256 weights instead of once per 64
-// (~54 instead of ~80 instructions per 64 weights), and one shuffle tree reduces two rows.
-// Activations: aq at 272 bytes per block (256 + 16 pad: conflict-free 128-bit loads at lane stride), s32 8 x int16 per block.
-__device__ __forceinline__ int dp2a_hi_su(uint32_t a16x2, uint32_t b8, int c) {   // a.lo16*b.byte2 + a.hi16*b.byte3
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8), "r"(c));
-    return d;
-}
-template <bool Q5>
-__device__ __forceinline__ float block_q45k(const uint8_t *b, const uint8_t *ap, uint4 sums, float da) {
-    const uint4 hdr = *(const uint4 *)b;
-    const uint32_t sc_lo = hdr.y & 0x3f3f3f3fu, mn_lo = hdr.z & 0x3f3f3f3fu;
-    const uint32_t sc_hi = (hdr.w & 0x0f0f0f0fu) | ((hdr.y >> 2) & 0x30303030u);
-    const uint32_t mn_hi = ((hdr.w >> 4) & 0x0f0f0f0fu) | ((hdr.z >> 2) & 0x30303030u);
-    uint4 ha, hb;
-    if (Q5) { ha = *(const uint4 *)(b + 16); hb = *(const uint4 *)(b + 32); }
-    int P = 0;
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-        const uint8_t *qp = b + (Q5 ? 48 : 16) + g * 32;
-        const uint4 qa = *(const uint4 *)qp, qb = *(const uint4 *)(qp + 16);
-        const uint4 a0 = *(const uint4 *)(ap + g * 64), a1 = *(const uint4 *)(ap + g * 64 + 16);
-        const uint4 a2 = *(const uint4 *)(ap + g * 64 + 32), a3 = *(const uint4 *)(ap + g * 64 + 48);
-        int sA, sB;
-        if (!Q5) {
-            int s0 = __dp4a((int)(qa.x & 0x0f0f0f0fu), (int)a0.x, 0), s1 = __dp4a((int)(qa.y & 0x0f0f0f0fu), (int)a0.y, 0);
-            s0 = __dp4a((int)(qa.z & 0x0f0f0f0fu), (int)a0.z, s0); s1 = __dp4a((int)(qa.w & 0x0f0f0f0fu), (int)a0.w, s1);
-            s0 = __dp4a((int)(qb.x & 0x0f0f0f0fu), (int)a1.x, s0); s1 = __dp4a((int)(qb.y & 0x0f0f0f0fu), (int)a1.y, s1);
-            s0 = __dp4a((int)(qb.z & 0x0f0f0f0fu), (int)a1.z, s0); s1 = __dp4a((int)(qb.w & 0x0f0f0f0fu), (int)a1.w, s1);
-            sA = s0 + s1;
-            int t0 = dp4a_us(qa.x & 0xf0f0f0f0u, a2.x, 0), t1 = dp4a_us(qa.y & 0xf0f0f0f0u, a2.y, 0);      // high nibbles in place: 16x, exact
-            t0 = dp4a_us(qa.z & 0xf0f0f0f0u, a2.z, t0); t1 = dp4a_us(qa.w & 0xf0f0f0f0u, a2.w, t1);
-            t0 = dp4a_us(qb.x & 0xf0f0f0f0u, a3.x, t0); t1 = dp4a_us(qb.y & 0xf0f0f0f0u, a3.y, t1);
-            t0 = dp4a_us(qb.z & 0xf0f0f0f0u, a3.z, t0); t1 = dp4a_us(qb.w & 0xf0f0f0f0u, a3.w, t1);
-            sB = (t0 + t1) >> 4;
-        } else {
-            const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-            const uint32_t hw[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-            const uint32_t al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const uint32_t ah[8] = {a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
-            int s0 = 0, s1 = 0, t0 = 0, t1 = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t hsh = hw[i] >> (2 * g);
-                const uint32_t lo = (qw[i] & 0x0f0f0f0fu) | ((hsh << 4) & 0x10101010u);
-                const uint32_t hi = ((qw[i] >> 4) & 0x0f0f0f0fu) | ((hsh << 3) & 0x10101010u);
-                if (i & 1) { s1 = __dp4a((int)lo, (int)al[i], s1); t1 = __dp4a((int)hi, (int)ah[i], t1); }
-                else       { s0 = __dp4a((int)lo, (int)al[i], s0); t0 = __dp4a((int)hi, (int)ah[i], t0); }
-            }
-            sA = s0 + s1; sB = t0 + t1;
-        }
-        const uint32_t scw = g < 2 ? sc_lo : sc_hi;
-        const int sh = (g & 1) * 16;
-        P += (int)((scw >> sh) & 0xffu) * sA + (int)((scw >> (sh + 8)) & 0xffu) * sB;
-    }
-    int M = dp2a_lo_su(sums.x, mn_lo, 0);
-    M = dp2a_hi_su(sums.y, mn_lo, M);
-    M = dp2a_lo_su(sums.z, mn_hi, M);
-    M = dp2a_hi_su(sums.w, mn_hi, M);
-    const float d = half_bits_to_float(hdr.x), dmin = half_bits_to_float(hdr.x >> 16);
-    return (d * da) * (float)P - (dmin * da) * (float)M;
-}
-
-// ---------------------------------------------------------------------------------------------- Q6_K
-// item = 128 weights (half h of a 210-byte block: ql 64 B at 64h, qh 32 B at 128+32h, int8 scales 8 B at 192+8h, half d at 208).
-// Blocks are only 2-byte aligned: every 4-byte word is fetched as two aligned words and a PRMT whose selector is computed
-// from the address, so both alignments run the same instructions.
-__device__ __forceinline__ void ld4_words(const uint32_t *W, int word, uint32_t sel, uint32_t (&out)[4]) {
-    const uint32_t r0 = W[word], r1 = W[word + 1], r2 = W[word + 2], r3 = W[word + 3], r4 = W[word + 4];
-    out[0] = __byte_perm(r0, r1, sel); out[1] = __byte_perm(r1, r2, sel); out[2] = __byte_perm(r2, r3, sel); out[3] = __byte_perm(r3, r4, sel);
-}
-__device__ __forceinline__ float item_q6k(const uint8_t *row, int it, const uint8_t *aq, const uint4 *s16, const float *ad) {
-    const uint8_t *b = row + (it >> 1) * 210;
-    const int h = it & 1;
-    const uint32_t mis = (uint32_t)(uintptr_t)b & 2u;
-    const uint32_t *W = (const uint32_t *)(b - mis);
-    const uint32_t sel = mis ? 0x5432u : 0x3210u;
-    const uint8_t *ap = aq + it * 144;
-    const uint4 bs = s16[it];
-    const uint32_t bsw[4] = {bs.x, bs.y, bs.z, bs.w};
-    uint32_t S[2];
-    {
-        const int w = 48 + 2 * h;
-        const uint32_t r0 = W[w], r1 = W[w + 1], r2 = W[w + 2];
-        S[0] = __byte_perm(r0, r1, sel); S[1] = __byte_perm(r1, r2, sel);
-    }
-    int P = 0;
-#pragma unroll
-    for (int hs = 0; hs < 2; hs++) {
-        uint32_t H[4];
-        ld4_words(W, 32 + 8 * h + 4 * hs, sel, H);
-#pragma unroll
-        for (int tl = 0; tl < 2; tl++) {
-            uint32_t L[4];
-            ld4_words(W, 16 * h + 8 * tl + 4 * hs, sel, L);
-#pragma unroll
-            for (int nib = 0; nib < 2; nib++) {
-                const int t = tl + 2 * nib, sg = 2 * t + hs;
-                const uint4 a = *(const uint4 *)(ap + 16 * sg);
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-                int s = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t lo = nib ? (L[k] >> 4) : L[k];
-                    const uint32_t hi = t == 0 ? (H[k] << 4) : t == 1 ? (H[k] << 2) : t == 2 ? H[k] : (H[k] >> 2);
-                    s = __dp4a((int)((lo & 0x0f0f0f0fu) | (hi & 0x30303030u)), (int)aw[k], s);
-                }
-                // quants kept unsigned (0..63); the -32 offset goes through the activation bsums (exact)
-                const int bsum = (int)(int16_t)((sg & 1) ? (bsw[sg >> 1] >> 16) : (bsw[sg >> 1] & 0xffffu));
-                const int scale = (int)(int8_t)((S[sg >> 2] >> (8 * (sg & 3))) & 0xffu);
-                P += scale * (s - 32 * bsum);
-            }
-        }
-    }
-    const float d = half_bits_to_float(*(const uint16_t *)(b + 208));
-    return (d * ad[it >> 1]) * (float)P;
-}
+using namespace bs1;        // the block decoders live in gemv_bs1_items.cuh (host/device portable: tests/host_emul runs them on the CPU)
 
 // ---------------------------------------------------------------------------------------------- prologue
 // f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref
@@ -473,7 +289,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
     // ---------------------------------------------------------------------- consumers: main loop
     const uint8_t *aq64 = smem + p.off_aq64, *aq128 = smem + p.off_aq128;
     const uint32_t *s32 = (const uint32_t *)(smem + p.off_s32);
-    const uint4 *s16 = (const uint4 *)(smem + p.off_s16);
+    const U4 *s16 = (const U4 *)(smem + p.off_s16);
     const float *ad = (const float *)(smem + p.off_ad);
     const int nblk = p.K >> 8, nit128 = p.K >> 7;
 #pragma unroll 1
@@ -500,7 +316,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
                 const bool q5 = (TYPES & TB_Q5_K) && (TYPES == TB_Q5_K || ty == B200_TYPE_Q5_K);
                 const int lpr = (nblk >= 32 && sg.R == 1) ? 32 : 16, rpp = 32 / lpr;          // lanes per row, rows per pass
                 const int sub = lane / lpr, bl = lane % lpr;
-                const uint4 *sums4 = (const uint4 *)s32;
+                const U4 *sums4 = (const U4 *)s32;
                 const uint32_t bbytes = q5 ? 176u : 144u;
 #pragma unroll 1
                 for (int r = 0; r < nr; r += rpp) {
