@@ -17,12 +17,19 @@ void b200_set_error(const char *fmt, ...) {
     if (getenv("GGML_B200_DEBUG")) fprintf(stderr, "[ggml-b200] error: %s\n", g_err);
 }
 
+void graph_cache_free(b200_ctx *ctx);   // graph.cu
+
 void *b200_ctx::get_scratch(int slot, size_t size) {
     if (size <= scratch_size[slot]) return scratch[slot];
     if (capturing) { b200_set_error("scratch growth during graph capture"); return nullptr; }
     size_t want = size + size / 4;
     want = (want + 255) & ~(size_t)255;
     cudaStreamSynchronize(stream);
+    // captured cudaGraphExec entries have the OLD scratch pointers baked into their kernel nodes: a replay after this
+    // reallocation would read and write freed memory.  Drop every captured graph (they are re-captured on the next
+    // sightings); scratch growth is rare (sizes grow by 25% and the large areas are allocated at their upper bound).
+    graph_cache_free(this);
+    scratch_gen++;
     if (scratch[slot]) cudaFree(scratch[slot]);
     scratch[slot] = nullptr; scratch_size[slot] = 0;
     void *p = nullptr;
@@ -32,7 +39,6 @@ void *b200_ctx::get_scratch(int slot, size_t size) {
 }
 
 struct b200_event { int device; cudaEvent_t ev; };
-void graph_cache_free(b200_ctx *ctx);   // graph.cu
 extern int g_gemm_desc_swap;            // gemm_i8.cu
 
 extern "C" {
@@ -88,6 +94,7 @@ b200_ctx *b200_ctx_create(int device) {
     if (const char *e = getenv("GGML_B200_GRAPHS")) ctx->opt_cuda_graphs = atoi(e);
     if (const char *e = getenv("GGML_B200_FUSION")) ctx->opt_fusion = atoi(e);
     if (const char *e = getenv("GGML_B200_PDL")) ctx->opt_pdl = atoi(e);
+    if (const char *e = getenv("GGML_B200_FA_EXACT")) ctx->opt_fa_exact = atoi(e);
     return ctx;
 }
 
@@ -116,7 +123,7 @@ int b200_synchronize(b200_ctx *ctx) {
 int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     std::string k(key);
     int *slot = k == "fusion" ? &ctx->opt_fusion : k == "pdl" ? &ctx->opt_pdl : k == "l2_prefetch" ? &ctx->opt_l2_prefetch :
-                k == "debug_skip" ? &ctx->opt_debug_skip : nullptr;
+                k == "debug_skip" ? &ctx->opt_debug_skip : k == "fa_exact" ? &ctx->opt_fa_exact : nullptr;
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
     else if (slot) {
         if (*slot != value) {                 // captured graphs bake these options in: drop them

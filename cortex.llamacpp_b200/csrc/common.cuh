@@ -123,11 +123,13 @@ struct b200_ctx {
     void *        scratch[5]      = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t        scratch_size[5] = {0, 0, 0, 0, 0};
     int64_t       launches = 0;
+    int64_t       scratch_gen = 0;          // bumped on every scratch reallocation (captured graphs are dropped with it)
     // options
     int           opt_cuda_graphs = 0;
     int           opt_fusion      = 2;      // 0 off, 1 two-op fusions, 2 + llama layer fusions for decode ubatches
     int           opt_pdl         = 0;
     int           opt_l2_prefetch = 0;      // L2 look-ahead of the next matmul's weights: measured neutral on B200 (profiles/r1_gemv_diag.md), off
+    int           opt_fa_exact    = 0;      // 1: f16-cache flash attention reproduces the CPU's fp16 V accumulator cell by cell (parity mode, serial over n_kv)
     int           opt_debug_skip  = 0;      // timing experiments only: bit 0 flash_attn, 1 rope+store, 2 GEMV are not launched
     GraphCache *  graph_cache = nullptr;
     void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)

@@ -580,6 +580,100 @@ __global__ void __launch_bounds__(128) b200_fattn_combine_kernel(const FaParams 
     for (int j = 0; j < PER; j++) o[lane + 32 * j] = acc[j] / L;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "cpu-exact" mode for an f16 cache (option fa_exact / GGML_B200_FA_EXACT=1).  The reference CPU path accumulates f16 V rows
+// in an FP16 accumulator, cell by cell, rounding after every step (VKQ16: ggml_vec_scale_f16 / ggml_vec_mad_f16,
+// ggml-cpu.c:12376-12390) -- about 1e-2 of relative noise at a few hundred cells, which no f32 kernel can agree with.  This
+// kernel restates that arithmetic: one warp per (query column, head), cells in order, masked cells skipped, K.Q with the
+// accumulator layout of ggml_vec_dot_f16 on the AVX2 build (4 x 8 FMA lanes over 32-element steps, then the
+// GGML_F32x8_REDUCE tree, ggml-cpu.c:671-689, 1565-1605), the running maximum / rescale logic of :12359-12395, and an
+// accumulator that is rounded to fp16 after the rescale and after every fused multiply-add.  Only libm-vs-CUDA expf ulps
+// remain.  It is a serial chain over n_kv, so it is the parity mode, not the fast mode (the default kernel above
+// accumulates in f32 and is closer to exact attention: tests/test_gpu_fattn.py bounds both against f64).
+template <int D>
+__global__ void __launch_bounds__(128) b200_fattn_f16acc_kernel(const FaParams p) {
+    constexpr int PER = D / 32;
+    __shared__ float sq[4][D];
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + warp;
+    if (wid >= p.n_q * p.H) return;
+    const int col = wid / p.H, head = wid % p.H, hk = head / p.gq;
+    const float *qp = (const float *)(p.q + (uint64_t)col * p.q_nb1 + (uint64_t)head * p.q_nb2);
+#pragma unroll
+    for (int i = 0; i < PER; i++) sq[warp][lane + 32 * i] = __half2float(__float2half_rn(qp[lane + 32 * i]));
+    __syncwarp();
+    float slope = 1.0f;
+    if (p.max_bias > 0.0f) slope = head < p.n_head_log2 ? powf(p.m0, (float)(head + 1)) : powf(p.m1, (float)(2 * (head - p.n_head_log2) + 1));
+    const char *kbase = p.k + (uint64_t)hk * p.k_nb2;
+    const char *vbase = p.v + (uint64_t)hk * p.v_nb2;
+    const __half *mp = p.mask ? (const __half *)(p.mask + (uint64_t)col * p.m_nb1) : nullptr;
+    float M = -INFINITY, S = 0.0f;
+    float acc[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) acc[i] = 0.0f;
+    for (int c0 = 0; c0 < p.n_kv; c0 += 32) {
+        const int ic = c0 + lane;
+        float s = 0.0f;
+        bool skip = ic >= p.n_kv;
+        float mv = 0.0f;
+        if (!skip && mp) { mv = __fmul_rn(slope, __half2float(mp[ic])); skip = mv == -INFINITY; }
+        if (!skip) {
+            const uint4 *kr = (const uint4 *)(kbase + (uint64_t)ic * p.k_nb1);
+            float sum[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D / 32; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint4 kv = kr[i * 4 + j];
+                    const __half2 *h = (const __half2 *)&kv;
+                    const float *qq = &sq[warp][i * 32 + j * 8];
+#pragma unroll
+                    for (int l = 0; l < 4; l++) {
+                        const float2 kf = __half22float2(h[l]);
+                        sum[j][2 * l] = __fmaf_rn(kf.x, qq[2 * l], sum[j][2 * l]);
+                        sum[j][2 * l + 1] = __fmaf_rn(kf.y, qq[2 * l + 1], sum[j][2 * l + 1]);
+                    }
+                }
+            float x0[8];
+#pragma unroll
+            for (int l = 0; l < 8; l++) x0[l] = __fadd_rn(__fadd_rn(sum[0][l], sum[2][l]), __fadd_rn(sum[1][l], sum[3][l]));
+            const float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]), t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
+            s = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+            s = __fmul_rn(s, p.scale);
+            if (p.softcap != 0.0f) s = __fmul_rn(p.softcap, tanhf(s));
+            s = __fadd_rn(s, mv);
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, !skip);
+        for (int t = 0; t < 32; t++) {
+            if (!((live >> t) & 1u)) continue;
+            const float sc = __shfl_sync(0xffffffffu, s, t);
+            const __half *vr = (const __half *)(vbase + (uint64_t)(c0 + t) * p.v_nb1) + lane * PER;
+            float vv[PER];
+            if (PER == 4) { const uint2 raw = *(const uint2 *)vr; const float2 a = __half22float2(*(const __half2 *)&raw.x), b = __half22float2(*(const __half2 *)&raw.y); vv[0] = a.x; vv[1] = a.y; vv[PER - 2] = b.x; vv[PER - 1] = b.y; }
+            else { const float2 a = __half22float2(*(const __half2 *)vr); vv[0] = a.x; vv[1] = a.y; }
+            float ms = 1.0f, vs = 1.0f;
+            if (sc > M) {
+                ms = expf(M - sc);
+                M = sc;
+#pragma unroll
+                for (int i = 0; i < PER; i++) acc[i] = __half2float(__float2half_rn(__fmul_rn(acc[i], ms)));
+            } else vs = expf(sc - M);
+#pragma unroll
+            for (int i = 0; i < PER; i++) acc[i] = __half2float(__float2half_rn(__fmaf_rn(vv[i], vs, acc[i])));
+            S = __fadd_rn(__fmul_rn(S, ms), vs);
+        }
+    }
+    const float Sinv = __fdiv_rn(1.0f, S);
+    float *o = p.dst + ((uint64_t)col * p.H + head) * D + lane * PER;
+#pragma unroll
+    for (int i = 0; i < PER; i++) o[i] = __fmul_rn(acc[i], Sinv);
+}
+
 int kv_kind(int type) { return type == B200_TYPE_F16 ? KV_F16 : type == B200_TYPE_Q8_0 ? KV_Q8_0 : type == B200_TYPE_Q4_0 ? KV_Q4_0 : -1; }
 
 template <int D, int KT, int VT>
@@ -683,6 +777,22 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     p.m1 = powf(2.0f, -(p.max_bias / 2.0f) / p.n_head_log2);
     const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;
     if (n_tiles == 0 || p.n_q == 0) return B200_OK;
+    // parity mode: reproduce the CPU's fp16 V accumulator (see b200_fattn_f16acc_kernel)
+    if (ctx->opt_fa_exact && kv_kind(k.type) == KV_F16 && kv_kind(v.type) == KV_F16) {
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((p.n_q * p.H + 3) / 4));
+        cfg.blockDim = dim3(128);
+        cfg.stream = ctx->stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = p.use_pdl ? 1 : 0;
+        if (D == 128) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<128>, p));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<64>, p));
+        ctx->launches++;
+        return B200_OK;
+    }
     // single-token decode over an f16 cache: the vector kernel (one warp per 32 positions, all heads of the group).  Parity green,
     // but measured SLOWER than the mma tile kernel in round 1 (10.5 + 9.2 us with 24 splits to merge vs 9.5 + 5.1 us; 499 vs
     // 536 tok/s on Llama-3-8B bs1), so it is opt-in until its latency chain is understood
@@ -730,7 +840,9 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     ns = (p.n_kv + p.kv_per_split - 1) / p.kv_per_split;
     p.n_splits = ns;
     if (ns > 1) {
-        p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)n_tiles * ns * 16 * (D + 2) * 4);
+        // sized by its upper bound (n_tiles * ns <= 3 * sm_count + n_tiles) so that a growing n_kv never reallocates it under
+        // captured graphs
+        p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)(3 * ctx->sm_count + n_tiles) * 16 * (D + 2) * 4);
         if (!p.part) return B200_ERR_ALLOC;
         // merging the splits in the last-arriving CTA instead of a second kernel was measured SLOWER on B200 (471 vs 523 tok/s on
         // Llama-3-8B bs1: a PDL kernel boundary costs ~1 us, the serialised fence + atomic + 128-thread merge costs more): off

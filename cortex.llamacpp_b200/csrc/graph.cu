@@ -116,14 +116,6 @@ static bool live_after(const b200_op *ops, int n, int from, const b200_tensor &t
     }
     return false;
 }
-// is tensor t read by any op in [from, n) other than `except`?  (old, address-only test for the two-op fusions)
-static bool read_later(const b200_op *ops, int n, int from, int except, const b200_tensor &t) {
-    for (int i = from; i < n; i++) {
-        if (i == except) continue;
-        for (int s = 0; s < ops[i].n_src; s++) if (ops[i].src[s].data == t.data) return true;
-    }
-    return false;
-}
 
 static bool is_vec_f32(const b200_tensor &t, int64_t rows) {   // dense f32 [rows, T<=4]
     return t.type == B200_TYPE_F32 && t.ne[0] == rows && t.ne[1] >= 1 && t.ne[1] <= 4 && t.ne[2] == 1 && t.ne[3] == 1 && t.nb[0] == 4 &&
@@ -394,7 +386,7 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
             // RMS_NORM -> MUL(norm, weight): y = rms_norm(x) * w
             if (a.op == B200_OP_RMS_NORM && b.op == B200_OP_MUL && same_tensor(b.src[0], a.dst) && b.src[1].type == B200_TYPE_F32 &&
                 b.src[1].nb[0] == 4 && b.src[1].ne[0] == a.dst.ne[0] &&
-                (b.dst.data == a.dst.data || !read_later(ops, n, i + 2, -1, a.dst))) {
+                (b.dst.data == a.dst.data || !live_after(ops, n, i + 2, a.dst))) {
                 b200_op f = a;
                 f.op = B200_OP_RMS_NORM_MUL;
                 f.n_src = 2;
@@ -404,7 +396,7 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
             }
             // SILU(gate) -> MUL(silu, up)
             if (a.op == B200_OP_SILU && b.op == B200_OP_MUL && same_tensor(b.src[0], a.dst) &&
-                (b.dst.data == a.dst.data || !read_later(ops, n, i + 2, -1, a.dst))) {
+                (b.dst.data == a.dst.data || !live_after(ops, n, i + 2, a.dst))) {
                 b200_op f = a;
                 f.op = B200_OP_SWIGLU_FUSED;
                 f.n_src = 2;

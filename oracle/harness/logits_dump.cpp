@@ -5,6 +5,9 @@
 // Output: int32 n_rows, int32 n_vocab, then n_rows*n_vocab f32.  Also prints per-phase timings.
 // OUT.bin == "-" is bench mode (bench.py e2e / --impl reference legs): nothing is stored, the prompt only asks for the
 // logits of its last token, and env LOGITS_DUMP_WARMUP=W runs W untimed decode steps before the n_gen timed ones.
+// env LOGITS_DUMP_GREEDY=1: instead of teacher forcing, every slot feeds back the argmax of its previous logits row
+// (llama-cli --temp 0 --top-k 1); the chosen token ids are written to OUT.bin.tok (int32 [n_gen][n_parallel]) so two
+// backends' greedy streams can be compared token for token.  env LOGITS_DUMP_SEED=S reseeds the synthetic prompt.
 #include "llama.h"
 #include "ggml.h"
 #include "ggml-backend.h"
@@ -12,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 // optional per-node dump (env LOGITS_DUMP_NODES=file): every f32 node output of every graph, in execution order,
@@ -61,6 +65,11 @@ int main(int argc, char **argv) {
     const int V = llama_vocab_n_tokens(llama_model_get_vocab(model));
     // seeded token ids in [3, V)
     uint64_t s = 0x9E3779B97F4A7C15ull;
+    if (const char *sd = getenv("LOGITS_DUMP_SEED")) s ^= (uint64_t)atoll(sd) * 0xD1B54A32D192ED03ull;
+    const bool greedy = getenv("LOGITS_DUMP_GREEDY") && atoi(getenv("LOGITS_DUMP_GREEDY")) != 0;
+    std::vector<llama_token> last_tok((size_t)n_par, 0);
+    std::vector<int32_t> stream;
+    auto argmax = [&](const float *l) { int b = 0; for (int i = 1; i < V; i++) if (l[i] > l[b]) b = i; return (llama_token)b; };
     auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (llama_token)(3 + (s % (uint64_t)(V - 3))); };
     std::vector<float> all;
     int rows = 0;
@@ -77,6 +86,7 @@ int main(int argc, char **argv) {
     llama_synchronize(ctx);
     const double t_prefill = now_ms() - t0;
     if (!bench) for (int j = 0; j < batch.n_tokens; j++) { const float *l = llama_get_logits_ith(ctx, j); all.insert(all.end(), l, l + V); rows++; }
+    if (greedy) for (int p = 0; p < n_par; p++) last_tok[p] = argmax(llama_get_logits_ith(ctx, p * n_prompt + n_prompt - 1));
     // ---- decode: one token per slot per step, teacher forced ----
     t0 = now_ms();
     float sink = 0.0f;
@@ -85,13 +95,15 @@ int main(int argc, char **argv) {
         batch.n_tokens = 0;
         for (int p = 0; p < n_par; p++) {
             const int j = batch.n_tokens++;
-            batch.token[j] = next(); batch.pos[j] = n_prompt + n_warm + g; batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = 1;
+            batch.token[j] = greedy ? last_tok[p] : next(); batch.pos[j] = n_prompt + n_warm + g;
+            if (greedy) stream.push_back(batch.token[j]); batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = 1;
         }
         if (llama_decode(ctx, batch) != 0) { fprintf(stderr, "decode failed at %d\n", g); return 1; }
         // reading the logits is what the sampler does every step: it forces the device->host copy + synchronize
         for (int j = 0; j < batch.n_tokens; j++) {
             const float *l = llama_get_logits_ith(ctx, j);
             if (bench) sink += l[0] + l[V - 1]; else { all.insert(all.end(), l, l + V); rows++; }
+            if (greedy) last_tok[j] = argmax(l);
         }
     }
     llama_synchronize(ctx);
@@ -99,6 +111,11 @@ int main(int argc, char **argv) {
     if (!bench) {
         FILE *f = fopen(out_path, "wb");
         fwrite(&rows, 4, 1, f); fwrite(&V, 4, 1, f); fwrite(all.data(), 4, all.size(), f); fclose(f);
+        if (greedy) {
+            std::string tp = std::string(out_path) + ".tok";
+            FILE *ft = fopen(tp.c_str(), "wb");
+            fwrite(stream.data(), 4, stream.size(), ft); fclose(ft);
+        }
     } else if (sink != sink) fprintf(stderr, "nan in logits\n");
     printf("{\"ngl\": %d, \"n_parallel\": %d, \"n_prompt\": %d, \"n_gen\": %d, \"kv\": \"%s\", \"prefill_ms\": %.3f, \"prefill_tok_s\": %.1f, \"decode_ms\": %.3f, \"decode_tok_s\": %.1f}\n",
            ngl, n_par, n_prompt, n_gen, kv, t_prefill, 1000.0 * n_prompt * n_par / t_prefill, t_decode, n_gen > 0 ? 1000.0 * n_gen * n_par / t_decode : 0.0);

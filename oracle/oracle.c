@@ -478,6 +478,27 @@ void orc_silu_mul(const float *gate, const float *up, float *y, int64_t n) {
 
 /* ---------------------------------------------------------------- flash attention */
 
+/* ggml_vec_dot_f16 as the AVX2 + F16C + FMA build computes it (ggml-cpu.c:1565-1605 with GGML_F16_STEP 32, GGML_F16_EPR 8,
+ * :704-705): four 8-lane f32 accumulators, one FMA per element, then GGML_F32x8_REDUCE (:671-689):
+ * (s0+s2)+(s1+s3) lane-wise, low half + high half, two horizontal adds.  k: f16 bits, q: f32 values already rounded to f16 */
+static float dot_f16_simd_order(const uint8_t *k, const float *q, int64_t n) {
+    float sum[4][8];
+    for (int j = 0; j < 4; j++) for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
+    const int64_t np = n & ~(int64_t)31;
+    for (int64_t i = 0; i < np; i += 32)
+        for (int j = 0; j < 4; j++)
+            for (int l = 0; l < 8; l++) {
+                const int64_t e = i + 8 * j + l;
+                sum[j][l] = fmaf(orc_f16_to_f32(rd16(k + 2 * e)), q[e], sum[j][l]);
+            }
+    float x0[8], t[4];
+    for (int l = 0; l < 8; l++) x0[l] = (sum[0][l] + sum[2][l]) + (sum[1][l] + sum[3][l]);
+    for (int l = 0; l < 4; l++) t[l] = x0[l] + x0[l + 4];
+    double sumf = (double)((t[0] + t[1]) + (t[2] + t[3]));
+    for (int64_t e = np; e < n; e++) sumf += (double)(orc_f16_to_f32(rd16(k + 2 * e)) * q[e]);
+    return (float)sumf;
+}
+
 void orc_flash_attn_ext(const float *q, const void *k, const void *v, const uint16_t *mask, float *dst,
                         int64_t D, int64_t n_q, int64_t H, int64_t n_kv, int64_t Hkv,
                         int type_k, int type_v,
@@ -504,10 +525,8 @@ void orc_flash_attn_ext(const float *q, const void *k, const void *v, const uint
                 const uint8_t *kr = (const uint8_t *)k + ic * k_nb1 + (h / gq) * k_nb2;
                 const uint8_t *vr = (const uint8_t *)v + ic * v_nb1 + (h / gq) * v_nb2;
                 float s;
-                if (type_k == ORC_TYPE_F16) {
-                    double t = 0; for (int64_t d = 0; d < D; d++) t += (double)orc_f16_to_f32(rd16(kr + 2 * d)) * qf[d];
-                    s = (float)t;
-                } else s = orc_vec_dot(type_k, kr, qq, D);
+                if (type_k == ORC_TYPE_F16) s = dot_f16_simd_order(kr, qf, D);
+                else s = orc_vec_dot(type_k, kr, qq, D);
                 s *= scale;
                 if (logit_softcap != 0.0f) s = logit_softcap * tanhf(s);
                 s += mv;
@@ -519,7 +538,7 @@ void orc_flash_attn_ext(const float *q, const void *k, const void *v, const uint
                     for (int64_t d = 0; d < D; d++) {
                         float a16 = orc_f16_to_f32(acc16[d]);
                         if (ms != 1.0f) a16 = orc_f16_to_f32(orc_f32_to_f16(a16 * ms));
-                        a16 = a16 + orc_f16_to_f32(rd16(vr + 2 * d)) * vs;
+                        a16 = fmaf(orc_f16_to_f32(rd16(vr + 2 * d)), vs, a16);      /* GGML_F16_VEC_FMA = _mm256_fmadd_ps (ggml-cpu.c:665, 1706) */
                         acc16[d] = orc_f32_to_f16(a16);
                     }
                 } else {

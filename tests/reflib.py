@@ -225,3 +225,126 @@ def ref():
     if _ref is None:
         _ref = _Ref()
     return _ref
+
+
+# ----------------------------------------------------------------------------- one-op ggml graphs on the reference CPU backend
+class _InitParams(C.Structure):
+    _fields_ = [("mem_size", C.c_size_t), ("mem_buffer", C.c_void_p), ("no_alloc", C.c_bool)]
+
+
+class RefGraph:
+    """Builds and runs a small ggml graph on the reference's CPU backend through its public C API (ggml.h / ggml-cpu.h),
+    the way tests/test-backend-ops.cpp does.  Used by tests/golden/make_golden_ops.py (fixtures) and, when oracle/_ref is
+    present, directly by tests/test_oracle_pin.py."""
+
+    def __init__(self, mem_mb=256):
+        r = ref()
+        self.b, self.c = r.base, r.cpu
+        b = self.b
+        vp, i64, f32, i32 = C.c_void_p, C.c_int64, C.c_float, C.c_int
+        b.ggml_init.restype = vp
+        b.ggml_init.argtypes = [_InitParams]
+        b.ggml_free.argtypes = [vp]
+        b.ggml_new_tensor_4d.restype = vp
+        b.ggml_new_tensor_4d.argtypes = [vp, i32, i64, i64, i64, i64]
+        b.ggml_get_data.restype = vp
+        b.ggml_get_data.argtypes = [vp]
+        b.ggml_nbytes.restype = C.c_size_t
+        b.ggml_nbytes.argtypes = [vp]
+        for name, args in {
+            "ggml_rms_norm": [vp, vp, f32], "ggml_mul": [vp, vp, vp], "ggml_add": [vp, vp, vp], "ggml_silu": [vp, vp],
+            "ggml_rope_ext": [vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, f32, f32],
+            "ggml_soft_max_ext": [vp, vp, vp, f32, f32],
+            "ggml_flash_attn_ext": [vp, vp, vp, vp, vp, f32, f32, f32],
+            "ggml_cpy": [vp, vp, vp], "ggml_cont": [vp, vp], "ggml_permute": [vp, vp, i32, i32, i32, i32],
+            "ggml_get_rows": [vp, vp, vp], "ggml_mul_mat": [vp, vp, vp], "ggml_new_graph": [vp],
+        }.items():
+            fn = getattr(b, name)
+            fn.restype = vp
+            fn.argtypes = args
+        b.ggml_flash_attn_ext_set_prec.argtypes = [vp, i32]
+        b.ggml_build_forward_expand.argtypes = [vp, vp]
+        self.c.ggml_graph_compute_with_ctx.argtypes = [vp, vp, i32]
+        self.c.ggml_graph_compute_with_ctx.restype = i32
+        self.ctx = b.ggml_init(_InitParams(mem_mb << 20, None, False))
+        assert self.ctx
+
+    def close(self):
+        self.b.ggml_free(self.ctx)
+        self.ctx = None
+
+    def tensor(self, t, ne, data=None):
+        ne = list(ne) + [1] * (4 - len(ne))
+        x = self.b.ggml_new_tensor_4d(self.ctx, t, *ne)
+        if data is not None:
+            data = np.ascontiguousarray(data)
+            n = self.b.ggml_nbytes(x)
+            assert data.nbytes == n, (data.nbytes, n)
+            C.memmove(self.b.ggml_get_data(x), _ptr(data), n)
+        return x
+
+    def run(self, out, dtype, shape, threads=4):
+        g = self.b.ggml_new_graph(self.ctx)
+        self.b.ggml_build_forward_expand(g, out)
+        assert self.c.ggml_graph_compute_with_ctx(self.ctx, g, threads) == 0
+        n = self.b.ggml_nbytes(out)
+        buf = np.zeros(n, np.uint8)
+        C.memmove(_ptr(buf), self.b.ggml_get_data(out), n)
+        return buf.view(dtype).reshape(shape).copy()
+
+
+def ref_rms_norm(x, eps):
+    g = RefGraph()
+    rows, n = x.shape
+    y = g.run(g.b.ggml_rms_norm(g.ctx, g.tensor(F32, [n, rows], x.astype(np.float32)), eps), np.float32, (rows, n))
+    g.close()
+    return y
+
+
+def ref_rope(x, pos, n_dims, mode, freq_base, freq_scale=1.0, ext_factor=0.0, attn_factor=1.0, beta_fast=32.0, beta_slow=1.0,
+             n_ctx_orig=4096, freq_factors=None):
+    """x f32 [n_tok, n_head, ne0]"""
+    g = RefGraph()
+    n_tok, n_head, ne0 = x.shape
+    a = g.tensor(F32, [ne0, n_head, n_tok], x.astype(np.float32))
+    p = g.tensor(I32, [n_tok], np.asarray(pos, np.int32))
+    ff = g.tensor(F32, [ne0 // 2], np.asarray(freq_factors, np.float32)) if freq_factors is not None else None
+    out = g.b.ggml_rope_ext(g.ctx, a, p, ff, n_dims, mode, n_ctx_orig, freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow)
+    y = g.run(out, np.float32, (n_tok, n_head, ne0))
+    g.close()
+    return y
+
+
+def ref_soft_max(x, mask_f16, scale):
+    g = RefGraph()
+    rows, n = x.shape
+    a = g.tensor(F32, [n, rows], x.astype(np.float32))
+    m = g.tensor(F16, [n, mask_f16.shape[0]], mask_f16.astype(np.float16)) if mask_f16 is not None else None
+    y = g.run(g.b.ggml_soft_max_ext(g.ctx, a, m, scale, 0.0), np.float32, (rows, n))
+    g.close()
+    return y
+
+
+def ref_silu_mul(gate, up):
+    g = RefGraph()
+    n = gate.size
+    a = g.tensor(F32, [n], gate.astype(np.float32))
+    b = g.tensor(F32, [n], up.astype(np.float32))
+    y = g.run(g.b.ggml_mul(g.ctx, g.b.ggml_silu(g.ctx, a), b), np.float32, gate.shape)
+    g.close()
+    return y
+
+
+def ref_flash_attn(q, k_bytes, v_bytes, mask_f16, D, n_kv, Hkv, type_k, type_v, scale, softcap=0.0):
+    """same contract as orc_flash_attn: q f32 [H, n_q, D]; k/v uint8 [Hkv, n_kv, row_size]; mask f16 [n_q_pad, n_kv] -> [n_q, H, D]"""
+    g = RefGraph()
+    H, n_q, _ = q.shape
+    qt = g.tensor(F32, [D, n_q, H], q.astype(np.float32))
+    kt = g.tensor(type_k, [D, n_kv, Hkv], k_bytes)
+    vt = g.tensor(type_v, [D, n_kv, Hkv], v_bytes)
+    mt = g.tensor(F16, [n_kv, mask_f16.shape[0]], mask_f16.astype(np.float16)) if mask_f16 is not None else None
+    out = g.b.ggml_flash_attn_ext(g.ctx, qt, kt, vt, mt, scale, 0.0, softcap)
+    g.b.ggml_flash_attn_ext_set_prec(out, 1)         # GGML_PREC_F32 (ggml.h:395-398), as llama.cpp sets it (llama-graph.cpp:1197)
+    y = g.run(out, np.float32, (n_q, H, D))
+    g.close()
+    return y

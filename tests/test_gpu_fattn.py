@@ -149,3 +149,27 @@ def test_flash_attn_integer_kq_exactness(b200, ctx):
     vdeq = R.orc_dequantize(R.Q8_0, vb.reshape(-1), D).reshape(Hkv, n_kv, D)
     want = vdeq[:, 77, :][None]
     assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("D,H,Hkv,n_q,n_kv", [(128, 32, 8, 1, 512), (128, 8, 2, 5, 256), (64, 32, 4, 1, 512), (64, 8, 4, 3, 192), (128, 4, 1, 1, 2048)])
+def test_flash_attn_cpu_exact_f16_accumulator_mode(b200, ctx, D, H, Hkv, n_q, n_kv):
+    """option fa_exact: the f16-cache kernel that restates the reference's FP16 V accumulator (ggml-cpu.c:12376-12390) cell by
+    cell.  The oracle's f16 path is bit-identical to the reference (tests/test_oracle_pin.py); the GPU may differ from it only
+    where CUDA's expf and glibc's differ by an ulp (a handful of fp16 rounding flips), i.e. orders of magnitude below the
+    ~1e-2 noise the accumulator itself carries."""
+    rng = np.random.default_rng(D + H + n_q + n_kv)
+    q, kb, vb, mask = make_case(rng, D, H, Hkv, n_q, n_kv, R.F16, causal_from=n_kv - n_q - 3)
+    scale = 1.0 / np.sqrt(D)
+    want = R.orc_flash_attn(q, kb, vb, mask, D, n_kv, Hkv, R.F16, R.F16, scale)
+    fast = run_fa(b200, ctx, q, kb, vb, mask, D, n_kv, Hkv, R.F16, scale)
+    ctx.set_option("fa_exact", 1)
+    try:
+        got = run_fa(b200, ctx, q, kb, vb, mask, D, n_kv, Hkv, R.F16, scale)
+    finally:
+        ctx.set_option("fa_exact", 0)
+    assert np.isfinite(got).all()
+    same = float((got == want).mean())
+    err, err_fast = np.abs(got - want).max() / np.abs(want).max(), np.abs(fast - want).max() / np.abs(want).max()
+    print("fa_exact: bit-identical elements %.4f, max rel err %.3g (fast mode %.3g)" % (same, err, err_fast))
+    assert same >= 0.97 and err <= 2e-3, (same, err)
+    assert nmse(got, want) <= 1e-8

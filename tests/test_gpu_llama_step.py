@@ -146,3 +146,49 @@ def test_llama_decode_graph_replay_follows_kv_head(b200, ctx, kv):
     assert all(n > 1 for n in outs[0][1])
     ctx.set_option("pdl", 0)
     ctx.set_option("cuda_graphs", 0)
+
+
+def test_graph_replay_survives_scratch_growth(b200, ctx):
+    """a captured graph bakes scratch pointers in; growing a scratch area (a later, larger ubatch) frees
+    and reallocates it.  Replaying the earlier graph afterwards must not touch freed memory: capture a decode step at
+    n_kv = 256, run a 64-token prompt ubatch and a decode step over the whole 2048-cell cache (both grow scratch areas),
+    then submit the first op list again and compare with its eager result bit for bit."""
+    import torch
+    from __graft_entry__ import load_llama_graph
+    lg = load_llama_graph()
+    g = lg.LlamaGraph(b200, model="tiny-d128", ftype="q4_k_m", kv="f16", n_ctx=2048, max_tokens=64)
+    rng = np.random.default_rng(9)
+
+    def load(T, kv_head, n_kv):
+        emb, pos, mask = g.set_inputs_host(T, kv_head, n_kv, rng)
+        g.inp_embd[:T * g.E] = torch.from_numpy(emb.reshape(-1)).cuda()
+        g.pos[:T] = torch.from_numpy(pos).cuda()
+        g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda()
+        torch.cuda.synchronize()
+        return emb, pos, mask
+    g.fill_cache(2000)
+    small = load(1, 100, 256)
+    ops_small = g.build(1, 100, 256)
+    ctx.set_option("fusion", 2); ctx.set_option("pdl", 1); ctx.set_option("cuda_graphs", 0)
+    ctx.compute(ops_small); ctx.sync()
+    eager = g.logits[:g.V].cpu().numpy().copy()
+    ctx.set_option("cuda_graphs", 1)
+    for _ in range(3):                                   # first sighting, capture, replay
+        ctx.compute(ops_small); ctx.sync()
+    assert np.array_equal(g.logits[:g.V].cpu().numpy(), eager)
+    load(64, 1000, 1280)
+    ctx.compute(g.build(64, 1000, 1280)); ctx.sync()      # prompt ubatch: activation scratch grows
+    load(1, 1999, 2048)
+    for _ in range(3):
+        ctx.compute(g.build(1, 1999, 2048)); ctx.sync()   # long context: more KV splits
+    # back to the first list (same inputs as at capture time)
+    emb, pos, mask = small
+    g.inp_embd[:g.E] = torch.from_numpy(emb.reshape(-1)).cuda()
+    g.pos[:1] = torch.from_numpy(pos).cuda()
+    g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        g.logits.zero_(); torch.cuda.synchronize()
+        ctx.compute(ops_small); ctx.sync()
+        assert np.array_equal(g.logits[:g.V].cpu().numpy(), eager)
+    ctx.set_option("pdl", 0); ctx.set_option("cuda_graphs", 0)

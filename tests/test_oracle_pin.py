@@ -77,3 +77,79 @@ def test_reference_own_quantize_tests_pass():
         pytest.skip("tool not built")
     p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-2000:]
+
+
+# ----------------------------------------------------------------------------- glue ops + flash attention (tests/golden/ops_golden.npz)
+OPS = np.load(os.path.join(os.path.dirname(__file__), "golden", "ops_golden.npz"))
+
+
+def _close(got, want, tol):
+    return np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-30)
+
+
+def test_rms_norm_matches_reference_golden():
+    assert np.array_equal(R.orc_rms_norm(OPS["rms_x"], 1e-5), OPS["rms_y"])
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("rope_norm", dict(mode=0, freq_base=10000.0)), ("rope_neox", dict(mode=2, freq_base=10000.0)),
+    ("rope_l3_ff", dict(mode=0, freq_base=500000.0, n_ctx_orig=8192, ff=True)),
+    ("rope_yarn", dict(mode=0, freq_base=10000.0, freq_scale=0.25, ext_factor=1.0, n_ctx_orig=2048))])
+def test_rope_matches_reference_golden(name, kw):
+    kw = dict(kw)
+    ff = OPS["rope_ff"] if kw.pop("ff", False) else None
+    mode = kw.pop("mode")
+    fb = kw.pop("freq_base")
+    got = R.orc_rope(OPS["rope_x"], OPS["rope_pos"], 128, mode, fb, freq_factors=ff, **kw)
+    # same libm on both sides, same multiplicative theta recurrence: only the rotation's fp contraction could differ
+    assert _close(got, OPS[name], 1e-6), np.abs(got - OPS[name]).max()
+
+
+def test_soft_max_matches_reference_golden():
+    got = R.orc_soft_max(OPS["sm_x"], OPS["sm_mask"], 0.125)
+    assert _close(got, OPS["sm_y"], 1e-6)
+    assert np.array_equal(got == 0, OPS["sm_y"] == 0)
+
+
+def test_silu_mul_matches_reference_golden():
+    assert _close(R.orc_silu_mul(OPS["silu_g"], OPS["silu_u"]), OPS["silu_y"], 1e-6)
+
+
+FA_GOLD = [("f16_d128", 128, 8, 2, 3, 256, R.F16), ("q8_0_d128", 128, 8, 2, 3, 256, R.Q8_0), ("q4_0_d128", 128, 4, 4, 2, 128, R.Q4_0),
+           ("f16_d64", 64, 4, 1, 1, 192, R.F16), ("f16_d128_long", 128, 2, 1, 1, 1024, R.F16)]
+
+
+@pytest.mark.parametrize("name,D,H,Hkv,n_q,n_kv,kvt", FA_GOLD)
+def test_flash_attn_matches_reference_golden(name, D, H, Hkv, n_q, n_kv, kvt):
+    """f16 KV: the oracle restates the reference's SIMD summation order and its FP16 accumulator, so it must agree with the
+    reference to the last bit; quantised KV: the f32 order of the per-block partial sums differs (<= 1e-6)."""
+    rs = R.row_size(kvt, D)
+    got = R.orc_flash_attn(OPS["fa_q_" + name], OPS["fa_k_" + name].reshape(Hkv, n_kv, rs), OPS["fa_v_" + name].reshape(Hkv, n_kv, rs),
+                           OPS["fa_m_" + name], D, n_kv, Hkv, kvt, kvt, 1.0 / np.sqrt(D))
+    want = OPS["fa_y_" + name]
+    if kvt == R.F16:
+        assert np.array_equal(got, want), (np.abs(got - want).max(), np.abs(want).max())
+    else:
+        assert _close(got, want, 2e-6), np.abs(got - want).max()
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not built")
+def test_flash_attn_oracle_vs_reference_live_random_shapes():
+    rng = np.random.default_rng(77)
+    for D, H, Hkv, n_q, n_kv, kvt in [(128, 4, 2, 2, 128, R.F16), (64, 2, 2, 3, 64, R.F16), (128, 4, 1, 1, 96, R.Q8_0)]:
+        q = rng.standard_normal((H, n_q, D)).astype(np.float32)
+        kf = rng.standard_normal((Hkv * n_kv, D)).astype(np.float32)
+        vf = rng.standard_normal((Hkv * n_kv, D)).astype(np.float32)
+        if kvt == R.F16:
+            kb, vb = kf.astype(np.float16).view(np.uint8).reshape(-1), vf.astype(np.float16).view(np.uint8).reshape(-1)
+        else:
+            kb, vb = R.ref().quantize_weights(kvt, kf), R.ref().quantize_weights(kvt, vf)
+        mask = np.zeros((64, n_kv), np.float16)
+        mask[:, n_kv - 7:] = -np.inf
+        rs = R.row_size(kvt, D)
+        want = R.ref_flash_attn(q, kb, vb, mask, D, n_kv, Hkv, kvt, kvt, 0.09)
+        got = R.orc_flash_attn(q, kb.reshape(Hkv, n_kv, rs), vb.reshape(Hkv, n_kv, rs), mask, D, n_kv, Hkv, kvt, kvt, 0.09)
+        if kvt == R.F16:
+            assert np.array_equal(got, want)
+        else:
+            assert _close(got, want, 2e-6)
