@@ -94,7 +94,8 @@ b200_ctx *b200_ctx_create(int device) {
     if (const char *e = getenv("GGML_B200_GRAPHS")) ctx->opt_cuda_graphs = atoi(e);
     if (const char *e = getenv("GGML_B200_FUSION")) ctx->opt_fusion = atoi(e);
     if (const char *e = getenv("GGML_B200_PDL")) ctx->opt_pdl = atoi(e);
-    if (const char *e = getenv("GGML_B200_FA_EXACT")) ctx->opt_fa_exact = atoi(e);
+    if (const char *e = getenv("GGML_B200_FA_EXACT")) ctx->opt_cpu_exact = atoi(e);
+    if (const char *e = getenv("GGML_B200_CPU_EXACT")) ctx->opt_cpu_exact = atoi(e);
     return ctx;
 }
 
@@ -123,7 +124,7 @@ int b200_synchronize(b200_ctx *ctx) {
 int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     std::string k(key);
     int *slot = k == "fusion" ? &ctx->opt_fusion : k == "pdl" ? &ctx->opt_pdl : k == "l2_prefetch" ? &ctx->opt_l2_prefetch :
-                k == "debug_skip" ? &ctx->opt_debug_skip : k == "fa_exact" ? &ctx->opt_fa_exact : nullptr;
+                k == "debug_skip" ? &ctx->opt_debug_skip : (k == "fa_exact" || k == "cpu_exact") ? &ctx->opt_cpu_exact : nullptr;
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
     else if (slot) {
         if (*slot != value) {                 // captured graphs bake these options in: drop them

@@ -129,7 +129,8 @@ struct b200_ctx {
     int           opt_fusion      = 2;      // 0 off, 1 two-op fusions, 2 + llama layer fusions for decode ubatches
     int           opt_pdl         = 0;
     int           opt_l2_prefetch = 0;      // L2 look-ahead of the next matmul's weights: measured neutral on B200 (profiles/r1_gemv_diag.md), off
-    int           opt_fa_exact    = 0;      // 1: f16-cache flash attention reproduces the CPU's fp16 V accumulator cell by cell (parity mode, serial over n_kv)
+    int           opt_cpu_exact   = 0;      // parity mode (exact.cu, fattn.cu): every float sum in the order of the reference's AVX2 CPU build, the fp16
+                                            // V accumulator of f16-cache attention, correctly rounded exp/sin/cos.  Slow; proves summation order is the only difference
     int           opt_debug_skip  = 0;      // timing experiments only: bit 0 flash_attn, 1 rope+store, 2 GEMV are not launched
     GraphCache *  graph_cache = nullptr;
     void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)
@@ -173,6 +174,9 @@ int launch_rope_store(b200_ctx *ctx, const RopeStoreDesc &d);
 int launch_quantize_act(b200_ctx *ctx, int q8k, const float *x, size_t x_col_stride_bytes, int64_t K, int64_t ncols,
                         uint8_t *scratch);
 // decode GEMV over pre-quantised activations (gemv.cu)
+// cpu-exact matmul over pre-quantised activations (exact.cu)
+int launch_mul_mat_exact(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int64_t ncols,
+                         float *dst, size_t dst_stride);
 int launch_gemv(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
                 int ncols, float *dst, size_t dst_col_stride_elems, bool w_const);
 
@@ -180,6 +184,131 @@ int launch_gemv(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int
 // device helpers
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// expf exactly as the reference CPU backend computes it inside silu / soft_max on its SIMD builds: ggml_v_expf
+// (ggml-cpu.c:2116-2153, the same polynomial on AVX2, AVX512, SSE2 and NEON), restated per lane with explicit FMAs.
+// The vector code's result for a lane does not depend on the other lanes, so this scalar form is bit-identical.  Using it
+// (instead of CUDA's expf, which differs by an ulp here and there) makes silu(gate)*up identical to the CPU's, so the
+// activation quantiser of the down projection sees the same values and rounds the same way.
+__device__ __forceinline__ float ggml_v_expf_lane(float x) {
+    const float r = 0x1.8p23f;
+    const float z = __fmaf_rn(x, 0x1.715476p+0f, r);
+    const float n = __fsub_rn(z, r);
+    const float b = __fmaf_rn(-n, 0x1.7f7d1cp-20f, __fmaf_rn(-n, 0x1.62e4p-1f, x));
+    const uint32_t e = __float_as_uint(z) << 23;
+    const float k = __uint_as_float(e + 0x3f800000u);
+    const float an = fabsf(n);
+    const float u = __fmul_rn(b, b);
+    const float j = __fmaf_rn(__fmaf_rn(__fmaf_rn(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, __fmaf_rn(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u,
+                              __fmul_rn(0x1.ffffecp-1f, b));
+    if (!(an > 126.0f)) return __fmaf_rn(j, k, k);
+    const uint32_t g = n <= 0.0f ? 0x82000000u : 0u;
+    const float s1 = __uint_as_float(g + 0x7f000000u), s2 = __uint_as_float(e - g);
+    if (an > 192.0f) return __fmul_rn(s1, s1);
+    return __fmul_rn(__fmaf_rn(s2, j, s2), s1);
+}
+// ---- libm of the reference host, restated (cpu-exact mode only) ---------------------------------------------------------
+// The CPU backend calls glibc's sinf / cosf (rope) and expf (flash-attention softmax weights).  glibc >= 2.28 implements them
+// with the ARM optimized-routines algorithms (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, e_expf.c, sincosf_data.c,
+// e_exp2f_data.c: glibc is not part of /root/reference; published algorithm, LGPL): double-precision polynomials on a
+// quadrant / 2^(k/32) table reduction, result rounded to float once.  They are accurate to ~0.5 ulp but NOT correctly
+// rounded, so neither CUDA's sinf/expf nor a correctly rounded (float)sin((double)x) agrees with them bit for bit (the
+// latter differs on ~1.3% of inputs); with a chaotic consumer (fp16 accumulator, q8 quantisers) every such ulp matters.
+// These restatements use explicit double FMAs where the x86-64 FMA build of glibc contracts them; they were checked
+// bit-identical to the libm of this image over 60M random arguments each, |x| up to 1.4e5 (tools/check_libm_restatement.c).
+__device__ __forceinline__ float glibc_sincos_poly(double x, double x2, int tbl, int n) {
+    // __sincosf_table[tbl]: tbl 1 negates the cosine coefficients
+    const double sg = tbl ? -1.0 : 1.0;
+    if ((n & 1) == 0) {
+        const double x3 = __dmul_rn(x, x2), s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+        const double x7 = __dmul_rn(x3, x2), s = __fma_rn(x3, -0x1.555545995a603p-3, x);
+        return (float)__fma_rn(x7, s1, s);
+    }
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __fma_rn(x2, sg * 0x1.99343027bf8c3p-16, sg * -0x1.6c087e89a359dp-10);
+    const double c1 = __fma_rn(x2, sg * -0x1.ffffffd0c621cp-2, sg * 0x1p0);
+    const double x6 = __dmul_rn(x4, x2), c = __fma_rn(x4, sg * 0x1.55553e1068f19p-5, c1);
+    return (float)__fma_rn(x6, c2, c);
+}
+__device__ __forceinline__ double glibc_reduce_large(uint32_t xi, int &np) {
+    // __inv_pio4: bits of 4/pi, one byte further per entry
+    const uint32_t inv_pio4[24] = {0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27,
+                                   0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62, 0xc0db6295,
+                                   0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+    const uint32_t *arr = &inv_pio4[(xi >> 26) & 15];
+    const int shift = (xi >> 23) & 7;
+    xi = (xi & 0xffffffu) | 0x800000u;
+    xi <<= shift;
+    uint64_t res0 = (uint64_t)(uint32_t)(xi * arr[0]);
+    const uint64_t res1 = (uint64_t)xi * arr[4], res2 = (uint64_t)xi * arr[8];
+    res0 = (res2 >> 32) | (res0 << 32);
+    res0 += res1;
+    const uint64_t n = (res0 + (1ULL << 61)) >> 62;
+    res0 -= n << 62;
+    np = (int)n;
+    return __dmul_rn((double)(int64_t)res0, 0x1.921FB54442D18p-62);
+}
+__device__ __forceinline__ void glibc_sincosf(float y, float &sn, float &cs) {
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+    double x = (double)y;
+    if (top < ((0x3f490fdbu >> 20) & 0x7ffu)) {                         // |y| < pi/4
+        const double x2 = __dmul_rn(x, x);
+        if (top < ((0x39800000u >> 20) & 0x7ffu)) { sn = y; cs = 1.0f; return; }      // |y| < 2^-12
+        sn = glibc_sincos_poly(x, x2, 0, 0);
+        cs = glibc_sincos_poly(x, x2, 0, 1);
+        return;
+    }
+    int n, add = 0;
+    if (top < ((0x42f00000u >> 20) & 0x7ffu)) {                          // |y| < 120: reduce_fast
+        const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+        n = ((int32_t)r + 0x800000) >> 24;
+        x = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+    } else {
+        const uint32_t xi = __float_as_uint(y);
+        add = (int)(xi >> 31);
+        x = glibc_reduce_large(xi, n);
+    }
+    const int q = (n + add) & 3;
+    const double sgn = (q == 1 || q == 2) ? -1.0 : 1.0;                   // sign[] = {1, -1, -1, 1}
+    const int tbl = ((n + add) & 2) ? 1 : 0;
+    const double xs = __dmul_rn(x, sgn), x2 = __dmul_rn(x, x);
+    sn = glibc_sincos_poly(xs, x2, tbl, n);
+    cs = glibc_sincos_poly(xs, x2, tbl, n ^ 1);
+}
+__device__ __forceinline__ float glibc_expf(float x) {
+    const uint32_t abstop = (__float_as_uint(x) >> 20) & 0x7ffu;
+    if (abstop >= (0x42b00000u >> 20)) {                                  // |x| >= 88 or nan
+        if (x == -INFINITY) return 0.0f;
+        if (abstop >= (0x7f800000u >> 20)) return x + x;
+        if (x > 0x1.62e42ep6f) return INFINITY;
+        if (x < -0x1.9fe368p6f) return 0.0f;
+    }
+    // __exp2f_data.tab[i] = bits(2^(i/32)) - (i << 47)
+    const uint64_t tab[32] = {
+        0x3ff0000000000000, 0x3fefd9b0d3158574, 0x3fefb5586cf9890f, 0x3fef9301d0125b51, 0x3fef72b83c7d517b, 0x3fef54873168b9aa,
+        0x3fef387a6e756238, 0x3fef1e9df51fdee1, 0x3fef06fe0a31b715, 0x3feef1a7373aa9cb, 0x3feedea64c123422, 0x3feece086061892d,
+        0x3feebfdad5362a27, 0x3feeb42b569d4f82, 0x3feeab07dd485429, 0x3feea47eb03a5585, 0x3feea09e667f3bcd, 0x3fee9f75e8ec5f74,
+        0x3feea11473eb0187, 0x3feea589994cce13, 0x3feeace5422aa0db, 0x3feeb737b0cdc5e5, 0x3feec49182a3f090, 0x3feed503b23e255d,
+        0x3feee89f995ad3ad, 0x3feeff76f2fb5e47, 0x3fef199bdd85529c, 0x3fef3720dcef9069, 0x3fef5818dcfba487, 0x3fef7c97337b9b5f,
+        0x3fefa4afa2a490da, 0x3fefd0765b6e4540};
+    const double xd = (double)x, IL = 0x1.71547652b82fep+5;               // InvLn2N = N / ln 2, N = 32
+    double kd = __fma_rn(IL, xd, 0x1.8p+52);
+    const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    kd = __dadd_rn(kd, -0x1.8p+52);
+    const double r = __fma_rn(IL, xd, -kd);
+    const uint64_t t = tab[ki & 31] + (ki << 47);
+    const double s = __longlong_as_double((long long)t);
+    const double z = __fma_rn(0x1.c6af84b912394p-5 / 32 / 32 / 32, r, 0x1.ebfce50fac4f3p-3 / 32 / 32);
+    const double r2 = __dmul_rn(r, r);
+    double yv = __fma_rn(0x1.62e42ff0c52d6p-1 / 32, r, 1.0);
+    yv = __fma_rn(z, r2, yv);
+    return (float)__dmul_rn(yv, s);
+}
+
+// ggml_v_silu (ggml-cpu.c:2156-2164): x / (1 + expf(0 - x)), IEEE division
+__device__ __forceinline__ float ggml_silu_lane(float x) {
+    return __fdiv_rn(x, __fadd_rn(1.0f, ggml_v_expf_lane(__fsub_rn(0.0f, x))));
+}
 
 __device__ __forceinline__ float warp_reduce_sum(float v) {
 #pragma unroll

@@ -588,20 +588,42 @@ __global__ void __launch_bounds__(128) b200_fattn_combine_kernel(const FaParams 
 // accumulator layout of ggml_vec_dot_f16 on the AVX2 build (4 x 8 FMA lanes over 32-element steps, then the
 // GGML_F32x8_REDUCE tree, ggml-cpu.c:671-689, 1565-1605), the running maximum / rescale logic of :12359-12395, and an
 // accumulator that is rounded to fp16 after the rescale and after every fused multiply-add.  Only libm-vs-CUDA expf ulps
-// remain.  It is a serial chain over n_kv, so it is the parity mode, not the fast mode (the default kernel above
+// remain (and those are removed too: exp_rn below).  It is a serial chain over n_kv, so it is the parity mode, not the fast mode (the default kernel above
 // accumulates in f32 and is closer to exact attention: tests/test_gpu_fattn.py bounds both against f64).
-template <int D>
+// softmax weights through glibc's expf restated (common.cuh): the CPU backend's weights bit for bit.  One ulp of difference in
+// a weight flips fp16 roundings of the accumulator (5e-4 each), and those flip q8 activation roundings in the next matmul.
+__device__ __forceinline__ float exp_rn(float x) { return glibc_expf(x); }
+
+template <int D, int KT>
 __global__ void __launch_bounds__(128) b200_fattn_f16acc_kernel(const FaParams p) {
     constexpr int PER = D / 32;
-    __shared__ float sq[4][D];
+    constexpr int NBQ = D / 32;
+    constexpr bool QUANT = KT != KV_F16;
+    constexpr int BB = KT == KV_Q8_0 ? 34 : 18;           // bytes per 32-element block of a quantised cache row
+    __shared__ float sq[4][D];                            // f16-rounded Q (f16 K) ...
+    __shared__ __align__(16) int8_t sqq[4][D];            // ... or Q quantised to q8_0 (quantised K): quants and fp16-rounded scales
+    __shared__ float sdq[4][NBQ];
     if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * 4 + warp;
     if (wid >= p.n_q * p.H) return;
     const int col = wid / p.H, head = wid % p.H, hk = head / p.gq;
     const float *qp = (const float *)(p.q + (uint64_t)col * p.q_nb1 + (uint64_t)head * p.q_nb2);
+    if (!QUANT) {
 #pragma unroll
-    for (int i = 0; i < PER; i++) sq[warp][lane + 32 * i] = __half2float(__float2half_rn(qp[lane + 32 * i]));
+        for (int i = 0; i < PER; i++) sq[warp][lane + 32 * i] = __half2float(__float2half_rn(qp[lane + 32 * i]));
+    } else {
+        // quantize_row_q8_0 (AVX2 path, ggml-cpu-quants.c:808-845): block b = elements [32b, 32b+32), one element per lane
+#pragma unroll
+        for (int b = 0; b < NBQ; b++) {
+            const float x = qp[32 * b + lane];
+            const float amax = warp_reduce_max(fabsf(x));
+            const float d = __fdiv_rn(amax, 127.0f);
+            const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+            sqq[warp][32 * b + lane] = (int8_t)__float2int_rn(__fmul_rn(x, id));
+            if (lane == 0) sdq[warp][b] = __half2float(__float2half_rn(d));
+        }
+    }
     __syncwarp();
     float slope = 1.0f;
     if (p.max_bias > 0.0f) slope = head < p.n_head_log2 ? powf(p.m0, (float)(head + 1)) : powf(p.m1, (float)(2 * (head - p.n_head_log2) + 1));
@@ -619,31 +641,57 @@ __global__ void __launch_bounds__(128) b200_fattn_f16acc_kernel(const FaParams p
         float mv = 0.0f;
         if (!skip && mp) { mv = __fmul_rn(slope, __half2float(mp[ic])); skip = mv == -INFINITY; }
         if (!skip) {
-            const uint4 *kr = (const uint4 *)(kbase + (uint64_t)ic * p.k_nb1);
-            float sum[4][8];
+            if (!QUANT) {
+                const uint4 *kr = (const uint4 *)(kbase + (uint64_t)ic * p.k_nb1);
+                float sum[4][8];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+                for (int j = 0; j < 4; j++)
 #pragma unroll
-                for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
+                    for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
 #pragma unroll
-            for (int i = 0; i < D / 32; i++)
+                for (int i = 0; i < D / 32; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint4 kv = kr[i * 4 + j];
-                    const __half2 *h = (const __half2 *)&kv;
-                    const float *qq = &sq[warp][i * 32 + j * 8];
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 kv = kr[i * 4 + j];
+                        const __half2 *h = (const __half2 *)&kv;
+                        const float *qq = &sq[warp][i * 32 + j * 8];
 #pragma unroll
-                    for (int l = 0; l < 4; l++) {
-                        const float2 kf = __half22float2(h[l]);
-                        sum[j][2 * l] = __fmaf_rn(kf.x, qq[2 * l], sum[j][2 * l]);
-                        sum[j][2 * l + 1] = __fmaf_rn(kf.y, qq[2 * l + 1], sum[j][2 * l + 1]);
+                        for (int l = 0; l < 4; l++) {
+                            const float2 kf = __half22float2(h[l]);
+                            sum[j][2 * l] = __fmaf_rn(kf.x, qq[2 * l], sum[j][2 * l]);
+                            sum[j][2 * l + 1] = __fmaf_rn(kf.y, qq[2 * l + 1], sum[j][2 * l + 1]);
+                        }
+                    }
+                float x0[8];
+#pragma unroll
+                for (int l = 0; l < 8; l++) x0[l] = __fadd_rn(__fadd_rn(sum[0][l], sum[2][l]), __fadd_rn(sum[1][l], sum[3][l]));
+                const float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]), t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
+                s = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+            } else {
+                // ggml_vec_dot_{q8_0,q4_0}_q8_0, AVX2 order (see exact.cu): 8 lane partials per block, one FMA per block, hsum_float_8
+                const uint8_t *kr = (const uint8_t *)(kbase + (uint64_t)ic * p.k_nb1);
+                float a8[8];
+#pragma unroll
+                for (int l = 0; l < 8; l++) a8[l] = 0.0f;
+#pragma unroll
+                for (int b = 0; b < NBQ; b++) {
+                    const uint8_t *blk = kr + b * BB;
+                    const float d = __fmul_rn(__half2float(__ushort_as_half((unsigned short)(blk[0] | (blk[1] << 8)))), sdq[warp][b]);
+#pragma unroll
+                    for (int l = 0; l < 8; l++) {
+                        const uint32_t a = *(const uint32_t *)&sqq[warp][32 * b + 4 * l];
+                        uint32_t w;
+                        if (KT == KV_Q8_0) w = (uint32_t)blk[2 + 4 * l] | ((uint32_t)blk[3 + 4 * l] << 8) | ((uint32_t)blk[4 + 4 * l] << 16) | ((uint32_t)blk[5 + 4 * l] << 24);
+                        else {
+                            const int o = 2 + 4 * (l & 3);
+                            const uint32_t raw = (uint32_t)blk[o] | ((uint32_t)blk[o + 1] << 8) | ((uint32_t)blk[o + 2] << 16) | ((uint32_t)blk[o + 3] << 24);
+                            w = __vsub4(l < 4 ? (raw & 0x0f0f0f0fu) : ((raw >> 4) & 0x0f0f0f0fu), 0x08080808u);
+                        }
+                        a8[l] = __fmaf_rn(d, (float)__dp4a((int)w, (int)a, 0), a8[l]);
                     }
                 }
-            float x0[8];
-#pragma unroll
-            for (int l = 0; l < 8; l++) x0[l] = __fadd_rn(__fadd_rn(sum[0][l], sum[2][l]), __fadd_rn(sum[1][l], sum[3][l]));
-            const float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]), t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
-            s = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+                s = __fadd_rn(__fadd_rn(__fadd_rn(a8[0], a8[4]), __fadd_rn(a8[2], a8[6])), __fadd_rn(__fadd_rn(a8[1], a8[5]), __fadd_rn(a8[3], a8[7])));
+            }
             s = __fmul_rn(s, p.scale);
             if (p.softcap != 0.0f) s = __fmul_rn(p.softcap, tanhf(s));
             s = __fadd_rn(s, mv);
@@ -652,19 +700,34 @@ __global__ void __launch_bounds__(128) b200_fattn_f16acc_kernel(const FaParams p
         for (int t = 0; t < 32; t++) {
             if (!((live >> t) & 1u)) continue;
             const float sc = __shfl_sync(0xffffffffu, s, t);
-            const __half *vr = (const __half *)(vbase + (uint64_t)(c0 + t) * p.v_nb1) + lane * PER;
             float vv[PER];
-            if (PER == 4) { const uint2 raw = *(const uint2 *)vr; const float2 a = __half22float2(*(const __half2 *)&raw.x), b = __half22float2(*(const __half2 *)&raw.y); vv[0] = a.x; vv[1] = a.y; vv[PER - 2] = b.x; vv[PER - 1] = b.y; }
-            else { const float2 a = __half22float2(*(const __half2 *)vr); vv[0] = a.x; vv[1] = a.y; }
+            if (!QUANT) {
+                const __half *vr = (const __half *)(vbase + (uint64_t)(c0 + t) * p.v_nb1) + lane * PER;
+                if (PER == 4) { const uint2 raw = *(const uint2 *)vr; const float2 a = __half22float2(*(const __half2 *)&raw.x), b = __half22float2(*(const __half2 *)&raw.y); vv[0] = a.x; vv[1] = a.y; vv[PER - 2] = b.x; vv[PER - 1] = b.y; }
+                else { const float2 a = __half22float2(*(const __half2 *)vr); vv[0] = a.x; vv[1] = a.y; }
+            } else {
+                // dequantize_row_q8_0 / q4_0 (ggml-quants.c:349, 255): (float)q * d; lane owns elements [PER*lane, PER*lane + PER)
+                const uint8_t *vr = (const uint8_t *)(vbase + (uint64_t)(c0 + t) * p.v_nb1);
+#pragma unroll
+                for (int i = 0; i < PER; i++) {
+                    const int e = lane * PER + i, b = e >> 5, j = e & 31;
+                    const uint8_t *blk = vr + b * BB;
+                    const float d = __half2float(__ushort_as_half((unsigned short)(blk[0] | (blk[1] << 8))));
+                    int q;
+                    if (KT == KV_Q8_0) q = (int)(int8_t)blk[2 + j];
+                    else q = (j < 16 ? (blk[2 + j] & 0x0f) : (blk[2 + j - 16] >> 4)) - 8;
+                    vv[i] = __fmul_rn((float)q, d);
+                }
+            }
             float ms = 1.0f, vs = 1.0f;
             if (sc > M) {
-                ms = expf(M - sc);
+                ms = exp_rn(M - sc);
                 M = sc;
 #pragma unroll
-                for (int i = 0; i < PER; i++) acc[i] = __half2float(__float2half_rn(__fmul_rn(acc[i], ms)));
-            } else vs = expf(sc - M);
+                for (int i = 0; i < PER; i++) acc[i] = QUANT ? __fmul_rn(acc[i], ms) : __half2float(__float2half_rn(__fmul_rn(acc[i], ms)));
+            } else vs = exp_rn(sc - M);
 #pragma unroll
-            for (int i = 0; i < PER; i++) acc[i] = __half2float(__float2half_rn(__fmaf_rn(vv[i], vs, acc[i])));
+            for (int i = 0; i < PER; i++) acc[i] = QUANT ? __fmaf_rn(vv[i], vs, acc[i]) : __half2float(__float2half_rn(__fmaf_rn(vv[i], vs, acc[i])));
             S = __fadd_rn(__fmul_rn(S, ms), vs);
         }
     }
@@ -778,7 +841,7 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;
     if (n_tiles == 0 || p.n_q == 0) return B200_OK;
     // parity mode: reproduce the CPU's fp16 V accumulator (see b200_fattn_f16acc_kernel)
-    if (ctx->opt_fa_exact && kv_kind(k.type) == KV_F16 && kv_kind(v.type) == KV_F16) {
+    if (ctx->opt_cpu_exact && kv_kind(k.type) == kv_kind(v.type)) {
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -788,8 +851,11 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
         cfg.stream = ctx->stream;
         cfg.attrs = attr;
         cfg.numAttrs = p.use_pdl ? 1 : 0;
-        if (D == 128) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<128>, p));
-        else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<64>, p));
+        const int kt_ = kv_kind(k.type);
+        if (D == 128 && kt_ == KV_F16) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<128, KV_F16>, p));
+        else if (D == 128 && kt_ == KV_Q8_0) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<128, KV_Q8_0>, p));
+        else if (D == 128 && kt_ == KV_Q4_0) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<128, KV_Q4_0>, p));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<64, KV_F16>, p));
         ctx->launches++;
         return B200_OK;
     }

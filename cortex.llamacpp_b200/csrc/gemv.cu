@@ -124,7 +124,7 @@ __device__ __forceinline__ void quantize_col_to_smem(const GemvParams &p, int co
                         for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fmul_rn(v[j], norm_scale), w[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fdiv_rn(v[j], 1.0f + expf(-v[j])), w[j]);
+                        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(ggml_silu_lane(v[j]), w[j]);
                     }
                 }
             } else {

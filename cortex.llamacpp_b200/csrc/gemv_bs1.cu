@@ -117,7 +117,7 @@ __device__ __forceinline__ void bs1_apply_mode(const Bs1Params &p, float (&v)[8]
         for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fmul_rn(v[j], norm_scale), w[j]);
     } else if (p.act_mode == ACT_F32_SWIGLU) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fdiv_rn(v[j], 1.0f + expf(-v[j])), w[j]);
+        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(ggml_silu_lane(v[j]), w[j]);
     }
 }
 // sum over the consumer warps of per-warp partial sums of squares -> 1/rms (rms_norm like glue.cu / the CPU oracle: sum in double)

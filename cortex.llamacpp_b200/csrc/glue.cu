@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) b200_bin_fast_kernel(const float4 *a, con
 enum { UN_SILU, UN_GELU, UN_RELU, UN_TANH, UN_SIGMOID, UN_SCALE, UN_SWIGLU };
 template <int OP> __device__ __forceinline__ float unary(float x, float p) {
     switch (OP) {
-        case UN_SILU:    return __fdiv_rn(x, 1.0f + expf(-x));
+        case UN_SILU:    return ggml_silu_lane(x);
         case UN_GELU:    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
         case UN_RELU:    return fmaxf(x, 0.0f);
         case UN_TANH:    return tanhf(x);
@@ -118,7 +118,13 @@ struct RopeParams {
     int n_dims, mode, n_ctx_orig;
     float freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow;
     float theta_scale, corr0, corr1;
+    int exact;        // cpu-exact mode: glibc's sinf/cosf restated (common.cuh), which the CPU backend calls; CUDA's sinf/cosf are
+                      // 1-2 ulp off here and there and every ulp can flip a KV-store / activation rounding downstream
 };
+__device__ __forceinline__ void rope_sincos(float th, int exact, float &s, float &c) {
+    if (exact) glibc_sincosf(th, s, c);
+    else { s = sinf(th); c = cosf(th); }
+}
 template <typename T>
 __global__ void __launch_bounds__(128) b200_rope_kernel(b200_tensor x, b200_tensor pos, b200_tensor ff, b200_tensor y, RopeParams rp, int has_ff) {
     // grid: (ne2 tokens, ne1 heads, ne3); threads over pairs
@@ -142,7 +148,9 @@ __global__ void __launch_bounds__(128) b200_rope_kernel(b200_tensor x, b200_tens
                 th = __fadd_rn(__fmul_rn(ti, 1.0f - ramp), __fmul_rn(te, ramp));
                 ms = __fmul_rn(ms, 1.0f + 0.1f * logf(__fdiv_rn(1.0f, rp.freq_scale)));
             }
-            const float c = __fmul_rn(cosf(th), ms), s = __fmul_rn(sinf(th), ms);
+            float sn, cs;
+            rope_sincos(th, rp.exact, sn, cs);
+            const float c = __fmul_rn(cs, ms), s = __fmul_rn(sn, ms);
             const int64_t ia = neox ? ip : i0, ib = neox ? ip + rp.n_dims / 2 : i0 + 1;
             const float x0 = (float)((const T *)xp)[ia], x1 = (float)((const T *)xp)[ib];
             ((T *)yp)[ia] = (T)__fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
@@ -474,7 +482,9 @@ __global__ void __launch_bounds__(64) b200_rope_store_kernel(const RopeStoreDesc
                     th = __fadd_rn(__fmul_rn(ti, 1.0f - ramp), __fmul_rn(te, ramp));
                     ms = __fmul_rn(ms, 1.0f + 0.1f * logf(__fdiv_rn(1.0f, rp.freq_scale)));
                 }
-                const float c = __fmul_rn(cosf(th), ms), s = __fmul_rn(sinf(th), ms);
+                float sn, cs;
+                rope_sincos(th, rp.exact, sn, cs);
+                const float c = __fmul_rn(cs, ms), s = __fmul_rn(sn, ms);
                 const int ia = neox ? ip : i0, ib = neox ? ip + rp.n_dims / 2 : i0 + 1;
                 const float x0 = src[ia], x1 = src[ib];
                 qo[ia] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
@@ -535,6 +545,7 @@ RopeParams make_rope_params(const int32_t *params) {
     float hi = ceilf(yarn_corr_dim(rp.n_dims, rp.n_ctx_orig, rp.beta_slow, rp.freq_base));
     rp.corr0 = lo < 0 ? 0 : lo;
     rp.corr1 = hi > rp.n_dims - 1 ? (float)(rp.n_dims - 1) : hi;
+    rp.exact = 0;
     return rp;
 }
 
@@ -543,7 +554,8 @@ RopeParams make_rope_params(const int32_t *params) {
 int launch_rope_store(b200_ctx *ctx, const RopeStoreDesc &din) {
     RopeStoreDesc d = din;
     d.use_pdl = ctx->opt_pdl;
-    const RopeParams rp = make_rope_params(d.rope_params);
+    RopeParams rp = make_rope_params(d.rope_params);
+    rp.exact = ctx->opt_cpu_exact;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(d.H + 2 * d.Hkv), (unsigned)d.T);
     cfg.blockDim = dim3(64);
@@ -637,6 +649,7 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
             float hi = ceilf(yarn_corr_dim(rp.n_dims, rp.n_ctx_orig, rp.beta_slow, rp.freq_base));
             rp.corr0 = lo < 0 ? 0 : lo;
             rp.corr1 = hi > rp.n_dims - 1 ? (float)(rp.n_dims - 1) : hi;
+            rp.exact = ctx->opt_cpu_exact;
             const int has_ff = op->n_src > 2 && op->src[2].data != nullptr;
             if (a.ne[2] == 0 || a.ne[1] == 0) return B200_OK;
             const dim3 grid((unsigned)a.ne[2], (unsigned)a.ne[1], (unsigned)a.ne[3]);

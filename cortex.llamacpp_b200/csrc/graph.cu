@@ -356,7 +356,7 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
     out.reserve(n);
     // scratch for the intermediates of the layer fusions (q,k,v and gate,up): sized from the largest matmuls in the list
     FuseScratch fs = {};
-    bool layer_fusion = ctx->opt_fusion >= 2;
+    bool layer_fusion = ctx->opt_fusion >= 2 && !ctx->opt_cpu_exact;     // parity mode: matmuls go through exact.cu one by one
     if (layer_fusion) {
         int64_t maxN = 0;
         for (int i = 0; i < n; i++) if (ops[i].op == B200_OP_MUL_MAT && is_decode_mm(ops[i]) && ops[i].src[0].ne[1] < (1 << 16)) maxN = std::max(maxN, ops[i].src[0].ne[1]);

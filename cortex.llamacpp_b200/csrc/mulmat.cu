@@ -121,6 +121,23 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     // up to this many columns the streaming GEMV (4 columns per launch, weights re-streamed per chunk) beats the tensor-core
     // GEMM, whose per-super-block drain costs the same for 8 tokens as for 128 (measured: profiles/r1_batched.md)
     static const int64_t gemv_max_m = getenv("GGML_B200_GEMV_MAX_M") ? atoi(getenv("GGML_B200_GEMV_MAX_M")) : 8;
+    if (ctx->opt_cpu_exact) {
+        // parity mode: same quantised activations, float sums in the reference's SIMD order (exact.cu)
+        uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)(M * nbatch));
+        if (!act) return B200_ERR_ALLOC;
+        for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+                const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+                const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+                const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+                float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+                uint8_t *ab = act + (size_t)((i3 * x.ne[2] + i2) * M) * L.col_bytes;
+                int rc = launch_quantize_act(ctx, q8k, xp, x.nb[1], K, M, ab);
+                if (!rc) rc = launch_mul_mat_exact(ctx, w.type, wp, rb, N, K, ab, M, dp, d.nb[1] / 4);
+                if (rc) return rc;
+            }
+        return B200_OK;
+    }
     if (M <= gemv_max_m) {
         // decode path: one fused launch per (batch) matmul -- activation quantisation happens in the GEMV prologue
         for (int64_t i3 = 0; i3 < x.ne[3]; i3++)

@@ -308,36 +308,81 @@ void orc_block_sums(int type, const void *vw, const void *vact, int64_t k, int32
     }
 }
 
+/* ---------------------------------------------------------------- the reference's SIMD summation order
+ * The AVX2 branches of ggml_vec_dot_{q4_0,q8_0}_q8_0 (ggml-cpu-quants.c:2273-2296, 3935-3952) and
+ * ggml_vec_dot_{q4_K,q5_K,q6_K}_q8_K (:6776-6837, 7413-7490, 8405-8481) all have the same shape: per weight block an
+ * 8-lane int32 vector whose lane l collects the products of bytes 4l..4l+3 of every 32-element group of the block
+ * (maddubs pairs, then madd with the group's sub-scale), converted to float and accumulated with one FMA per block into an
+ * 8-lane f32 accumulator (acc = fma(d_block, (float)lanes, acc)), reduced at the end by hsum_float_8 (:49-55):
+ * ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)).  The mins of q4_K go through a 4-lane FMA accumulator (:6796-6799, 6833-6836), the
+ * mins of q5_K through a scalar float (:7439-7443).  Restating exactly that order makes the float result bit-identical to
+ * the reference build in oracle/_ref (which is what the tests assert), not just equal up to summation order. */
+static void lane_sums(int type, const uint8_t *w, const uint8_t *a, int32_t L[8], int32_t prod[4]) {
+    for (int l = 0; l < 8; l++) L[l] = 0;
+    for (int k = 0; k < 4; k++) prod[k] = 0;
+    switch (type) {
+    case ORC_TYPE_Q4_0: {
+        const int8_t *q8 = (const int8_t *)(a + 2);
+        for (int i = 0; i < 32; i++) {
+            const int q = i < 16 ? (w[2 + i] & 0x0F) - 8 : (w[2 + i - 16] >> 4) - 8;
+            L[i >> 2] += q * q8[i];
+        }
+        break; }
+    case ORC_TYPE_Q8_0: {
+        const int8_t *q8 = (const int8_t *)(a + 2), *qw = (const int8_t *)(w + 2);
+        for (int i = 0; i < 32; i++) L[i >> 2] += qw[i] * q8[i];
+        break; }
+    case ORC_TYPE_Q4_K: case ORC_TYPE_Q5_K: {
+        const int8_t *q8 = (const int8_t *)(a + 4);
+        int sc[8], mn[8]; unpack_scales_k4(w + 4, sc, mn);
+        for (int j = 0; j < 8; j++)
+            for (int i = 0; i < 32; i++) {
+                const int e = 32 * j + i;
+                const int q = type == ORC_TYPE_Q4_K ? q4k_elem(w + 16, e) : q5k_elem(w + 16, w + 48, e);
+                L[i >> 2] += sc[j] * (q * q8[e]);
+            }
+        for (int k = 0; k < 4; k++) {       /* q8s = hadd_epi16(bsums lo, hi) = per-32 sums; prod = madd_epi16(mins, q8s) */
+            const int s0 = (int16_t)(rds16(a + 260 + 2 * (4 * k)) + rds16(a + 260 + 2 * (4 * k + 1)));
+            const int s1 = (int16_t)(rds16(a + 260 + 2 * (4 * k + 2)) + rds16(a + 260 + 2 * (4 * k + 3)));
+            prod[k] = mn[2 * k] * s0 + mn[2 * k + 1] * s1;
+        }
+        break; }
+    case ORC_TYPE_Q6_K: {
+        const int8_t *q8 = (const int8_t *)(a + 4);
+        const int8_t *scales = (const int8_t *)(w + 192);
+        for (int e = 0; e < QKK; e++) {
+            const int h = e >> 7, t = (e & 127) >> 5, i = e & 31;
+            L[i >> 2] += scales[8 * h + 2 * t + i / 16] * (q6k_elem(w, w + 128, e) * q8[e]);
+        }
+        break; }
+    default: break;
+    }
+}
+
 float orc_vec_dot(int type, const void *vw, const void *vact, int64_t k) {
     const int be = orc_block_elems(type);
     const int64_t nb = k / be;
-    int32_t *P = (int32_t *)malloc(sizeof(int32_t) * (size_t)nb * 2), *M = P + nb;
-    orc_block_sums(type, vw, vact, k, P, M);
     const uint8_t *w = (const uint8_t *)vw, *a = (const uint8_t *)vact;
-    float sum = 0.0f;
-    switch (type) {
-    case ORC_TYPE_Q4_0: case ORC_TYPE_Q8_0: {
-        const size_t wb = type == ORC_TYPE_Q4_0 ? 18 : 34;
-        for (int64_t b = 0; b < nb; b++)
-            sum += (float)P[b] * (orc_f16_to_f32(rd16(w + b * wb)) * orc_f16_to_f32(rd16(a + b * 34)));
-        break; }
-    case ORC_TYPE_Q4_K: case ORC_TYPE_Q5_K: {
-        const size_t wb = type == ORC_TYPE_Q4_K ? 144 : 176;
-        for (int64_t b = 0; b < nb; b++) {
-            const float da = rdf32(a + b * 292);
-            const float d = orc_f16_to_f32(rd16(w + b * wb)) * da, dmin = orc_f16_to_f32(rd16(w + b * wb + 2)) * da;
-            sum += d * (float)P[b];
-            sum -= dmin * (float)M[b];
+    const size_t wb = type == ORC_TYPE_Q4_0 ? 18 : type == ORC_TYPE_Q8_0 ? 34 : type == ORC_TYPE_Q4_K ? 144 : type == ORC_TYPE_Q5_K ? 176 : 210;
+    const size_t ab = be == 32 ? 34 : 292;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc_m[4] = {0, 0, 0, 0}, summs = 0.0f;
+    for (int64_t b = 0; b < nb; b++, w += wb, a += ab) {
+        int32_t L[8], prod[4];
+        lane_sums(type, w, a, L, prod);
+        float d;
+        if (be == 32) d = orc_f16_to_f32(rd16(w)) * orc_f16_to_f32(rd16(a));
+        else d = rdf32(a) * orc_f16_to_f32(rd16(w + (type == ORC_TYPE_Q6_K ? 208 : 0)));
+        for (int l = 0; l < 8; l++) acc[l] = fmaf(d, (float)L[l], acc[l]);
+        if (type == ORC_TYPE_Q4_K || type == ORC_TYPE_Q5_K) {
+            const float dmin = -rdf32(a) * orc_f16_to_f32(rd16(w + 2));
+            if (type == ORC_TYPE_Q4_K) for (int kk = 0; kk < 4; kk++) acc_m[kk] = fmaf(dmin, (float)prod[kk], acc_m[kk]);
+            else summs += dmin * (float)((prod[0] + prod[1]) + (prod[2] + prod[3]));      /* hadd_epi32 twice, then scalar float (:7442-7443) */
         }
-        break; }
-    case ORC_TYPE_Q6_K:
-        for (int64_t b = 0; b < nb; b++)
-            sum += (orc_f16_to_f32(rd16(w + b * 210 + 208)) * rdf32(a + b * 292)) * (float)P[b];
-        break;
-    default: break;
     }
-    free(P);
-    return sum;
+    const float h8 = ((acc[0] + acc[4]) + (acc[2] + acc[6])) + ((acc[1] + acc[5]) + (acc[3] + acc[7]));
+    if (type == ORC_TYPE_Q4_K) return h8 + ((acc_m[0] + acc_m[2]) + (acc_m[1] + acc_m[3]));
+    if (type == ORC_TYPE_Q5_K) return h8 + summs;
+    return h8;
 }
 
 /* vec_dot_type table: ggml-cpu.c:266-341 */
@@ -471,9 +516,30 @@ void orc_soft_max(const float *x, const uint16_t *mask, float *y, int64_t ncols,
     }
 }
 
-/* ggml_silu_f32 = x/(1+expf(-x)); then elementwise product with `up` */
+/* silu as the SIMD builds of the CPU backend compute it: ggml_vec_silu_f32 (ggml-cpu.c:2221-2243) maps every full vector
+ * through ggml_v_silu = x / (1 + ggml_v_expf(0 - x)) (:2116-2164), a polynomial expf (NOT libm); only the n % 8 leftovers go
+ * through ggml_silu_f32 = x/(1+expf(-x)).  ggml_v_expf restated per lane (lanes are independent): */
+static float v_expf_lane(float x) {
+    union { float f; uint32_t u; } cz, ck, cs1, cs2;
+    const float r = 0x1.8p23f;
+    const float z = fmaf(x, 0x1.715476p+0f, r);
+    const float n = z - r;
+    const float b = fmaf(-n, 0x1.7f7d1cp-20f, fmaf(-n, 0x1.62e4p-1f, x));
+    cz.f = z;
+    const uint32_t e = cz.u << 23;
+    ck.u = e + 0x3f800000u;
+    const float k = ck.f, an = fabsf(n), u = b * b;
+    const float j = fmaf(fmaf(fmaf(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, fmaf(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u, 0x1.ffffecp-1f * b);
+    if (!(an > 126.0f)) return fmaf(j, k, k);
+    const uint32_t g = n <= 0.0f ? 0x82000000u : 0u;
+    cs1.u = g + 0x7f000000u; cs2.u = e - g;
+    if (an > 192.0f) return cs1.f * cs1.f;
+    return fmaf(cs2.f, j, cs2.f) * cs1.f;
+}
 void orc_silu_mul(const float *gate, const float *up, float *y, int64_t n) {
-    for (int64_t i = 0; i < n; i++) y[i] = (gate[i] / (1.0f + expf(-gate[i]))) * up[i];
+    const int64_t nv = n & ~(int64_t)7;
+    for (int64_t i = 0; i < nv; i++) y[i] = (gate[i] / (1.0f + v_expf_lane(0.0f - gate[i]))) * up[i];
+    for (int64_t i = nv; i < n; i++) y[i] = (gate[i] / (1.0f + expf(-gate[i]))) * up[i];
 }
 
 /* ---------------------------------------------------------------- flash attention */
@@ -543,7 +609,8 @@ void orc_flash_attn_ext(const float *q, const void *k, const void *v, const uint
                     }
                 } else {
                     orc_dequantize_row(type_v, vr, vrow, D);
-                    for (int64_t d = 0; d < D; d++) { if (ms != 1.0f) acc[d] *= ms; acc[d] += vrow[d] * vs; }
+                    /* ggml_vec_scale_f32 (mul) then ggml_vec_mad_f32 = GGML_F32_VEC_FMA (_mm256_fmadd_ps) */
+                    for (int64_t d = 0; d < D; d++) { if (ms != 1.0f) acc[d] *= ms; acc[d] = fmaf(vrow[d], vs, acc[d]); }
                 }
                 S = S * ms + vs;
             }

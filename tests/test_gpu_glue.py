@@ -58,6 +58,26 @@ def test_rope(b200, ctx, mode, ff):
     assert np.abs(got - want).max() <= 2e-6 * np.abs(x).max()
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_rope_cpu_exact_mode_bit_identical(b200, ctx, mode):
+    """option cpu_exact: sin/cos through the restated glibc sinf/cosf (common.cuh) -> the oracle's rope (same libm, itself
+    bit-identical to the reference golden) bit for bit, including positions that take glibc's large-argument reduction"""
+    rng = np.random.default_rng(12)
+    n_tok, n_head, D = 9, 4, 128
+    x = rng.standard_normal((n_tok, n_head, D)).astype(np.float32)
+    pos = np.array([0, 1, 5, 100, 119, 121, 4095, 8191, 131071], np.int32)
+    ctx.set_option("cpu_exact", 1)
+    try:
+        for base, ff in ((10000.0, None), (500000.0, rng.uniform(1.0, 8.0, D // 2).astype(np.float32))):
+            params = [0, D, mode, 0, 8192, base, 1.0, 0.0, 1.0, 32.0, 1.0]
+            srcs = [(x, b200.F32, [D, n_head, n_tok]), (pos, b200.I32, [n_tok]), (ff, b200.F32, [D // 2]) if ff is not None else None]
+            got = run(b200, ctx, b200.OP_ROPE, [D, n_head, n_tok], b200.F32, srcs, params).view(np.float32).reshape(n_tok, n_head, D)
+            want = R.orc_rope(x, pos, D, mode, base, n_ctx_orig=8192, freq_factors=ff)
+            assert np.array_equal(got, want), (base, np.abs(got - want).max())
+    finally:
+        ctx.set_option("cpu_exact", 0)
+
+
 def test_rope_yarn(b200, ctx):
     rng = np.random.default_rng(3)
     n_tok, n_head, D = 4, 4, 64
@@ -109,8 +129,11 @@ def test_add_mul_div_broadcast_and_swiglu(b200, ctx):
     assert np.array_equal(got, a / c)
     g, u = rng.standard_normal((2, 14336)).astype(np.float32), rng.standard_normal((2, 14336)).astype(np.float32)
     got = run(b200, ctx, b200.OP_SWIGLU_FUSED, [14336, 2], b200.F32, [(g, b200.F32, [14336, 2]), (u, b200.F32, [14336, 2])]).view(np.float32).reshape(2, -1)
+    g[0, :16] = [-200, -130, -100, -90, -88, -20, 0, 1e-8, 20, 88, 90, 100, 130, 200, -0.0, 7.5]
+    got = run(b200, ctx, b200.OP_SWIGLU_FUSED, [14336, 2], b200.F32, [(g, b200.F32, [14336, 2]), (u, b200.F32, [14336, 2])]).view(np.float32).reshape(2, -1)
     want = R.orc_silu_mul(g, u)
-    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    # bit-exact: kernels and oracle both restate the reference's polynomial ggml_v_expf (pinned to the reference golden)
+    assert np.array_equal(got, want), np.abs(got - want).max()
     got = run(b200, ctx, b200.OP_SCALE, [256, 5, 3], b200.F32, [(a, b200.F32, [256, 5, 3])], [0.125]).view(np.float32).reshape(a.shape)
     assert np.array_equal(got, a * np.float32(0.125))
 

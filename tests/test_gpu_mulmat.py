@@ -177,3 +177,35 @@ def test_mul_mat_id_device_side_routing(b200, ctx, t, b_ne1):
     got = out.cpu().numpy().view(np.float32).reshape(n_tok, n_used, N)
     want = R.orc_mul_mat_id(t, As, b, ids, N, K, n_expert)
     assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+# ----------------------------------------------------------------------------- cpu-exact mode (exact.cu)
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+def test_cpu_exact_mode_bit_identical_to_reference_golden(b200, ctx, t):
+    """option cpu_exact: float sums in the SIMD order of the reference build -> the committed reference outputs, bit for bit"""
+    ctx.set_option("cpu_exact", 1)
+    try:
+        for K in (256, 1280):
+            name = "%s_%d" % (R.TYPE_NAMES[t], K)
+            got = gpu_mul_mat(b200, ctx, t, G["mm_W_" + name], G["mm_x_%d" % K], 12, K)
+            assert np.array_equal(got, G["mm_out_" + name]), (name, np.abs(got - G["mm_out_" + name]).max())
+    finally:
+        ctx.set_option("cpu_exact", 0)
+
+
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+@pytest.mark.parametrize("N,K,M", [(64, 4096, 1), (24, 14336, 3), (40, 2048, 33)])
+def test_cpu_exact_mode_bit_identical_to_oracle(b200, ctx, t, N, K, M):
+    """real decode / prefill shapes against the oracle's vec_dot (itself bit-identical to the reference, tests/test_oracle_pin.py)"""
+    rng = np.random.default_rng(N + K + M + t)
+    W = rand_quant_rows(t, N, K, rng)
+    x = (rng.standard_normal((M, K)) * rng.uniform(0.2, 5, (M, 1))).astype(np.float32)
+    want = R.orc_mul_mat(t, W, x, N, K)
+    fast = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    ctx.set_option("cpu_exact", 1)
+    try:
+        got = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    finally:
+        ctx.set_option("cpu_exact", 0)
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    assert np.abs(fast - want).max() <= 3e-6 * np.abs(want).max()          # the fast path: same integers, its own float order

@@ -83,8 +83,8 @@ def need_tools():
 
 # (model, ftype, layers, kv, prompt seed, plugin env) -- seeds from tools/scan_margins.py (largest smallest-margin)
 CASES = [
-    pytest.param("tinyllama", "q4_0", 0, "f16", 9, {"GGML_B200_FA_EXACT": "1"}, id="tinyllama-1.1b-q4_0-f16kv-ctx512"),
-    pytest.param("llama3-8b", "q4_k_m", 2, "q8_0", 10, {}, id="llama3-8b-shaped-2L-q4_k_m-q8_0kv"),
+    pytest.param("tinyllama", "q4_0", 0, "f16", 9, {"GGML_B200_CPU_EXACT": "1"}, id="tinyllama-1.1b-q4_0-f16kv-ctx512"),
+    pytest.param("llama3-8b", "q4_k_m", 2, "q8_0", 10, {"GGML_B200_CPU_EXACT": "1"}, id="llama3-8b-shaped-2L-q4_k_m-q8_0kv"),
 ]
 N_PROMPT, N_GEN = 32, 128
 
