@@ -10,9 +10,10 @@ on the same synthetic GGUF (tools/make_gguf.py, seeded) and the same token ids. 
       (prompt seeds chosen with tools/scan_margins.py so that the smallest margin of the stream is well above the error)
 Configs: BASELINE.json #1 TinyLlama-1.1B Q4_0 real shape, ctx 512, f16 KV; an 8B-shaped (E=4096, FF=14336, V=128256)
 2-layer Q4_K_M model with q8_0 KV (the shapes and the K_M type mixture of config #3).
-f16 KV: the reference accumulates V in an FP16 accumulator (ggml-cpu.c:12376-12390); the product reproduces that in its
-parity mode (GGML_B200_FA_EXACT=1, fattn.cu b200_fattn_f16acc_kernel) and is ALSO checked in its default f32-accumulating
-mode against the documented, looser bound that the CPU's own fp16 rounding noise allows.
+The strict comparison runs the backend in its parity mode (GGML_B200_CPU_EXACT=1: every float sum in the order of the reference's
+AVX2 build, the FP16 V accumulator of f16-cache attention, ggml-cpu.c:12376-12390, glibc's sinf/cosf/expf restated): observed result
+is BIT-IDENTICAL logits.  The default fast mode is checked against the envelope inside which two builds of the reference itself
+agree (profiles/r2_reference_cross_build.md).
 Nothing here reads /root/reference: the reference binaries were built into oracle/_ref by oracle/Makefile and travel.
 """
 import json
@@ -120,20 +121,25 @@ def test_logits_and_greedy_tokens_match_reference_cpu_backend(model, ftype, laye
     assert len(cpu_t) == N_GEN and np.array_equal(cpu_t, gpu_t), greport
 
 
-def test_f16_kv_default_mode_bound():
-    """Default (fast) mode with an f16 cache accumulates P.V in f32; the reference rounds its accumulator to fp16 after every
-    cell, which is worth ~1e-2 of noise at a few hundred cells.  The default mode must stay within that
-    documented bound of the CPU arm, and the parity mode must be at least 3x closer."""
+@pytest.mark.parametrize("model,ftype,layers,kv,seed,penv", CASES)
+def test_fast_mode_within_reference_cross_build_envelope(model, ftype, layers, kv, seed, penv):
+    """The default (fast) mode computes the reference's integers exactly but adds float terms in its own order (and, for an f16
+    cache, accumulates P.V in f32 instead of the reference's FP16 accumulator).  The reference pipeline amplifies any such
+    difference to ~1e-2 of the logits within a few layers: two builds of the reference itself (AVX2 vs SSE4.2) differ by
+    max 1.6e-2 / 3.7e-2, mean 0.9e-2 / 2.8e-2 on these two fixtures (profiles/r2_reference_cross_build.md).  The fast mode
+    must stay inside that same envelope, and may only pick another greedy token where the CPU's own margin is that small."""
     need_tools()
-    gguf = gguf_for("tinyllama", "q4_0", 0)
-    cpu, _, _ = dump(gguf, "f16b_cpu", 0, N_PROMPT, 64, "f16", False, 0)
-    fast, _, _ = dump(gguf, "f16b_fast", 99, N_PROMPT, 64, "f16", False, 0, {"GGML_B200_FA_EXACT": "0"})
-    exact, _, _ = dump(gguf, "f16b_exact", 99, N_PROMPT, 64, "f16", False, 0, {"GGML_B200_FA_EXACT": "1"})
-    rf, re_ = rel_err(cpu, fast), rel_err(cpu, exact)
-    print("PARITY f16-kv modes", json.dumps({"fast_max": float(rf.max()), "fast_mean": float(rf.mean()), "exact_max": float(re_.max()), "exact_mean": float(re_.mean())}))
-    assert re_.max() <= 1e-2
-    assert rf.max() <= 6e-2
-    assert re_.mean() * 3 <= rf.mean() or rf.mean() <= 1e-3
+    gguf = gguf_for(model, ftype, layers)
+    tag = "%s_%s_fast" % (model, kv)
+    cpu, _, _ = dump(gguf, tag + "_cpu", 0, N_PROMPT, 64, kv, False, seed)
+    gpu, _, _ = dump(gguf, tag + "_gpu", 99, N_PROMPT, 64, kv, False, seed, {"GGML_B200_CPU_EXACT": "0"})
+    rel, m = rel_err(cpu, gpu), margins(cpu)
+    agree = cpu.argmax(1) == gpu.argmax(1)
+    print("PARITY fast-mode", json.dumps({"case": tag, "max_rel_err": float(rel.max()), "mean_rel_err": float(rel.mean()), "argmax_agree": int(agree.sum()),
+                                          "rows": int(len(rel)), "margin_at_disagreements": [float(x) for x in m[~agree][:8]]}))
+    assert np.isfinite(gpu).all()
+    assert rel.max() <= 5e-2 and rel.mean() <= 3.5e-2
+    assert all(m[i] <= 2 * rel[i] for i in np.nonzero(~agree)[0])
 
 
 def test_no_cpu_fallback_splits():
