@@ -156,6 +156,16 @@ bool supports_glue(const b200_op *op);
 int op_allreduce(b200_ctx *ctx, const b200_op *op);     // comm.cu
 bool supports_allreduce(const b200_op *op);
 
+// rope parameters shared by glue.cu and the decode-step kernel (dstep.cu)
+struct RopeParams {
+    int n_dims, mode, n_ctx_orig;
+    float freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow;
+    float theta_scale, corr0, corr1;
+    int exact;        // cpu-exact mode: glibc's sinf/cosf restated (common.cuh), which the CPU backend calls; CUDA's sinf/cosf are
+                      // 1-2 ulp off here and there and every ulp can flip a KV-store / activation rounding downstream
+};
+RopeParams make_rope_params(const int32_t *params);      // glue.cu: op_params words -> RopeParams (theta_scale, YaRN corr dims)
+
 // fused ROPE(q) + ROPE(k) + KV-store of k and v for a decode ubatch (glue.cu); q/k/v are contiguous [D, heads, T] f32
 struct RopeStoreDesc {
     const float *q, *k, *v;
@@ -303,6 +313,11 @@ __device__ __forceinline__ float glibc_expf(float x) {
     double yv = __fma_rn(0x1.62e42ff0c52d6p-1 / 32, r, 1.0);
     yv = __fma_rn(z, r2, yv);
     return (float)__dmul_rn(yv, s);
+}
+
+__device__ __forceinline__ void rope_sincos(float th, int exact, float &s, float &c) {
+    if (exact) glibc_sincosf(th, s, c);
+    else { s = sinf(th); c = cosf(th); }
 }
 
 // ggml_v_silu (ggml-cpu.c:2156-2164): x / (1 + expf(0 - x)), IEEE division

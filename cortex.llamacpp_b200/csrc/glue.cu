@@ -114,17 +114,6 @@ __global__ void __launch_bounds__(256) b200_unary_kernel(const float *x, const f
 // ---------------------------------------------------------------------------------------------- rope
 // ggml_compute_forward_rope_f32 (ggml-cpu.c:10671-10800) with ggml_rope_cache_init (:10597-10613): theta starts at
 // pos and is multiplied by theta_scale once per pair (sequential product, reproduced here), YaRN mix per rope_yarn.
-struct RopeParams {
-    int n_dims, mode, n_ctx_orig;
-    float freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow;
-    float theta_scale, corr0, corr1;
-    int exact;        // cpu-exact mode: glibc's sinf/cosf restated (common.cuh), which the CPU backend calls; CUDA's sinf/cosf are
-                      // 1-2 ulp off here and there and every ulp can flip a KV-store / activation rounding downstream
-};
-__device__ __forceinline__ void rope_sincos(float th, int exact, float &s, float &c) {
-    if (exact) glibc_sincosf(th, s, c);
-    else { s = sinf(th); c = cosf(th); }
-}
 template <typename T>
 __global__ void __launch_bounds__(128) b200_rope_kernel(b200_tensor x, b200_tensor pos, b200_tensor ff, b200_tensor y, RopeParams rp, int has_ff) {
     // grid: (ne2 tokens, ne1 heads, ne3); threads over pairs
@@ -534,7 +523,7 @@ __global__ void __launch_bounds__(64) b200_rope_store_kernel(const RopeStoreDesc
     }
 }
 
-RopeParams make_rope_params(const int32_t *params) {
+RopeParams make_rope_params_impl(const int32_t *params) {
     RopeParams rp;
     auto f = [&](int i) { float v; memcpy(&v, &params[i], 4); return v; };
     rp.n_dims = params[1]; rp.mode = params[2]; rp.n_ctx_orig = params[4];
@@ -551,10 +540,12 @@ RopeParams make_rope_params(const int32_t *params) {
 
 }  // namespace
 
+RopeParams make_rope_params(const int32_t *params) { return make_rope_params_impl(params); }
+
 int launch_rope_store(b200_ctx *ctx, const RopeStoreDesc &din) {
     RopeStoreDesc d = din;
     d.use_pdl = ctx->opt_pdl;
-    RopeParams rp = make_rope_params(d.rope_params);
+    RopeParams rp = make_rope_params_impl(d.rope_params);
     rp.exact = ctx->opt_cpu_exact;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(d.H + 2 * d.Hkv), (unsigned)d.T);
