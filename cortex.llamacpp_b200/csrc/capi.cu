@@ -18,6 +18,7 @@ void b200_set_error(const char *fmt, ...) {
 }
 
 void graph_cache_free(b200_ctx *ctx);   // graph.cu
+void dstep_cache_free(b200_ctx *ctx);   // dstep.cu
 
 void *b200_ctx::get_scratch(int slot, size_t size) {
     if (size <= scratch_size[slot]) return scratch[slot];
@@ -96,6 +97,7 @@ b200_ctx *b200_ctx_create(int device) {
     if (const char *e = getenv("GGML_B200_PDL")) ctx->opt_pdl = atoi(e);
     if (const char *e = getenv("GGML_B200_FA_EXACT")) ctx->opt_cpu_exact = atoi(e);
     if (const char *e = getenv("GGML_B200_CPU_EXACT")) ctx->opt_cpu_exact = atoi(e);
+    if (const char *e = getenv("GGML_B200_DSTEP")) ctx->opt_dstep = atoi(e);
     return ctx;
 }
 
@@ -104,6 +106,8 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     graph_cache_free(ctx);
+    dstep_cache_free(ctx);
+    if (ctx->eager_kv_table) cudaFree(ctx->eager_kv_table);
     b200_comm_destroy(ctx);
     if (ctx->fattn_counters) cudaFree(ctx->fattn_counters);
     for (int i = 0; i < SCRATCH_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
@@ -124,7 +128,7 @@ int b200_synchronize(b200_ctx *ctx) {
 int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     std::string k(key);
     int *slot = k == "fusion" ? &ctx->opt_fusion : k == "pdl" ? &ctx->opt_pdl : k == "l2_prefetch" ? &ctx->opt_l2_prefetch :
-                k == "debug_skip" ? &ctx->opt_debug_skip : (k == "fa_exact" || k == "cpu_exact") ? &ctx->opt_cpu_exact : nullptr;
+                k == "debug_skip" ? &ctx->opt_debug_skip : (k == "fa_exact" || k == "cpu_exact") ? &ctx->opt_cpu_exact : k == "dstep" ? &ctx->opt_dstep : nullptr;
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
     else if (slot) {
         if (*slot != value) {                 // captured graphs bake these options in: drop them

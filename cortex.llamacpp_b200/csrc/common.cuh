@@ -133,6 +133,9 @@ struct b200_ctx {
                                             // V accumulator of f16-cache attention, correctly rounded exp/sin/cos.  Slow; proves summation order is the only difference
     int           opt_debug_skip  = 0;      // timing experiments only: bit 0 flash_attn, 1 rope+store, 2 GEMV are not launched
     GraphCache *  graph_cache = nullptr;
+    void *        dstep_cache = nullptr;       // decode-step programs (dstep.cu)
+    void **       eager_kv_table = nullptr;    // KV-store destinations of eagerly run decode-step programs (graph.cu)
+    int           opt_dstep = 1;               // 1: a batch-1 decode step runs as one persistent kernel (dstep.cu)
     void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)
     b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
     bool          capturing = false;

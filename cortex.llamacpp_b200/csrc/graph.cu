@@ -9,8 +9,10 @@
 //      replay the captured cudaGraphExec instead of re-launching ~10 kernels per layer.
 #include "common.cuh"
 #include "gemv.h"
+#include "dstep.h"
 #include <string.h>
 #include <algorithm>
+#include <memory>
 
 // A decode step of llama.cpp differs from the previous one ONLY in where the new K/V rows are stored (the CPY destinations are
 // views of the cache at kv_head, llama-graph.cpp:1375-1397).  The reference patches those kernel parameters into its captured
@@ -79,7 +81,7 @@ extern "C" int b200_op_compute(b200_ctx *ctx, const b200_op *op) {
 // A llama layer becomes: [norm+QKV] [rope+store] [flash_attn (+combine)] [wo+residual] [norm+gate|up] [swiglu+down+residual].
 // Intermediates that only lived between the fused ops are never materialised; the matcher proves with a liveness scan
 // over the op list (address ranges, first access after the pattern) that nobody else reads them.
-enum { EX_OP = 0, EX_GEMV = 1, EX_ROPE_STORE = 2 };
+enum { EX_OP = 0, EX_GEMV = 1, EX_ROPE_STORE = 2, EX_DSTEP = 3 };
 static const int g_fuse_debug = getenv("GGML_B200_FUSE_DEBUG") ? atoi(getenv("GGML_B200_FUSE_DEBUG")) : 0;
 struct ExecNode {
     int kind = EX_OP;
@@ -89,6 +91,7 @@ struct ExecNode {
     const void *pf_ptr = nullptr; size_t pf_bytes = 0;
     RopeStoreDesc rs;                            // EX_ROPE_STORE
     int kv_slot = -1;                            // index of this node's K destination in the KV pointer table (V = +1)
+    std::shared_ptr<std::vector<DsNode>> ds;     // EX_DSTEP: the run of nodes one persistent decode-step launch executes (dstep.cu)
 };
 
 static bool same_tensor(const b200_tensor &a, const b200_tensor &b) {
@@ -350,6 +353,61 @@ static int match_norm_mm(const b200_op *ops, int n, int i, std::vector<ExecNode>
     return 3;
 }
 
+// Batch-1 decode: maximal runs of nodes the persistent decode-step kernel can execute (fused GEMVs, rope+store followed by its
+// flash attention, plain decode matmuls, row gathers, dense adds) become ONE launch (dstep.cu).  A run needs >= 2 matmuls.
+static void pack_dstep(b200_ctx *ctx, std::vector<ExecNode> &list) {
+    static const int env_skip = getenv("GGML_B200_DEBUG_SKIP") ? atoi(getenv("GGML_B200_DEBUG_SKIP")) : 0;
+    const int dbg_skip = env_skip | ctx->opt_debug_skip;
+    std::vector<ExecNode> out;
+    out.reserve(list.size());
+    size_t i = 0;
+    while (i < list.size()) {
+        std::vector<DsNode> run;
+        size_t j = i;
+        int n_mm = 0;
+        while (j < list.size()) {
+            const ExecNode &e = list[j];
+            DsNode d;
+            if (e.kind == EX_GEMV && dstep_gemv_eligible(ctx, e.seg, e.nseg, e.K, e.act, e.ncols)) {
+                d.kind = DS_GEMV; d.nseg = e.nseg; d.K = e.K; d.act = e.act;
+                for (int s = 0; s < e.nseg; s++) d.seg[s] = e.seg[s];
+                if (!(dbg_skip & 4)) run.push_back(d);
+                n_mm++; j++;
+            } else if (e.kind == EX_ROPE_STORE && j + 1 < list.size() && list[j + 1].kind == EX_OP && list[j + 1].op.op == B200_OP_FLASH_ATTN_EXT &&
+                       dstep_attn_eligible(ctx, e.rs, list[j + 1].op)) {
+                d.kind = DS_ATTN; d.rs = e.rs; d.fa = list[j + 1].op;
+                if (!(dbg_skip & 3)) run.push_back(d);
+                j += 2;
+            } else if (e.kind == EX_OP && e.op.op == B200_OP_MUL_MAT && is_decode_mm(e.op) && e.op.dst.ne[1] == 1 && (e.op.src[0].flags & B200_TENSOR_FLAG_WEIGHT)) {
+                GemvSegDesc sg = seg_of(e.op, (float *)e.op.dst.data, (size_t)e.op.src[0].ne[1], nullptr);
+                GemvActDesc ga = {};
+                ga.mode = ACT_F32; ga.x = (const float *)e.op.src[1].data; ga.x_stride = e.op.src[1].nb[1];
+                if (!dstep_gemv_eligible(ctx, &sg, 1, e.op.src[0].ne[0], ga, 1)) break;
+                d.kind = DS_GEMV; d.nseg = 1; d.K = e.op.src[0].ne[0]; d.act = ga; d.seg[0] = sg;
+                if (!(dbg_skip & 4)) run.push_back(d);
+                n_mm++; j++;
+            } else if (e.kind == EX_OP && (e.op.op == B200_OP_GET_ROWS || e.op.op == B200_OP_ADD) && dstep_copy_eligible(e.op) && !run.empty()) {
+                d.kind = DS_COPY; d.cp = e.op;
+                run.push_back(d);
+                j++;
+            } else break;
+        }
+        // trailing gathers / adds without a consumer inside the run stay ordinary launches
+        while (j > i && !run.empty() && run.back().kind == DS_COPY) { run.pop_back(); j--; }
+        if (n_mm >= 2 && !run.empty()) {
+            ExecNode m;
+            m.kind = EX_DSTEP;
+            m.ds = std::make_shared<std::vector<DsNode>>(std::move(run));
+            out.push_back(m);
+            i = j;
+        } else {
+            out.push_back(list[i]);
+            i++;
+        }
+    }
+    list.swap(out);
+}
+
 // returns the list actually executed
 static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> &out) {
     out.clear();
@@ -421,6 +479,7 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
         }
         if (e.kind == EX_GEMV || mm_op) next = &e;
     }
+    if (layer_fusion && ctx->opt_dstep) pack_dstep(ctx, out);
     return B200_OK;
 }
 
@@ -436,7 +495,12 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
             if ((dbg_skip & 4) && e.kind == EX_GEMV) continue;
             if ((dbg_skip & 8) && e.kind == EX_OP && e.op.op == B200_OP_ALLREDUCE) continue;
         }
-        if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf_ptr, e.pf_bytes);
+        if (e.kind == EX_DSTEP) {
+            DsProgram *prog = nullptr;
+            rc = dstep_prepare(ctx, *e.ds, &prog);           // cached by content: a hit (no upload) once prepare_dstep() has seen this list
+            if (!rc) rc = dstep_launch(ctx, prog);
+        }
+        else if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf_ptr, e.pf_bytes);
         else if (e.kind == EX_ROPE_STORE) rc = launch_rope_store(ctx, e.rs);
         else rc = dispatch(ctx, &e.op);
         if (rc) return rc;
@@ -452,24 +516,72 @@ static bool is_kv_store(const b200_op &o) {
 }
 
 // point every fused rope+store node at its slots of the entry's device table; false if a KV store is not inside such a node
+// every rope+store descriptor of a list: plain EX_ROPE_STORE nodes and the attention nodes inside decode-step runs
+static void collect_rope_stores(std::vector<ExecNode> &list, std::vector<RopeStoreDesc *> &out) {
+    out.clear();
+    for (ExecNode &x : list) {
+        if (x.kind == EX_ROPE_STORE) out.push_back(&x.rs);
+        else if (x.kind == EX_DSTEP) for (DsNode &d : *x.ds) if (d.kind == DS_ATTN) out.push_back(&d.rs);
+    }
+}
 static bool bind_kv_table(GraphCacheEntry &e, const b200_op *ops, std::vector<ExecNode> &list, bool assign) {
     e.node_kv.clear();
     size_t covered = 0;
     int j = 0;
-    for (ExecNode &x : list) {
-        if (x.kind != EX_ROPE_STORE) continue;
+    std::vector<RopeStoreDesc *> rss;
+    collect_rope_stores(list, rss);
+    for (RopeStoreDesc *rs : rss) {
         int ki = -1, vi = -1;
         for (int idx : e.kv_idx) {
-            if (ops[idx].dst.data == x.rs.k_dst && ki < 0) ki = idx;
-            else if (ops[idx].dst.data == x.rs.v_dst && vi < 0) vi = idx;
+            if (ops[idx].dst.data == rs->k_dst && ki < 0) ki = idx;
+            else if (ops[idx].dst.data == rs->v_dst && vi < 0) vi = idx;
         }
         if (ki < 0 || vi < 0) return false;
         e.node_kv.push_back({ki, vi});
         covered += 2;
-        if (assign) { x.rs.k_dst_ind = (void *const *)(e.dev_table + 2 * j); x.rs.v_dst_ind = (void *const *)(e.dev_table + 2 * j + 1); }
+        if (assign) { rs->k_dst_ind = (void *const *)(e.dev_table + 2 * j); rs->v_dst_ind = (void *const *)(e.dev_table + 2 * j + 1); }
         j++;
     }
     return covered == e.kv_idx.size();
+}
+static void unbind_kv_table(std::vector<ExecNode> &list) {
+    std::vector<RopeStoreDesc *> rss;
+    collect_rope_stores(list, rss);
+    for (RopeStoreDesc *rs : rss) rs->k_dst_ind = rs->v_dst_ind = nullptr;
+}
+// Eagerly run lists: the decode-step programs are cached by content, and the KV-store destinations change every token.  Route
+// them through a context-owned device table (refreshed here, stream-ordered) so that the program stays the same from step to step.
+static int bind_eager_kv(b200_ctx *ctx, std::vector<ExecNode> &list) {
+    bool any = false;
+    for (ExecNode &x : list) any |= x.kind == EX_DSTEP;
+    if (!any) return B200_OK;
+    std::vector<RopeStoreDesc *> rss;
+    collect_rope_stores(list, rss);
+    if (rss.empty() || rss.size() > 512) return B200_OK;
+    if (!ctx->eager_kv_table && cudaMalloc((void **)&ctx->eager_kv_table, 2 * 512 * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); ctx->eager_kv_table = nullptr; return B200_OK; }
+    void *host[2 * 512];
+    for (size_t j = 0; j < rss.size(); j++) {
+        host[2 * j] = rss[j]->k_dst; host[2 * j + 1] = rss[j]->v_dst;
+        rss[j]->k_dst_ind = (void *const *)(ctx->eager_kv_table + 2 * j); rss[j]->v_dst_ind = (void *const *)(ctx->eager_kv_table + 2 * j + 1);
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->eager_kv_table, host, 2 * rss.size() * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+    return B200_OK;
+}
+// upload (or find) the decode-step programs of a list before any launch -- in particular before stream capture begins
+static int prepare_dstep(b200_ctx *ctx, std::vector<ExecNode> &list) {
+    for (ExecNode &x : list) {
+        if (x.kind != EX_DSTEP) continue;
+        DsProgram *prog = nullptr;
+        int rc = dstep_prepare(ctx, *x.ds, &prog);
+        if (rc) return rc;
+    }
+    return B200_OK;
+}
+static int run_eager(b200_ctx *ctx, std::vector<ExecNode> &list) {
+    int rc = bind_eager_kv(ctx, list);
+    if (!rc) rc = prepare_dstep(ctx, list);
+    if (!rc) rc = run_list(ctx, list);
+    return rc;
 }
 
 static int upload_kv_table(b200_ctx *ctx, const GraphCacheEntry &e, const b200_op *ops) {
@@ -494,13 +606,13 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
     if (ctx->opt_fusion) { int frc = fuse(ctx, ops, n_ops, list); if (frc) return frc; }
     else { list.resize(n_ops); for (int i = 0; i < n_ops; i++) list[i].op = ops[i]; }
 
-    if (!ctx->opt_cuda_graphs || n_ops < 8) return run_list(ctx, list);
+    if (!ctx->opt_cuda_graphs || n_ops < 8) return run_eager(ctx, list);
 
     // only decode-sized steps repeat (a prompt ubatch is seen once, and capturing its ~1000 big launches costs more than it saves)
     {
         bool decode_like = false;
-        for (const ExecNode &x : list) decode_like |= x.kind == EX_GEMV;
-        if (!decode_like && ctx->opt_fusion >= 2) return run_list(ctx, list);
+        for (const ExecNode &x : list) decode_like |= x.kind == EX_GEMV || x.kind == EX_DSTEP;
+        if (!decode_like && ctx->opt_fusion >= 2) return run_eager(ctx, list);
     }
     // ---- CUDA graph replay keyed on the op list modulo the KV-store destinations ----
     if (!ctx->graph_cache) ctx->graph_cache = new GraphCache();
@@ -530,7 +642,13 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
             if (!e.dev_table && cudaMalloc((void **)&e.dev_table, 2 * 512 * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); e.dev_table = nullptr; e.indirect = false; }
             if (e.indirect && (e.node_kv.size() > 512 || !bind_kv_table(e, ops, list, true))) e.indirect = false;
             if (e.indirect) { int rc = upload_kv_table(ctx, e, ops); if (rc) return rc; }
-            else { e.kv_ptrs.clear(); for (int idx : kv_idx) e.kv_ptrs.push_back(ops[idx].dst.data); for (ExecNode &x : list) if (x.kind == EX_ROPE_STORE) x.rs.k_dst_ind = x.rs.v_dst_ind = nullptr; }
+            else { e.kv_ptrs.clear(); for (int idx : kv_idx) e.kv_ptrs.push_back(ops[idx].dst.data); unbind_kv_table(list); }
+        }
+        {   // decode-step programs are uploaded before the capture starts; if that grew a scratch area the graph cache (and `e`) is gone
+            const int64_t gen = ctx->scratch_gen;
+            int prc = prepare_dstep(ctx, list);
+            if (prc) return prc;
+            if (gen != ctx->scratch_gen) { unbind_kv_table(list); return run_eager(ctx, list); }
         }
         cudaGraph_t g = nullptr;
         ctx->capturing = true;
@@ -541,13 +659,13 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
         if (rc || ce != cudaSuccess || !g) {
             cudaGetLastError();
             if (g) cudaGraphDestroy(g);
-            for (ExecNode &x : list) if (x.kind == EX_ROPE_STORE) x.rs.k_dst_ind = x.rs.v_dst_ind = nullptr;
-            return run_list(ctx, list);          // fall back to eager launches
+            unbind_kv_table(list);
+            return run_eager(ctx, list);          // fall back to eager launches
         }
         if (cudaGraphInstantiate(&e.exec, g, 0) != cudaSuccess) {
             cudaGetLastError(); e.exec = nullptr; cudaGraphDestroy(g);
-            for (ExecNode &x : list) if (x.kind == EX_ROPE_STORE) x.rs.k_dst_ind = x.rs.v_dst_ind = nullptr;
-            return run_list(ctx, list);
+            unbind_kv_table(list);
+            return run_eager(ctx, list);
         }
         cudaGraphDestroy(g);
         CUDA_TRY(cudaGraphLaunch(e.exec, ctx->stream));
@@ -573,8 +691,9 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
     }
     if (gdebug) {
         int ng = 0, nr = 0;
-        for (const ExecNode &x : list) { ng += x.kind == EX_GEMV; nr += x.kind == EX_ROPE_STORE; }
-        fprintf(stderr, "[b200 graph] new list: %d ops -> %zu nodes (%d fused gemv, %d rope+store), %zu kv stores; op ids:", n_ops, list.size(), ng, nr, kv_idx.size());
+        int nd = 0;
+        for (const ExecNode &x : list) { ng += x.kind == EX_GEMV; nr += x.kind == EX_ROPE_STORE; nd += x.kind == EX_DSTEP; }
+        fprintf(stderr, "[b200 graph] new list: %d ops -> %zu nodes (%d fused gemv, %d rope+store, %d decode-step runs), %zu kv stores; op ids:", n_ops, list.size(), ng, nr, nd, kv_idx.size());
         for (int i = 0; i < n_ops && i < 64; i++) fprintf(stderr, " %d", ops[i].op);
         fprintf(stderr, "\n");
     }
@@ -584,5 +703,5 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
     for (int idx : kv_idx) ne.kv_ptrs.push_back(ops[idx].dst.data);
     ne.indirect = !kv_idx.empty() && bind_kv_table(ne, ops, list, false);
     gc.entries.push_back(std::move(ne));
-    return run_list(ctx, list);
+    return run_eager(ctx, list);
 }

@@ -218,3 +218,50 @@ def test_graph_replay_survives_scratch_growth(b200, ctx):
         ctx.compute(ops_small); ctx.sync()
         assert np.array_equal(g.logits[:g.V].cpu().numpy(), eager)
     ctx.set_option("pdl", 0); ctx.set_option("cuda_graphs", 0)
+
+
+@pytest.mark.parametrize("model,ftype,kv", [("tiny-d128", "q4_k_m", "f16"), ("tiny-d128", "q4_k_m", "q8_0"), ("tiny-d128", "q5_k_m", "q4_0"),
+                                            ("mid-d128", "q4_k_m", "f16"), ("mid-d128", "q5_k_m", "q8_0")])
+def test_decode_step_kernel_vs_per_launch_path(b200, ctx, model, ftype, kv):
+    """option dstep: a batch-1 decode step as ONE persistent kernel (dstep.cu) against the per-launch fused path it replaces, on
+    the same cache contents: the GEMV phases use the same block decoders (identical integers) and the attention phase the same
+    arithmetic, so every single step must agree to float-summation-order noise; the whole loop stays inside the fast-mode envelope
+    of the oracle; and the step must really be one decode-step launch (+ the mask conversion)."""
+    import torch
+    import llama_forward as OF
+    from __graft_entry__ import load_llama_graph
+    lg = load_llama_graph()
+    g = lg.LlamaGraph(b200, model=model, ftype=ftype, kv=kv, n_ctx=512, max_tokens=4)
+    ctx.set_option("fusion", 2); ctx.set_option("cuda_graphs", 0); ctx.set_option("pdl", 1)
+    rng = np.random.default_rng(11)
+    g.fill_cache(300)
+    caches = None
+    worst_pair, worst_orc = 0.0, 0.0
+    try:
+        for step in range(6):
+            kv_head, n_kv = 300 + step, 512
+            emb, pos, mask = g.set_inputs_host(1, kv_head, n_kv, rng)
+            g.inp_embd[:g.E] = torch.from_numpy(emb.reshape(-1)).cuda()
+            g.pos[:1] = torch.from_numpy(pos).cuda()
+            g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda()
+            torch.cuda.synchronize()
+            want, caches = OF.forward(g, emb, pos, mask, kv_head, n_kv, caches=caches)
+            ops = g.build(1, kv_head, n_kv)
+            outs, launches = {}, {}
+            for d in (0, 1):                      # the per-launch run writes the same K/V cell first; the decode-step run overwrites it with equal bytes
+                ctx.set_option("dstep", d)
+                g.logits.zero_(); torch.cuda.synchronize()
+                n0 = ctx.launches()
+                ctx.compute(ops); ctx.sync()
+                launches[d] = ctx.launches() - n0
+                outs[d] = g.logits[:g.V].cpu().numpy().copy()
+            assert np.isfinite(outs[1]).all()
+            pair = float(np.abs(outs[0] - outs[1]).max() / np.abs(outs[0]).max())
+            orc = float(np.abs(outs[1] - want[0]).max() / np.abs(want[0]).max())
+            worst_pair, worst_orc = max(worst_pair, pair), max(worst_orc, orc)
+            assert launches[1] <= 2 < launches[0], launches
+            assert orc <= FAST_MODE_BOUND, (step, orc)
+            assert pair <= FAST_MODE_BOUND, (step, pair)
+        print("dstep %s %s %s: worst vs per-launch path %.3g, vs oracle %.3g" % (model, ftype, kv, worst_pair, worst_orc))
+    finally:
+        ctx.set_option("dstep", 1); ctx.set_option("pdl", 0)
