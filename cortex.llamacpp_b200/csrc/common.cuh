@@ -135,7 +135,8 @@ struct b200_ctx {
     GraphCache *  graph_cache = nullptr;
     void *        dstep_cache = nullptr;       // decode-step programs (dstep.cu)
     void **       eager_kv_table = nullptr;    // KV-store destinations of eagerly run decode-step programs (graph.cu)
-    int           opt_dstep = 1;               // 1: a batch-1 decode step runs as one persistent kernel (dstep.cu)
+    int           opt_dstep = 0;               // 1: a batch-1 decode step runs as ONE persistent kernel (dstep.cu).  Opt-in: correct, but measured
+                                               // slower than the per-launch path on B200 (2.66 vs 1.88 ms/step, profiles/r2_dstep_timeline.md)
     void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)
     b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
     bool          capturing = false;

@@ -20,11 +20,11 @@ ctx.set_option("cuda_graphs", 0); ctx.set_option("fusion", 2); ctx.set_option("d
 for _ in range(3): ctx.compute(ops)
 ctx.sync()
 nph = (6 if not skip else 4) * layers + 1
-prof = torch.zeros(148 * nph * 4, dtype=torch.int64, device="cuda"); torch.cuda.synchronize()
+prof = torch.zeros(148 * nph * 8, dtype=torch.int64, device="cuda"); torch.cuda.synchronize()
 L.b200_debug_set_prof(ctx.h, prof.data_ptr())
 ctx.compute(ops); ctx.sync()
 L.b200_debug_set_prof(ctx.h, None)
-p = prof.cpu().numpy().reshape(148, nph, 4).astype(np.int64)
+p = prof.cpu().numpy().reshape(148, nph, 8).astype(np.int64)
 t0 = p[:, 0, 0].min()
 names = ["qkv", "attn", "combine", "wo", "gate|up", "down"] if not skip else ["qkv", "wo", "gate|up", "down"]
 print("phase: start(min..max) | prologue(median) | work(median, max) | barrier wait(median) | phase total   [ns]")
@@ -33,4 +33,10 @@ for ph in range(min(nph, 2 * len(names) + 1)):
     nm = names[ph % len(names)] if ph < nph - 1 else "output"
     print("%2d %-8s start %7d..%7d | prologue %6d | work %6d max %6d | barrier %6d max %6d | total %6d" % (
         ph, nm, st.min(), st.max(), int(np.median(pr[pr > 0])) if (pr > 0).any() else 0, int(np.median(wk)), wk.max(), int(np.median(br)), br.max(), (p[:, ph, 3].max() - p[:, ph, 0].min())))
+for ph in range(nph):
+    if ph % len(names) == 1 and not skip and ph < 8:
+        a = p[:, ph, :]
+        ok = a[:, 4] > 0
+        f = lambda i, j: int(np.median(a[ok, i] - a[ok, j]))
+        print("   attn phase %d: inputs %d | rope+store %d | walk %d | bar %d | merge+publish %d  [ns, median over %d unit CTAs]" % (ph, f(4, 0), f(5, 4), f(6, 5), f(7, 6), f(2, 7), ok.sum()))
 print("kernel total %.1f us for %d phases" % ((p[:, -1, 3].max() - t0) / 1e3, nph))
