@@ -120,8 +120,8 @@ struct b200_ctx {
     int           sm_count = 148;
     size_t        smem_optin = 227 * 1024;
     // growable device scratch (activation quantisation, split-KV partials, MoE routing tables)
-    void *        scratch[5]      = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t        scratch_size[5] = {0, 0, 0, 0, 0};
+    void *        scratch[6]      = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t        scratch_size[6] = {0, 0, 0, 0, 0, 0};
     int64_t       launches = 0;
     int64_t       scratch_gen = 0;          // bumped on every scratch reallocation (captured graphs are dropped with it)
     // options
@@ -137,6 +137,11 @@ struct b200_ctx {
     void **       eager_kv_table = nullptr;    // KV-store destinations of eagerly run decode-step programs (graph.cu)
     int           opt_dstep = 0;               // 1: a batch-1 decode step runs as ONE persistent kernel (dstep.cu).  Opt-in: correct, but measured
                                                // slower than the per-launch path on B200 (2.66 vs 1.88 ms/step, profiles/r2_dstep_timeline.md)
+    // live-tile map of the attention mask (fattn.cu): built by the first FLASH_ATTN_EXT of a graph that uses a given mask, reused by
+    // the other layers; dropped at every graph_compute / compute_op entry and when an op writes into the mask
+    bool          fa_map_valid = false;
+    uintptr_t     fa_map_mask = 0, fa_map_mask_end = 0;
+    int64_t       fa_map_key[4] = {0, 0, 0, 0};        // m_nb1, n_kv, n_q, QC
     void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)
     b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
     bool          capturing = false;
@@ -146,7 +151,7 @@ struct b200_ctx {
     void *get_scratch(int slot, size_t size);   // grows (sync + realloc) when too small; nullptr on OOM
 };
 
-enum { SCRATCH_ACT = 0, SCRATCH_FATTN = 1, SCRATCH_MOE = 2, SCRATCH_MISC = 3, SCRATCH_FUSE = 4, SCRATCH_COUNT = 5 };
+enum { SCRATCH_ACT = 0, SCRATCH_FATTN = 1, SCRATCH_MOE = 2, SCRATCH_MISC = 3, SCRATCH_FUSE = 4, SCRATCH_FAMAP = 5, SCRATCH_COUNT = 6 };
 
 // op entry points (each in its own .cu); all asynchronous on ctx->stream
 int op_mul_mat(b200_ctx *ctx, const b200_op *op);
@@ -193,6 +198,12 @@ int launch_mul_mat_exact(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, i
                          float *dst, size_t dst_stride);
 int launch_gemv(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
                 int ncols, float *dst, size_t dst_col_stride_elems, bool w_const);
+// small-batch (<= 32 columns) weight-streaming matmul on mma.sync s8 (gemv_mma.cu)
+bool gemv_mma_supported(int type, int64_t N, int64_t K, int64_t M);
+int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int ncols,
+                    float *dst, size_t dst_stride, bool stream_once, bool w_const, const float *residual = nullptr);
+int launch_act_prologue(b200_ctx *ctx, int mode, const float *x, size_t x_stride_bytes, const float *x2, float eps, int64_t K, int ncols, int q8k,
+                        uint8_t *scratch);
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -398,6 +409,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     return p;
 }
 // programmatic dependent launch
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

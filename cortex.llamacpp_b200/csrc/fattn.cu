@@ -35,6 +35,7 @@ struct FaParams {
     float *dst;
     float *part;                 // [tile][split][16][D + 2]
     int *counters;               // [tile] arrivals of the KV splits (self-resetting); NULL: separate combine kernel
+    const int *map; int map_stride;   // live-tile map [n_coltiles][1 + n_kv / 32]: count, then the indices of the 32-position tiles with any unmasked cell
     int n_q, n_kv, H, Hkv, gq, HG, QC, n_headtiles, n_coltiles, n_splits, kv_per_split;
     float scale, softcap, max_bias, m0, m1;
     int n_head_log2;
@@ -206,9 +207,15 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
     const int kv_begin = split * p.kv_per_split;
     const int kv_end = min(p.n_kv, kv_begin + p.kv_per_split);
 
-    for (int kv0 = kv_begin + warp * BK; kv0 < kv_end; kv0 += NWARP * BK) {
+    // with a live-tile map the splits share the LIVE tiles of this column tile evenly (a unified multi-slot cache leaves a batched
+    // step ~3 % of the cache per column tile, all of it inside one or two uniform splits); without, a uniform split of [0, n_kv)
+    const int *mp = p.map ? p.map + (size_t)ct * p.map_stride : nullptr;
+    int it_begin = kv_begin / BK, it_end = kv_end / BK;
+    if (mp) { const int cnt = mp[0]; it_begin = (int)((long long)split * cnt / p.n_splits); it_end = (int)((long long)(split + 1) * cnt / p.n_splits); }
+    for (int it = it_begin + warp; it < it_end; it += NWARP) {
+        const int kv0 = (mp ? mp[1 + it] : it) * BK;
         // ---- skip tiles that are fully masked for every query column of this CTA -------------------------
-        if (p.mask) {
+        if (p.mask && !mp) {
             bool any = false;
             for (int c = 0; c < p.QC; c++) {
                 const int col = c0 + c;
@@ -414,6 +421,48 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
             }
             p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / Lsum;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Live-tile map of the mask: for every column tile (QC query columns) the ascending list of 32-position KV tiles in which at least
+// one cell is not -inf.  One CTA per column tile; built once per graph (the mask is shared by all layers).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MAP_MAX_BATCH = 32;       // 4 warps x 32 batches x 32 tiles = 4096 tiles = 131072 KV positions
+__global__ void __launch_bounds__(128) b200_fattn_maskmap_kernel(const char *mask, uint64_t m_nb1, int n_q, int n_kv, int QC, int *map, int map_stride, int use_pdl) {
+    __shared__ uint32_t bal[4][MAP_MAX_BATCH];
+    __shared__ int wcnt[4];
+    if (use_pdl) { pdl_trigger(); pdl_wait(); }
+    const int ct = blockIdx.x, c0 = ct * QC, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntile = n_kv / BK;
+    const int nbatch = (ntile + 127) / 128;             // batches of 32 tiles per warp; warp w owns tiles [w * nbatch * 32, (w + 1) * nbatch * 32)
+    int cnt = 0;
+    for (int b = 0; b < nbatch; b++) {
+        const int t = (warp * nbatch + b) * 32 + lane;
+        bool live = false;
+        if (t < ntile)
+            for (int c = 0; c < QC && c0 + c < n_q; c++) {
+                const uint4 *mp = (const uint4 *)(mask + (uint64_t)(c0 + c) * m_nb1 + (uint64_t)t * (BK * 2));
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 v = mp[i];
+                    live |= v.x != 0xFC00FC00u || v.y != 0xFC00FC00u || v.z != 0xFC00FC00u || v.w != 0xFC00FC00u;
+                }
+            }
+        const uint32_t m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) bal[warp][b] = m;
+        cnt += __popc(m);
+    }
+    if (lane == 0) wcnt[warp] = cnt;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; w++) off += wcnt[w];
+    int *out = map + (size_t)ct * map_stride;
+    if (threadIdx.x == 0) out[0] = wcnt[0] + wcnt[1] + wcnt[2] + wcnt[3];
+    for (int b = 0; b < nbatch; b++) {
+        const uint32_t m = bal[warp][b];
+        if (m & (1u << lane)) out[1 + off + __popc(m & ((1u << lane) - 1))] = (warp * nbatch + b) * 32 + lane;
+        off += __popc(m);
     }
 }
 
@@ -895,6 +944,29 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
         CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_combine_kernel<128>, p, n_tiles));
         ctx->launches++;
         return B200_OK;
+    }
+    // batched steps and prompt ubatches: live-tile map of the mask, shared by every layer of the graph
+    static const int use_map = getenv("GGML_B200_FA_MAP") ? atoi(getenv("GGML_B200_FA_MAP")) : 1;
+    if (use_map && has_mask && p.n_q > 1 && p.n_kv / BK <= 4 * MAP_MAX_BATCH * 32 && !((uintptr_t)m.data & 15) && !(m.nb[1] & 15)) {
+        p.map_stride = p.n_kv / BK + 1;
+        const size_t need = (size_t)p.n_coltiles * p.map_stride * sizeof(int);
+        const bool grow = need > ctx->scratch_size[SCRATCH_FAMAP];
+        int *map = (int *)ctx->get_scratch(SCRATCH_FAMAP, need);
+        if (!map) return B200_ERR_ALLOC;
+        const int64_t key[4] = {(int64_t)m.nb[1], p.n_kv, p.n_q, p.QC};
+        if (grow || !ctx->fa_map_valid || ctx->fa_map_mask != (uintptr_t)m.data || memcmp(key, ctx->fa_map_key, sizeof(key)) != 0) {
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)p.n_coltiles); cfg.blockDim = dim3(128); cfg.stream = ctx->stream;
+            cfg.attrs = attr; cfg.numAttrs = p.use_pdl ? 1 : 0;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_maskmap_kernel, p.mask, p.m_nb1, p.n_q, p.n_kv, p.QC, map, p.map_stride, p.use_pdl));
+            ctx->launches++;
+            ctx->fa_map_valid = true; ctx->fa_map_mask = (uintptr_t)m.data; ctx->fa_map_mask_end = (uintptr_t)m.data + (size_t)m.nb[1] * (size_t)m.ne[1];
+            memcpy(ctx->fa_map_key, key, sizeof(key));
+        }
+        p.map = map;
     }
     // split the KV range so the grid covers the machine ~2-3x; each split is a multiple of NWARP*BK positions
     const int unit = NWARP * BK;

@@ -553,6 +553,29 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
         total_rows += segs[s].N;
     }
     if (total_rows <= 0) return B200_OK;
+    if (ncols > 4) {
+        // continuous-batching step (5..32 token columns): one producer launch quantises the activations, then every segment streams
+        // its weights once through the mma.sync kernel (gemv_mma.cu); the residual is added by its epilogue / split-K reduction
+        bool ok = ncols <= 32;
+        for (int s = 0; s < nseg; s++) ok = ok && gemv_mma_supported(segs[s].type, segs[s].N, K, ncols) && !segs[s].expert_id && !segs[s].dbgP;
+        if (ok) {
+            const ActLayout Lb = ActLayout::make(q8k, K);
+            const uint8_t *act = ga.act;
+            if (ga.mode != ACT_PREQ) {
+                uint8_t *scr = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, Lb.col_bytes * (size_t)ncols);
+                if (!scr) return B200_ERR_ALLOC;
+                int rc = launch_act_prologue(ctx, ga.mode, ga.x, ga.x_stride, ga.x2, ga.eps, K, ncols, q8k, scr);
+                if (rc) return rc;
+                act = scr;
+            }
+            for (int s = 0; s < nseg; s++) {
+                int rc = launch_gemv_mma(ctx, segs[s].type, segs[s].W, segs[s].rb, segs[s].N, K, act, ncols, segs[s].dst, segs[s].dst_stride, true, w_const,
+                                         segs[s].residual);
+                if (rc) return rc;
+            }
+            return B200_OK;
+        }
+    }
     if (ncols == 1) {
         // batch-1 decode over K-quants: the compact half-SM kernel (gemv_bs1.cu); anything it does not take falls through
         const int l2pf = g_gemv_l2pf >= 0 ? g_gemv_l2pf : ctx->opt_l2_prefetch;

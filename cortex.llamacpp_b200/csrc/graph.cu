@@ -42,6 +42,10 @@ void graph_cache_free(b200_ctx *ctx) {
 }
 
 static int dispatch(b200_ctx *ctx, const b200_op *op) {
+    if (ctx->fa_map_valid && op->dst.data) {       // an op that writes into the attention mask drops its live-tile map (fattn.cu)
+        const uintptr_t lo = (uintptr_t)op->dst.data;
+        if (lo < ctx->fa_map_mask_end && lo + (size_t)op->dst.nb[3] * (size_t)(op->dst.ne[3] > 0 ? op->dst.ne[3] : 1) > ctx->fa_map_mask) ctx->fa_map_valid = false;
+    }
     switch (op->op) {
         case B200_OP_NONE: return B200_OK;
         case B200_OP_MUL_MAT: return op_mul_mat(ctx, op);
@@ -69,6 +73,7 @@ extern "C" int b200_op_compute(b200_ctx *ctx, const b200_op *op) {
     if (!ctx || !op) return B200_ERR_FAILED;
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!b200_supports_op(ctx->device, op)) { b200_set_error("op %d not supported for these operands", op->op); return B200_ERR_UNSUPPORTED; }
+    ctx->fa_map_valid = false;
     return dispatch(ctx, op);
 }
 
@@ -120,8 +125,9 @@ static bool live_after(const b200_op *ops, int n, int from, const b200_tensor &t
     return false;
 }
 
-static bool is_vec_f32(const b200_tensor &t, int64_t rows) {   // dense f32 [rows, T<=4]
-    return t.type == B200_TYPE_F32 && t.ne[0] == rows && t.ne[1] >= 1 && t.ne[1] <= 4 && t.ne[2] == 1 && t.ne[3] == 1 && t.nb[0] == 4 &&
+constexpr int FUSE_MAX_T = 32;        // layer fusions cover batch-1 decode (<= 4 columns: GEMV) and continuous-batching steps (<= 32: gemv_mma)
+static bool is_vec_f32(const b200_tensor &t, int64_t rows) {   // dense f32 [rows, T<=32]
+    return t.type == B200_TYPE_F32 && t.ne[0] == rows && t.ne[1] >= 1 && t.ne[1] <= FUSE_MAX_T && t.ne[2] == 1 && t.ne[3] == 1 && t.nb[0] == 4 &&
            t.nb[1] == (uint64_t)rows * 4 && !((uintptr_t)t.data & 15);
 }
 // a decode-sized quantised matmul the GEMV can take as a segment: W quant rows back to back, x dense [K, T], dst dense [N, T]
@@ -420,7 +426,9 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
         for (int i = 0; i < n; i++) if (ops[i].op == B200_OP_MUL_MAT && is_decode_mm(ops[i]) && ops[i].src[0].ne[1] < (1 << 16)) maxN = std::max(maxN, ops[i].src[0].ne[1]);
         if (maxN == 0) layer_fusion = false;
         else {
-            const size_t per = (size_t)maxN * 4 * 4;      // up to 4 columns
+            int64_t maxT = 1;
+            for (int i = 0; i < n; i++) if (ops[i].op == B200_OP_MUL_MAT && is_decode_mm(ops[i])) maxT = std::max(maxT, ops[i].dst.ne[1]);
+            const size_t per = (size_t)maxN * 4 * (size_t)(maxT <= 4 ? 4 : FUSE_MAX_T);
             float *base = (float *)ctx->get_scratch(SCRATCH_FUSE, per * 5);
             if (!base) return B200_ERR_ALLOC;
             fs.q = base; fs.k = base + per / 4; fs.v = base + 2 * (per / 4); fs.g = base + 3 * (per / 4); fs.u = base + 4 * (per / 4);
@@ -597,6 +605,7 @@ static int upload_kv_table(b200_ctx *ctx, const GraphCacheEntry &e, const b200_o
 extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) {
     if (!ctx || (!ops && n_ops)) return B200_ERR_FAILED;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->fa_map_valid = false;            // the mask may have been rewritten between calls
     for (int i = 0; i < n_ops; i++)
         if (!b200_supports_op(ctx->device, &ops[i])) {
             b200_set_error("graph op %d (id %d) not supported", i, ops[i].op);
@@ -611,7 +620,12 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
     // only decode-sized steps repeat (a prompt ubatch is seen once, and capturing its ~1000 big launches costs more than it saves)
     {
         bool decode_like = false;
-        for (const ExecNode &x : list) decode_like |= x.kind == EX_GEMV || x.kind == EX_DSTEP;
+        for (const ExecNode &x : list) {
+            decode_like |= x.kind == EX_GEMV || x.kind == EX_DSTEP;
+            // a continuous-batching step (<= 32 token columns) repeats like a decode step
+            decode_like |= x.kind == EX_OP && x.op.op == B200_OP_MUL_MAT && x.op.src[1].ne[1] <= 32 && (x.op.src[0].flags & B200_TENSOR_FLAG_WEIGHT) &&
+                           b200_type_is_quant(x.op.src[0].type);
+        }
         if (!decode_like && ctx->opt_fusion >= 2) return run_eager(ctx, list);
     }
     // ---- CUDA graph replay keyed on the op list modulo the KV-store destinations ----

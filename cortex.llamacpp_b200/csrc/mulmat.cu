@@ -118,9 +118,9 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     const size_t rb = b200_row_bytes(w.type, K);
     const bool w_const = (w.flags & B200_TENSOR_FLAG_WEIGHT) != 0;
     const int64_t nbatch = x.ne[2] * x.ne[3];
-    // up to this many columns the streaming GEMV (4 columns per launch, weights re-streamed per chunk) beats the tensor-core
-    // GEMM, whose per-super-block drain costs the same for 8 tokens as for 128 (measured: profiles/r1_batched.md)
-    static const int64_t gemv_max_m = getenv("GGML_B200_GEMV_MAX_M") ? atoi(getenv("GGML_B200_GEMV_MAX_M")) : 8;
+    // up to this many columns the streaming GEMV (one launch, activations quantised in its prologue); above, the mma.sync small-batch
+    // kernel (gemv_mma.cu: 23 us vs 59 us at 8 columns on a 14336 x 4096 Q4_K matrix)
+    static const int64_t gemv_max_m = getenv("GGML_B200_GEMV_MAX_M") ? atoi(getenv("GGML_B200_GEMV_MAX_M")) : 4;
     if (ctx->opt_cpu_exact) {
         // parity mode: same quantised activations, float sums in the reference's SIMD order (exact.cu)
         uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)(M * nbatch));
@@ -147,6 +147,26 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
                 const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
                 float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
                 int rc = launch_gemv_f32(ctx, w.type, wp, rb, N, K, xp, x.nb[1], (int)M, dp, d.nb[1] / 4, w_const, 0, nullptr, 0.0f, nullptr);
+                if (rc) return rc;
+            }
+        return B200_OK;
+    }
+    // continuous-batching decode (9..32 columns): weight-streaming mma.sync kernel (gemv_mma.cu); q4_0 / q8_0, which the tcgen05
+    // GEMM does not decode, go through it in chunks of 32 columns at any batch size
+    static const int64_t mma_max_m = getenv("GGML_B200_MMA_MAX_M") ? atoi(getenv("GGML_B200_MMA_MAX_M")) : 32;
+    if (gemv_mma_supported(w.type, N, K, M) && (M <= mma_max_m || !gemm_i8_supported(w.type, N, K, M))) {
+        uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)M);
+        if (!act) return B200_ERR_ALLOC;
+        for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+                const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+                const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+                const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+                float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+                int rc = launch_quantize_act(ctx, q8k, xp, x.nb[1], K, M, act);
+                for (int64_t c0 = 0; c0 < M && !rc; c0 += 32)
+                    rc = launch_gemv_mma(ctx, w.type, wp, rb, N, K, act + (size_t)c0 * L.col_bytes, (int)(M - c0 < 32 ? M - c0 : 32),
+                                         dp + (size_t)c0 * (d.nb[1] / 4), d.nb[1] / 4, M <= 32, w_const);
                 if (rc) return rc;
             }
         return B200_OK;

@@ -113,12 +113,14 @@ def test_flash_attn_vs_oracle(b200, ctx, tk, D, H, Hkv, n_q, n_kv):
     assert nmse(got, exact) <= nmse(want, exact) * 1.5 + 1e-11
 
 
+@pytest.mark.parametrize("n_kv,slots", [(2048, 8), (8192, 32)])
 @pytest.mark.parametrize("tk", [R.F16, R.Q8_0])
-def test_flash_attn_multislot_mask_and_tile_skipping(b200, ctx, tk):
-    """n_parallel slots share one cache: each query sees only its slot; fully masked 32-cell tiles are skipped"""
+def test_flash_attn_multislot_mask_and_tile_skipping(b200, ctx, tk, n_kv, slots):
+    """n_parallel slots share one cache: each query sees only its slot; fully masked 32-cell tiles are never requested: the live-tile
+    map of the mask (built once per graph) hands every KV split an equal share of the LIVE tiles of its column tile"""
     rng = np.random.default_rng(3)
-    D, H, Hkv, n_q, n_kv = 128, 32, 8, 32, 2048
-    q, kb, vb, mask = make_case(rng, D, H, Hkv, n_q, n_kv, tk, slots=8)
+    D, H, Hkv, n_q = 128, 32, 8, 32
+    q, kb, vb, mask = make_case(rng, D, H, Hkv, n_q, n_kv, tk, slots=slots)
     scale = 1.0 / np.sqrt(D)
     got = run_fa(b200, ctx, q, kb, vb, mask, D, n_kv, Hkv, tk, scale)
     want = R.orc_flash_attn(q, kb, vb, mask, D, n_kv, Hkv, tk, tk, scale)

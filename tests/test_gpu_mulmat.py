@@ -153,6 +153,43 @@ def test_batched_columns_prequantised_path(b200, ctx, t):
     assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("M", [9, 16, 17, 32])
+@pytest.mark.parametrize("N,K", [(16, 256), (48, 512), (1024, 4096), (4096, 4096), (304, 14336), (64, 28672), (160, 2304)])
+@pytest.mark.parametrize("t", R.QUANT_TYPES)
+def test_small_batch_mma_kernel_vs_oracle(b200, ctx, t, N, K, M):
+    """continuous-batching decode (9..32 token columns): gemv_mma.cu (mma.sync s8 over the streamed GGUF rows, split-K ranges of
+    2048 with a fixed-order reduction) against the oracle; every row of the first / last tile and a random sample"""
+    if M not in (17, 32) and (N, K) not in [(48, 512), (1024, 4096)]:
+        pytest.skip("column-count sweep on a subset of shapes")
+    rng = np.random.default_rng(N + K + t + M)
+    W = rand_quant_rows(t, N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    l0 = ctx.launches()
+    got = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    assert ctx.launches() - l0 == (3 if K > 2048 else 2), "expected quantise + gemv_mma (+ split-K reduce)"
+    rows = np.unique(np.concatenate([np.arange(min(N, 16)), rng.integers(0, N, 16), np.arange(N - 16, N)]))
+    rb = R.row_size(t, K)
+    Wsub = W.reshape(N, rb)[rows].reshape(-1)
+    want = R.orc_mul_mat(t, Wsub, x, len(rows), K)
+    scale = max(np.abs(want).max(), 1e-6)
+    assert np.abs(got[:, rows] - want).max() <= 3e-6 * scale
+    assert np.isfinite(got).all()
+    again = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    assert np.array_equal(got, again), "split-K reduction must be deterministic"
+
+
+@pytest.mark.parametrize("t", [R.Q4_0, R.Q8_0])
+def test_q4_0_q8_0_prefill_in_column_chunks_of_32(b200, ctx, t):
+    """the legacy block formats have no tcgen05 path: a prompt batch goes through gemv_mma in chunks of 32 columns"""
+    rng = np.random.default_rng(5 + t)
+    N, K, M = 128, 2048, 77
+    W = rand_quant_rows(t, N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    got = gpu_mul_mat(b200, ctx, t, W, x, N, K)
+    want = R.orc_mul_mat(t, W, x, N, K)
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("t", [R.Q4_K, R.Q6_K, R.Q8_0])
 @pytest.mark.parametrize("b_ne1", [1, 2])
 def test_mul_mat_id_device_side_routing(b200, ctx, t, b_ne1):
