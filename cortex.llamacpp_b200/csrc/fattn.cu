@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // stage one 32 x D tile of K or V into shared memory as f16 [32][D+8]; quantised types are converted on load.
 // RAWINT: keep the integer quants (K path: scales go to `sc`), else dequantise d*q (V path).
 template <int D, int T, bool RAWINT>
-__device__ __forceinline__ void stage_tile(__half *s, float *sc, const char *g, uint64_t nb1, int kv0, int lane) {
+__device__ __forceinline__ void stage_tile(__half *s, float *sc, const char *g, uint64_t nb1, int kv0, int lane, const uint8_t *rawbuf, float sc_mul) {
     constexpr int LD = D + 8;
     if (T == KV_F16) {
         constexpr int CH = D / 8;                      // 16-byte chunks per row
@@ -74,35 +74,64 @@ __device__ __forceinline__ void stage_tile(__half *s, float *sc, const char *g, 
             cp_async16(s + r * LD + cc * 8, g + (uint64_t)(kv0 + r) * nb1 + cc * 16);
         }
     } else {
-        // one lane per kv row: rows are 8-byte aligned (q8_0: 34*D/32, q4_0: 18*D/32 bytes with D = 128)
-        constexpr int RB = (T == KV_Q8_0 ? 34 : 18) * (D / 32);
-        const uint2 *src = (const uint2 *)(g + (uint64_t)(kv0 + lane) * nb1);
-        uint2 raw[RB / 8];
+        // quantised rows (q8_0: 34*D/32, q4_0: 18*D/32 bytes, 8-byte aligned) were fetched into `raw` by fetch_raw() with coalesced
+        // 8-byte cp.async; one lane converts one row.  The quants become exact f16 integers without a float conversion: 0x6400 | u is
+        // the half 1024 + u, so (byte ^ 0x80) -> 1024 + 128 + q and one HSUB2 by 1152 (q8_0), or nibble -> 1024 + n and HSUB2 by
+        // 1032 (q4_0: n - 8); 8 halves leave in one 16-byte store
+        static_assert(RAWINT, "quantised tiles are staged as raw integers; their scales go to `sc`");
+        constexpr int BB = T == KV_Q8_0 ? 34 : 18;
+        constexpr int RB = BB * (D / 32);
+        const uint2 *src = (const uint2 *)(rawbuf + lane * RB);
+        uint32_t raw[RB / 4 + 1];
 #pragma unroll
-        for (int i = 0; i < RB / 8; i++) raw[i] = src[i];
-        const uint8_t *rb = (const uint8_t *)raw;
+        for (int i = 0; i < RB / 8; i++) { const uint2 v = src[i]; raw[2 * i] = v.x; raw[2 * i + 1] = v.y; }
+        raw[RB / 4] = 0;
         __half *row = s + lane * LD;
+        auto word_at = [&](int byte_off) -> uint32_t {      // 32 bits at a 2-byte aligned offset of the row (constant after unrolling)
+            return (byte_off & 2) ? __funnelshift_r(raw[byte_off >> 2], raw[(byte_off >> 2) + 1], 16) : raw[byte_off >> 2];
+        };
+        auto h2 = [](uint32_t bytes, uint32_t sel, uint32_t bias) -> uint32_t {
+            const uint32_t v = __byte_perm(bytes, 0x64646464u, sel);
+            const __half2 r = __hsub2(*(const __half2 *)&v, *(const __half2 *)&bias);
+            return *(const uint32_t *)&r;
+        };
 #pragma unroll
         for (int b = 0; b < D / 32; b++) {
-            const uint8_t *blk = rb + b * (T == KV_Q8_0 ? 34 : 18);
-            const float d = __half2float(*(const __half *)blk);
-            if (RAWINT) sc[lane * (D / 32) + b] = d;
-            const float m = RAWINT ? 1.0f : d;
+            const uint32_t hd = word_at(b * BB);
+            sc[lane * (D / 32) + b] = __half2float(__ushort_as_half((unsigned short)(hd & 0xffffu))) * sc_mul;
             if (T == KV_Q8_0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float a = (float)(int8_t)blk[2 + j], c = (float)(int8_t)blk[3 + j];
-                    *(uint32_t *)(row + b * 32 + j) = pack_h2(__fmul_rn(a, m), __fmul_rn(c, m));
+                for (int j = 0; j < 32; j += 8) {
+                    const uint32_t w0 = word_at(b * BB + 2 + j) ^ 0x80808080u, w1 = word_at(b * BB + 6 + j) ^ 0x80808080u;
+                    *(uint4 *)(row + b * 32 + j) = make_uint4(h2(w0, 0x4140, 0x64806480u), h2(w0, 0x4342, 0x64806480u), h2(w1, 0x4140, 0x64806480u), h2(w1, 0x4342, 0x64806480u));
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const int q0 = blk[2 + j], q1 = blk[3 + j];
-                    *(uint32_t *)(row + b * 32 + j)      = pack_h2(__fmul_rn((float)((q0 & 15) - 8), m), __fmul_rn((float)((q1 & 15) - 8), m));
-                    *(uint32_t *)(row + b * 32 + 16 + j) = pack_h2(__fmul_rn((float)((q0 >> 4) - 8), m), __fmul_rn((float)((q1 >> 4) - 8), m));
+                for (int j = 0; j < 16; j += 8) {
+                    const uint32_t w0 = word_at(b * BB + 2 + j), w1 = word_at(b * BB + 6 + j);
+                    const uint32_t l0 = w0 & 0x0f0f0f0fu, l1 = w1 & 0x0f0f0f0fu, u0 = (w0 >> 4) & 0x0f0f0f0fu, u1 = (w1 >> 4) & 0x0f0f0f0fu;
+                    *(uint4 *)(row + b * 32 + j)      = make_uint4(h2(l0, 0x4140, 0x64086408u), h2(l0, 0x4342, 0x64086408u), h2(l1, 0x4140, 0x64086408u), h2(l1, 0x4342, 0x64086408u));
+                    *(uint4 *)(row + b * 32 + 16 + j) = make_uint4(h2(u0, 0x4140, 0x64086408u), h2(u0, 0x4342, 0x64086408u), h2(u1, 0x4140, 0x64086408u), h2(u1, 0x4342, 0x64086408u));
                 }
             }
         }
+    }
+}
+
+// quantised K/V: the 32 raw rows of a tile -> shared memory, consecutive lanes on consecutive 8-byte pieces of a row (a lane-per-row
+// global read touches 32 different lines per instruction and serialises in the L1 tag stage: 47 us per bs32 layer)
+template <int D, int T>
+__device__ __forceinline__ void fetch_raw(uint8_t *rawbuf, const char *g, uint64_t nb1, int kv0, int lane) {
+    constexpr int RB = (T == KV_Q8_0 ? 34 : 18) * (D / 32);
+    constexpr int PC = RB / 8;                  // 8-byte pieces per row; BK * PC / 32 = PC pieces per lane
+    int r = lane / PC, cc = lane % PC;
+    const uint32_t sbase = smem_u32(rawbuf);
+    const char *gb = g + (uint64_t)kv0 * nb1;
+#pragma unroll
+    for (int i = 0; i < PC; i++) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (uint32_t)(r * RB + cc * 8)), "l"(gb + (uint64_t)r * nb1 + cc * 8));
+        cc += 32 % PC; r += 32 / PC;
+        if (cc >= PC) { cc -= PC; r++; }
     }
 }
 
@@ -117,11 +146,13 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
     // per-warp staging: K tile, V tile, K scales
-    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * NB * 4;
+    constexpr int RAWK = KQ ? BK * (KT == KV_Q8_0 ? 34 : 18) * NB : 0, RAWV = VT != KV_F16 ? BK * (VT == KV_Q8_0 ? 34 : 18) * NB : 0;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * NB * 4 + RAWK + RAWV;
     __half *sK = (__half *)(fsm + warp * WARP_BYTES);
     __half *sV = sK + BK * LD;
     float *sKs = (float *)(sV + BK * LD);
     float *sVs = sKs + BK * NB;
+    uint8_t *rawK = (uint8_t *)(sVs + BK * NB), *rawV = rawK + RAWK;
     constexpr bool VQ = VT != KV_F16;
 
     const int split = blockIdx.x;
@@ -212,6 +243,13 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
     const int *mp = p.map ? p.map + (size_t)ct * p.map_stride : nullptr;
     int it_begin = kv_begin / BK, it_end = kv_end / BK;
     if (mp) { const int cnt = mp[0]; it_begin = (int)((long long)split * cnt / p.n_splits); it_end = (int)((long long)(split + 1) * cnt / p.n_splits); }
+    // quantised caches with a live-tile map: the raw rows of the NEXT tile are in flight (cp.async) while this one is multiplied
+    constexpr bool PREFETCH = KQ && VQ;
+    if (PREFETCH && mp && it_begin + warp < it_end) {
+        const int kvf = mp[1 + it_begin + warp] * BK;
+        fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kvf, lane);
+        fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kvf, lane);
+    }
     for (int it = it_begin + warp; it < it_end; it += NWARP) {
         const int kv0 = (mp ? mp[1 + it] : it) * BK;
         // ---- skip tiles that are fully masked for every query column of this CTA -------------------------
@@ -227,10 +265,20 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
             if (!__any_sync(0xffffffffu, any)) continue;
         }
         __syncwarp();
-        stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane);
-        stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane);
+        if (!(PREFETCH && mp)) {
+            if (KQ) fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kv0, lane);
+            if (VQ) fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kv0, lane);
+        }
+        if (KQ || VQ) { cp_async_wait_all(); __syncwarp(); }
+        stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane, rawK, 1.0f);
+        stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane, rawV, PV_SCALE);      // exact power of two, see below
         if (KT == KV_F16 || VT == KV_F16) cp_async_wait_all();
         __syncwarp();
+        if (PREFETCH && mp && it + NWARP < it_end) {
+            const int kvn = mp[1 + it + NWARP] * BK;
+            fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kvn, lane);
+            fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kvn, lane);
+        }
 
         // ---- S = Q K^T  (16 x 32) ---------------------------------------------------------------------
         float s[4][4];
@@ -293,8 +341,10 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
                 s[nt][2 * i] = p0; s[nt][2 * i + 1] = p1;
                 lrow[i] += p0 + p1;
             }
+        if (__any_sync(0xffffffffu, corr[0] != 1.0f || corr[1] != 1.0f)) {       // multiplying by 1 is the identity: skipping it changes nothing
 #pragma unroll
-        for (int t = 0; t < NDT; t++) { o[t][0] *= corr[0]; o[t][1] *= corr[0]; o[t][2] *= corr[1]; o[t][3] *= corr[1]; }
+            for (int t = 0; t < NDT; t++) { o[t][0] *= corr[0]; o[t][1] *= corr[0]; o[t][2] *= corr[1]; o[t][3] *= corr[1]; }
+        }
         // ---- O += P V : P as f16 hi+lo (22 bits); quantised V stays integer, its scale is folded into P per dim block ----
 #pragma unroll
         for (int kk = 0; kk < 2; kk++) {
@@ -313,8 +363,10 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
                 }
                 // exact power-of-two pre-scale: keeps the f16 hi/lo pair out of the f16 subnormal range for small
                 // softmax weights (w ~ 1e-4 would otherwise lose its low half); undone when the accumulators are stored
+                if (!VQ) {
 #pragma unroll
-                for (int e = 0; e < 8; e++) w[e] *= PV_SCALE;
+                    for (int e = 0; e < 8; e++) w[e] *= PV_SCALE;         // (quantised V: folded into the staged block scales)
+                }
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
@@ -791,7 +843,8 @@ int kv_kind(int type) { return type == B200_TYPE_F16 ? KV_F16 : type == B200_TYP
 template <int D, int KT, int VT>
 int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     constexpr int LD = D + 8;
-    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4;
+    constexpr int RAWK = KT != KV_F16 ? BK * (KT == KV_Q8_0 ? 34 : 18) * (D / 32) : 0, RAWV = VT != KV_F16 ? BK * (VT == KV_Q8_0 ? 34 : 18) * (D / 32) : 0;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4 + RAWK + RAWV;
     constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D) * 4;
     constexpr int SMEM = NWARP * WARP_BYTES > COMBINE_BYTES ? NWARP * WARP_BYTES : COMBINE_BYTES;
     auto kern = b200_fattn_kernel<D, KT, VT>;
@@ -972,15 +1025,17 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     const int unit = NWARP * BK;
     const int max_splits = (p.n_kv + unit - 1) / unit;
     int ns = (3 * ctx->sm_count + n_tiles - 1) / n_tiles;
+    if (p.map) ns = (2 * ctx->sm_count) / n_tiles;      // live tiles are shared evenly: one full wave of the 2 resident CTAs per SM (the per-warp
+                                                        // set-up -- Q fragments, merge -- costs about as much as one KV tile)
     if (ns > max_splits) ns = max_splits;
     if (ns < 1) ns = 1;
     p.kv_per_split = ((p.n_kv + ns - 1) / ns + unit - 1) / unit * unit;
     ns = (p.n_kv + p.kv_per_split - 1) / p.kv_per_split;
     p.n_splits = ns;
     if (ns > 1) {
-        // sized by its upper bound (n_tiles * ns <= 3 * sm_count + n_tiles) so that a growing n_kv never reallocates it under
+        // sized by its upper bound (n_tiles * ns <= 4 * sm_count + n_tiles) so that a growing n_kv never reallocates it under
         // captured graphs
-        p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)(3 * ctx->sm_count + n_tiles) * 16 * (D + 2) * 4);
+        p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)(4 * ctx->sm_count + n_tiles) * 16 * (D + 2) * 4);
         if (!p.part) return B200_ERR_ALLOC;
         // merging the splits in the last-arriving CTA instead of a second kernel was measured SLOWER on B200 (471 vs 523 tok/s on
         // Llama-3-8B bs1: a PDL kernel boundary costs ~1 us, the serialised fence + atomic + 128-thread merge costs more): off
