@@ -23,7 +23,7 @@ BLOCK = {F32: (1, 4), F16: (1, 2), BF16: (1, 2), I32: (1, 4), Q4_0: (32, 18), Q8
 
 (OP_NONE, OP_MUL_MAT, OP_MUL_MAT_ID, OP_FLASH_ATTN_EXT, OP_RMS_NORM, OP_ROPE, OP_CPY, OP_CONT, OP_ADD, OP_SUB, OP_MUL,
  OP_DIV, OP_SILU, OP_GELU, OP_RELU, OP_TANH, OP_SIGMOID, OP_GET_ROWS, OP_SOFT_MAX, OP_ARGSORT, OP_SUM_ROWS, OP_SCALE,
- OP_SWIGLU_FUSED, OP_RMS_NORM_MUL, OP_ALLREDUCE, OP_COUNT) = range(26)
+ OP_SWIGLU_FUSED, OP_RMS_NORM_MUL, OP_ALLREDUCE, OP_ARGMAX, OP_COUNT) = range(27)
 
 TENSOR_FLAG_WEIGHT = 1
 
@@ -87,6 +87,8 @@ def lib():
         "b200_event_synchronize": (C.c_int, [vp]),
         "b200_event_elapsed_ms": (C.c_float, [vp, vp]),
         "b200_supports_op": (C.c_int, [C.c_int, C.POINTER(Op)]),
+        "b200_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "b200_upload_slice": (C.c_int, [vp, vp, vp, C.c_size_t, i64, i64, C.c_size_t, C.c_size_t]),
         "b200_graph_compute": (C.c_int, [vp, C.POINTER(Op), C.c_int]),
         "b200_op_compute": (C.c_int, [vp, C.POINTER(Op)]),
         "b200_kernel_launches": (i64, [vp]),

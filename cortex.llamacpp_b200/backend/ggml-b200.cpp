@@ -89,6 +89,7 @@ bool translate(const ggml_tensor *node, b200_op &o) {
         case GGML_OP_SOFT_MAX: op = B200_OP_SOFT_MAX; nsrc = 2; break;
         case GGML_OP_ARGSORT: op = B200_OP_ARGSORT; nsrc = 1; break;
         case GGML_OP_SUM_ROWS: op = B200_OP_SUM_ROWS; nsrc = 1; break;
+        case GGML_OP_ARGMAX: op = B200_OP_ARGMAX; nsrc = 1; break;
         case GGML_OP_SCALE: op = B200_OP_SCALE; nsrc = 1; break;
         case GGML_OP_UNARY:
             nsrc = 1;
@@ -134,8 +135,24 @@ enum ggml_status buffer_init_tensor(ggml_backend_buffer_t buffer, ggml_tensor *t
 void buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor *tensor, uint8_t value, size_t offset, size_t size) {
     b200_memset(((buffer_ctx *)buffer->context)->device, (char *)tensor->data + offset, value, size);
 }
+// per-device context used by the buffer interface for the pipelined weight upload (buffers are not tied to a backend stream)
+b200_ctx *upload_ctx(int device) {
+    static std::mutex mu;
+    static b200_ctx *ctxs[16] = {nullptr};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 16) return nullptr;
+    if (!ctxs[device]) ctxs[device] = b200_ctx_create(device);
+    return ctxs[device];
+}
 void buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor *tensor, const void *data, size_t offset, size_t size) {
-    if (b200_memcpy_h2d(((buffer_ctx *)buffer->context)->device, (char *)tensor->data + offset, data, size) != B200_OK)
+    const int device = ((buffer_ctx *)buffer->context)->device;
+    // model load: `data` points into the mmap'd GGUF; big tensors go through the pinned-chunk pipeline (upload.cu) instead of one
+    // synchronous pageable cudaMemcpy (llama-model-loader.cpp:1019-1060 does the same with 4 x 1 MiB staging buffers)
+    if (size >= ((size_t)8 << 20)) {
+        b200_ctx *uc = upload_ctx(device);
+        if (uc && b200_upload(uc, (char *)tensor->data + offset, data, size) == B200_OK) return;
+    }
+    if (b200_memcpy_h2d(device, (char *)tensor->data + offset, data, size) != B200_OK)
         GGML_ABORT("ggml-b200: set_tensor failed: %s", b200_last_error());
 }
 void buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor *tensor, void *data, size_t offset, size_t size) {

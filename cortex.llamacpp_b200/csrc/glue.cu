@@ -271,6 +271,18 @@ __global__ void __launch_bounds__(256) b200_cpy_q_f32_kernel(b200_tensor s, b200
     *(float *)((char *)d.data + b.i0 * d.nb[0] + b.i1 * d.nb[1] + b.i2 * d.nb[2] + b.i3 * d.nb[3]) = dequant_elem(s.type, row, a.i0);
 }
 
+// same-type copy of quantised blocks between strided views (KV defrag: llama-context.cpp build_kv_self_defrag moves cache rows with
+// ggml_cpy(view_src, view_dst)); a block is the element, 2-byte granules (q4_0 / q8_0 blocks are only 2-byte aligned)
+__global__ void __launch_bounds__(256) b200_cpy_qblocks_kernel(b200_tensor s, b200_tensor d, int64_t nblocks, int be, int bb) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    int64_t sne[4] = {s.ne[0] / be, s.ne[1], s.ne[2], s.ne[3]}, dne[4] = {d.ne[0] / be, d.ne[1], d.ne[2], d.ne[3]};
+    const Idx4 a = unravel(i, sne), b = unravel(i, dne);
+    const unsigned short *sp = (const unsigned short *)((const char *)s.data + a.i0 * s.nb[0] + a.i1 * s.nb[1] + a.i2 * s.nb[2] + a.i3 * s.nb[3]);
+    unsigned short *dp = (unsigned short *)((char *)d.data + b.i0 * d.nb[0] + b.i1 * d.nb[1] + b.i2 * d.nb[2] + b.i3 * d.nb[3]);
+    for (int k = 0; k < bb / 2; k++) dp[k] = sp[k];
+}
+
 // get_rows: dst[:, i10, i11, i12] = src0[:, idx[i10,i11,i12], i11, i12]
 __global__ void __launch_bounds__(256) b200_get_rows_kernel(b200_tensor s, b200_tensor idx, b200_tensor d, int64_t total) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,6 +332,26 @@ __global__ void __launch_bounds__(256) b200_soft_max_kernel(b200_tensor x, b200_
 }
 
 // ---------------------------------------------------------------------------------------------- argsort / sum_rows
+// ARGMAX (ggml_vec_argmax_f32, ggml-cpu.c:2393-2401: `max = MAX(max, x[i]); if (max == x[i]) idx = i;` -> the LAST index holding the
+// maximum).  Greedy sampling on the device: the host reads 4 bytes per sequence instead of the full-vocabulary logits row.
+__global__ void __launch_bounds__(1024) b200_argmax_kernel(b200_tensor a, b200_tensor d) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    const int row = blockIdx.x, n = (int)a.ne[0];
+    const float *x = (const float *)((const char *)a.data + (size_t)row * a.nb[1]);
+    float best = -INFINITY; int bi = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i]; if (v >= best) { best = v; bi = i; } }
+    auto merge = [](float &v, int &i, float ov, int oi) { if (ov > v || (ov == v && oi > i)) { v = ov; i = oi; } };
+    for (int o = 16; o > 0; o >>= 1) merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = sv[threadIdx.x]; bi = si[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (threadIdx.x == 0) *(int32_t *)((char *)d.data + (size_t)row * d.nb[0]) = bi;
+    }
+}
+
 // bitonic sort of one row (ncols <= 1024) in shared memory; ties keep the lower index first like a stable CPU sort
 __global__ void b200_argsort_kernel(b200_tensor x, b200_tensor y, int ncols_pad, int desc) {
     extern __shared__ int sidx[];
@@ -412,7 +444,7 @@ bool cpy_pair_ok(int st, int dt) {
     if (st == B200_TYPE_F16) return dt == B200_TYPE_F16 || dt == B200_TYPE_F32;
     if (st == B200_TYPE_BF16) return dt == B200_TYPE_F32;
     if (st == B200_TYPE_I32) return dt == B200_TYPE_I32;
-    if (b200_type_is_quant(st)) return dt == B200_TYPE_F32;
+    if (b200_type_is_quant(st)) return dt == B200_TYPE_F32 || dt == st;
     return false;
 }
 
@@ -430,6 +462,10 @@ int launch_cpy(b200_ctx *ctx, const b200_tensor &s, const b200_tensor &d) {
     else if (st == B200_TYPE_I32 && dt == B200_TYPE_I32) CPY_CASE(int32_t, int32_t);
     else if (st == B200_TYPE_F32 && dt == B200_TYPE_Q8_0) b200_cpy_f32_q_kernel<B200_TYPE_Q8_0><<<nblk(total / 32, 128), 128, 0, ctx->stream>>>(s, d, total / 32);
     else if (st == B200_TYPE_F32 && dt == B200_TYPE_Q4_0) b200_cpy_f32_q_kernel<B200_TYPE_Q4_0><<<nblk(total / 32, 128), 128, 0, ctx->stream>>>(s, d, total / 32);
+    else if (b200_type_is_quant(st) && dt == st) {
+        const int be = b200_type_block_elems(st), bb = b200_type_block_bytes(st);
+        b200_cpy_qblocks_kernel<<<nblk(total / be, 256), 256, 0, ctx->stream>>>(s, d, total / be, be, bb);
+    }
     else if (b200_type_is_quant(st) && dt == B200_TYPE_F32) b200_cpy_q_f32_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(s, d, total);
     else { b200_set_error("cpy %d -> %d", st, dt); return B200_ERR_UNSUPPORTED; }
 #undef CPY_CASE
@@ -587,6 +623,9 @@ bool supports_glue(const b200_op *op) {
         case B200_OP_CPY: case B200_OP_CONT: {
             if (!cpy_pair_ok(a.type, d.type)) return false;
             if (tensor_nelements(a) != tensor_nelements(d)) return false;
+            if (b200_type_is_quant(a.type) && a.type == d.type)
+                return a.ne[0] % b200_type_block_elems(a.type) == 0 && d.ne[0] % b200_type_block_elems(a.type) == 0 &&
+                       a.nb[0] == (uint64_t)b200_type_block_bytes(a.type) && d.nb[0] == a.nb[0] && a.data != d.data;
             if (d.type == B200_TYPE_Q8_0 || d.type == B200_TYPE_Q4_0)
                 return a.nb[0] == 4 && a.ne[0] % 32 == 0 && d.ne[0] % 32 == 0 && !((uintptr_t)a.data & 15) && !(a.nb[1] & 15) &&
                        !(a.nb[2] & 15) && !(a.nb[3] & 15);
@@ -602,6 +641,7 @@ bool supports_glue(const b200_op *op) {
             return true;
         case B200_OP_ARGSORT: return rows_f32_ok(a) && d.type == B200_TYPE_I32 && a.ne[0] <= 1024 && tensor_is_contiguous(a);
         case B200_OP_SUM_ROWS: return rows_f32_ok(a) && d.type == B200_TYPE_F32;
+        case B200_OP_ARGMAX: return rows_f32_ok(a) && d.type == B200_TYPE_I32 && d.nb[0] == 4 && a.ne[2] == 1 && a.ne[3] == 1 && a.ne[0] < (1ll << 31);
         default: return false;
     }
 }
@@ -678,6 +718,14 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
             int pad = 1;
             while (pad < a.ne[0]) pad <<= 1;
             b200_argsort_kernel<<<(unsigned)rows, pad, pad * sizeof(int), ctx->stream>>>(a, d, pad, op->params[0]);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return B200_OK;
+        }
+        case B200_OP_ARGMAX: {
+            const int64_t rows = a.ne[1];
+            if (rows == 0) return B200_OK;
+            b200_argmax_kernel<<<(unsigned)rows, 1024, 0, ctx->stream>>>(a, d);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;

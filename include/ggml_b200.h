@@ -66,6 +66,7 @@ typedef enum b200_op_id {
     B200_OP_RMS_NORM_MUL,    /* dst = rms_norm(src0) * src1  (fusion of RMS_NORM+MUL)                                       */
     B200_OP_ALLREDUCE,       /* dst = sum over tensor-parallel ranks of src0 (+ src1 residual, optional); f32, contiguous:   */
                              /* the exchange that replaces ggml_cuda_op_mul_mat's row gather (ggml-cuda.cu:1363-1671)        */
+    B200_OP_ARGMAX,          /* src0 f32 [n, rows] -> i32 [rows]: index of the LAST maximum of each row      (argmax.cu; ggml-cpu.c:2393) */
     B200_OP_COUNT
 } b200_op_id;
 
@@ -117,6 +118,13 @@ B200_API int         b200_memcpy_d2d(int dst_device, void *dst, int src_device, 
 B200_API int         b200_memcpy_h2d_async(b200_ctx *ctx, void *dst, const void *src, size_t size);
 B200_API int         b200_memcpy_d2h_async(b200_ctx *ctx, void *dst, const void *src, size_t size);
 B200_API int         b200_memcpy_d2d_async(b200_ctx *ctx, void *dst, int src_device, const void *src, size_t size);
+/* GGUF -> device load path (replaces the staging loop of llama_model_loader::load_all_data, llama-model-loader.cpp:895-1071): `src` is
+ * pageable (mmap'd) host memory; the bytes are gathered into a ring of pinned chunks by a few host threads while the copy engine drains
+ * the previous chunks.  b200_upload_slice packs rows [row0, row0 + n_rows) x bytes [col_off, col_off + col_bytes) of a row-major host
+ * matrix (rows `src_row_stride` bytes apart) into a dense device buffer: the shard of a row-split / K-split weight, read once from the file. */
+B200_API int         b200_upload(b200_ctx *ctx, void *dst, const void *src, size_t size);
+B200_API int         b200_upload_slice(b200_ctx *ctx, void *dst, const void *src, size_t src_row_stride, int64_t row0, int64_t n_rows,
+                                       size_t col_off, size_t col_bytes);
 B200_API size_t      b200_alloc_size(int32_t type, const int64_t ne[4], size_t nbytes); /* padded size a tensor needs (get_alloc_size) */
 
 /* ---- events (ggml_backend_device_i::event_*, ggml_backend_i::event_record/wait) -------------- */

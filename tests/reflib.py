@@ -258,6 +258,8 @@ class RefGraph:
             "ggml_flash_attn_ext": [vp, vp, vp, vp, vp, f32, f32, f32],
             "ggml_cpy": [vp, vp, vp], "ggml_cont": [vp, vp], "ggml_permute": [vp, vp, i32, i32, i32, i32],
             "ggml_get_rows": [vp, vp, vp], "ggml_mul_mat": [vp, vp, vp], "ggml_new_graph": [vp],
+            "ggml_cast": [vp, vp, i32], "ggml_rope_ext_inplace": [vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, f32, f32],
+            "ggml_argmax": [vp, vp],
         }.items():
             fn = getattr(b, name)
             fn.restype = vp
@@ -348,3 +350,33 @@ def ref_flash_attn(q, k_bytes, v_bytes, mask_f16, D, n_kv, Hkv, type_k, type_v, 
     y = g.run(out, np.float32, (n_q, H, D))
     g.close()
     return y
+
+
+def ref_argmax_row(x):
+    """ggml_vec_argmax_f32 (ggml-cpu.c:2393-2401) restated: running maximum, index updated whenever the element equals it"""
+    x = np.asarray(x, np.float32)
+    m = np.maximum.accumulate(x)
+    hit = np.nonzero(m == x)[0]
+    return int(hit[-1]) if hit.size else 0
+
+
+def ref_k_shift(kbytes, ktype, D, Hkv, n_cells, shift, n_rot, mode, freq_base, freq_scale=1.0, n_ctx_orig=8192):
+    """llama_context::build_rope_shift (llama-context.cpp:464-514) run on the reference CPU backend: the cached K of one layer
+    [D, Hkv, n_cells] re-rotated by the per-cell `shift`; quantised K goes through ggml_cast -> f32, rope in place, ggml_cpy back"""
+    g = RefGraph()
+    cur = g.tensor(ktype, [D, Hkv, n_cells], np.asarray(kbytes, np.uint8))
+    sh = g.tensor(I32, [n_cells], np.asarray(shift, np.int32))
+    if ktype in (Q8_0, Q4_0):
+        tmp = g.b.ggml_cast(g.ctx, cur, F32)
+        tmp = g.b.ggml_rope_ext_inplace(g.ctx, tmp, sh, None, n_rot, mode, n_ctx_orig, freq_base, freq_scale, 0.0, 1.0, 32.0, 1.0)
+        out = g.b.ggml_cpy(g.ctx, tmp, cur)
+    else:
+        out = g.b.ggml_rope_ext_inplace(g.ctx, cur, sh, None, n_rot, mode, n_ctx_orig, freq_base, freq_scale, 0.0, 1.0, 32.0, 1.0)
+    gr = g.b.ggml_new_graph(g.ctx)
+    g.b.ggml_build_forward_expand(gr, out)
+    assert g.c.ggml_graph_compute_with_ctx(g.ctx, gr, 4) == 0
+    n = g.b.ggml_nbytes(cur)
+    buf = np.zeros(n, np.uint8)
+    C.memmove(_ptr(buf), g.b.ggml_get_data(cur), n)
+    g.close()
+    return buf

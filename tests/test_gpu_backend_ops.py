@@ -17,7 +17,7 @@ PLUGIN = os.path.join(ROOT, "cortex.llamacpp_b200", "libggml-b200.so")
 
 # op -> minimum number of cases that must have executed on the B200 backend (round-1 run: profiles/r1_test_backend_ops.txt)
 MIN_RAN = {"MUL_MAT": 240, "MUL_MAT_ID": 100, "FLASH_ATTN_EXT": 620, "RMS_NORM": 8, "ROPE": 144, "CPY": 48, "SOFT_MAX": 78,
-           "GET_ROWS": 30, "ADD": 24, "MUL": 24, "DIV": 24, "SILU": 2, "ARGSORT": 6, "SUM_ROWS": 1, "SCALE": 1, "CONT": 6}
+           "GET_ROWS": 30, "ADD": 24, "MUL": 24, "DIV": 24, "SILU": 2, "ARGSORT": 6, "SUM_ROWS": 1, "SCALE": 1, "CONT": 6, "ARGMAX": 6}
 ANSI = re.compile(r"\x1b\[[0-9;]*m")
 
 

@@ -167,3 +167,17 @@ def test_soft_max_argsort_sum_rows(b200, ctx):
     got = run(b200, ctx, b200.OP_SOFT_MAX, [1000, 3], b200.F32, [(big, b200.F32, [1000, 3]), (m, b200.F16, [1000, 3])], [0.5, 0.0]).view(np.float32).reshape(3, 1000)
     want = R.orc_soft_max(big, m, 0.5)
     assert np.abs(got - want).max() <= 1e-6
+
+
+def test_argmax_last_maximum_like_the_cpu(b200, ctx):
+    """greedy sampling on the device: ggml_vec_argmax_f32 keeps the LAST index that holds the maximum (ggml-cpu.c:2393-2401)"""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((5, 128256)).astype(np.float32)          # full Llama-3 vocabulary rows
+    x[1, 7] = x[1, 100000] = 9.0                                     # tie: the later index wins
+    x[2, :] = -np.inf                                                # every element equals the running maximum: last index
+    x[3, 128255] = 11.0
+    x[4, 0] = 12.0
+    got = run(b200, ctx, b200.OP_ARGMAX, [5], b200.I32, [(x, b200.F32, [128256, 5])]).view(np.int32).reshape(5)
+    want = np.array([R.ref_argmax_row(r) for r in x], np.int32)
+    assert np.array_equal(got, want), (got, want)
+    assert got[1] == 100000 and got[2] == 128255 and got[3] == 128255 and got[4] == 0

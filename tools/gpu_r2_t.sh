@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -q -m gpu -x 2>&1 | tail -25 > gpurun_out/r2t_tests.log
+cat gpurun_out/r2t_tests.log
