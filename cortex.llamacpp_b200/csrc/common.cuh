@@ -194,14 +194,24 @@ int launch_quantize_act(b200_ctx *ctx, int q8k, const float *x, size_t x_col_str
                         uint8_t *scratch);
 // decode GEMV over pre-quantised activations (gemv.cu)
 // cpu-exact matmul over pre-quantised activations (exact.cu)
+struct ExactMoe {             // MUL_MAT_ID through the exact kernel: column = (token, slot) pair
+    const char *ids; uint64_t ids_nb0, ids_nb1; int n_used, b_ne1; size_t expert_stride, d_nb1, d_nb2;   // d_nb*: dst element strides
+};
 int launch_mul_mat_exact(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int64_t ncols,
-                         float *dst, size_t dst_stride);
+                         float *dst, size_t dst_stride, const ExactMoe *moe = nullptr);
 int launch_gemv(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const uint8_t *act,
                 int ncols, float *dst, size_t dst_col_stride_elems, bool w_const);
 // small-batch (<= 32 columns) weight-streaming matmul on mma.sync s8 (gemv_mma.cu)
 bool gemv_mma_supported(int type, int64_t N, int64_t K, int64_t M);
 int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int ncols,
                     float *dst, size_t dst_stride, bool stream_once, bool w_const, const float *residual = nullptr);
+// MUL_MAT_ID routing tables built on the device (mulmat.cu) for the grouped small-batch kernel
+struct MmGroupDesc {
+    const int32_t *off, *pairs;          // [E + 1] first pair of every expert; pair ids (token * n_used + slot) sorted by expert
+    int E, n_used, b_ne1, max_chunks;    // max_chunks: upper bound of sum_e ceil(count_e / 32) = grid.y
+    size_t expert_stride, d_nb1, d_nb2;  // bytes between expert matrices; dst element strides of slot and token
+};
+int launch_gemv_mma_grouped(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, const MmGroupDesc &g, float *dst);
 int launch_act_prologue(b200_ctx *ctx, int mode, const float *x, size_t x_stride_bytes, const float *x2, float eps, int64_t K, int ncols, int q8k,
                         uint8_t *scratch);
 

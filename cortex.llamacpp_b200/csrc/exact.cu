@@ -30,11 +30,19 @@ __device__ __forceinline__ void scale_min_k4(const uint8_t *s, int j, int &sc, i
 
 template <int TYPE>
 __global__ void __launch_bounds__(256) b200_mul_mat_exact_kernel(const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act,
-                                                                 ActLayout L, int64_t ncols, float *dst, size_t dst_stride) {
+                                                                 ActLayout L, int64_t ncols, float *dst, size_t dst_stride, ExactMoe moe) {
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int l = threadIdx.x & 7;
     if (gid >= N * ncols) return;                         // whole 8-thread groups leave together (256 % 8 == 0)
-    const int64_t row = gid % N, col = gid / N;
+    const int64_t row = gid % N;
+    int64_t col = gid / N;
+    size_t dst_off = (size_t)col * dst_stride;
+    if (moe.ids) {                                        // MUL_MAT_ID: column = (token, slot) pair, expert read on the device
+        const int64_t t = col / moe.n_used, sl = col % moe.n_used;
+        W += (size_t)(*(const int32_t *)(moe.ids + sl * moe.ids_nb0 + t * moe.ids_nb1)) * moe.expert_stride;
+        dst_off = (size_t)sl * moe.d_nb1 + (size_t)t * moe.d_nb2;
+        if (moe.b_ne1 == 1) col = t;
+    }
     const uint8_t *wrow = W + (size_t)row * rb;
     const uint8_t *acol = act + (size_t)col * L.col_bytes;
     const int8_t *aq = (const int8_t *)acol;
@@ -127,23 +135,25 @@ __global__ void __launch_bounds__(256) b200_mul_mat_exact_kernel(const uint8_t *
     } else if (TYPE == B200_TYPE_Q5_K) {
         v = __fadd_rn(v, acc_m);
     }
-    if (l == 0) dst[(size_t)col * dst_stride + row] = v;
+    if (l == 0) dst[dst_off + row] = v;
 }
 
 }  // namespace
 
 int launch_mul_mat_exact(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int64_t ncols,
-                         float *dst, size_t dst_stride) {
+                         float *dst, size_t dst_stride, const ExactMoe *moep) {
+    ExactMoe moe = {};
+    if (moep) moe = *moep;
     const ActLayout L = ActLayout::make(b200_act_mode_q8k(type), K);
     const int64_t groups = N * ncols;
     if (groups == 0) return B200_OK;
     const unsigned grid = (unsigned)((groups * 8 + 255) / 256);
     switch (type) {
-        case B200_TYPE_Q4_0: b200_mul_mat_exact_kernel<B200_TYPE_Q4_0><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride); break;
-        case B200_TYPE_Q8_0: b200_mul_mat_exact_kernel<B200_TYPE_Q8_0><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride); break;
-        case B200_TYPE_Q4_K: b200_mul_mat_exact_kernel<B200_TYPE_Q4_K><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride); break;
-        case B200_TYPE_Q5_K: b200_mul_mat_exact_kernel<B200_TYPE_Q5_K><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride); break;
-        case B200_TYPE_Q6_K: b200_mul_mat_exact_kernel<B200_TYPE_Q6_K><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride); break;
+        case B200_TYPE_Q4_0: b200_mul_mat_exact_kernel<B200_TYPE_Q4_0><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride, moe); break;
+        case B200_TYPE_Q8_0: b200_mul_mat_exact_kernel<B200_TYPE_Q8_0><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride, moe); break;
+        case B200_TYPE_Q4_K: b200_mul_mat_exact_kernel<B200_TYPE_Q4_K><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride, moe); break;
+        case B200_TYPE_Q5_K: b200_mul_mat_exact_kernel<B200_TYPE_Q5_K><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride, moe); break;
+        case B200_TYPE_Q6_K: b200_mul_mat_exact_kernel<B200_TYPE_Q6_K><<<grid, 256, 0, ctx->stream>>>(W, rb, N, K, act, L, ncols, dst, dst_stride, moe); break;
         default: b200_set_error("mul_mat exact: type %d", type); return B200_ERR_UNSUPPORTED;
     }
     ctx->launches++;

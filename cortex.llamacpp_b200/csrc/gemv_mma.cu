@@ -43,7 +43,23 @@ struct MmParams {
     int nstages; uint32_t stage_bytes, rstride, bbytes;      // rstride: bytes between rows inside a stage; bbytes: bytes per 256 weights
     uint32_t off_aq, off_ad, off_as, off_comb, off_ring;
     int use_pdl, stream_once, w_const;
+    // grouped (MUL_MAT_ID) mode: blockIdx.y = chunk of <= 32 (token, slot) pairs routed to one expert
+    const int32_t *g_off;                   // [E + 1] first pair of every expert in g_pairs (device, written by the grouping kernel)
+    const int32_t *g_pairs;                 // pair ids (token * n_used + slot) sorted by expert
+    int g_E, g_n_used, g_b_ne1;             // g_E == 0: dense mode
+    size_t g_expert_stride;                 // bytes between expert matrices
+    size_t g_d_nb1, g_d_nb2;                // dst element strides of slot and token
 };
+
+// grouped mode: which (expert, chunk) does blockIdx.y stand for?  cnt = pairs in this chunk (0: nothing to do)
+__device__ __forceinline__ void group_lookup(const MmParams &p, int y, int &e, int &first, int &cnt) {
+    cnt = 0; first = 0;
+    for (e = 0; e < p.g_E; e++) {
+        const int o0 = p.g_off[e], n = p.g_off[e + 1] - o0, nch = (n + MM_COLS - 1) / MM_COLS;
+        if (y < nch) { first = o0 + y * MM_COLS; cnt = min(MM_COLS, n - y * MM_COLS); return; }
+        y -= nch;
+    }
+}
 
 __device__ __forceinline__ void ldsm_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t saddr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
@@ -227,6 +243,34 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
     if (p.use_pdl) pdl_trigger();
     const int r = blockIdx.x % p.nranges, g = blockIdx.x / p.nranges;
     if (g >= p.ngroups) return;
+    // column maps: activation column (byte offset into p.act) and destination (element offset into p.dst) of every token column
+    __shared__ uint32_t s_colact[MM_COLS];
+    __shared__ long long s_coldst[MM_COLS];
+    __shared__ int s_grp[2];
+    int ncols = p.ncols;
+    const uint8_t *Wb = p.W;
+    float *partb = p.part;
+    if (p.g_E) {
+        if (p.use_pdl) pdl_wait();             // the routing tables come from the grouping kernel just before
+        if (threadIdx.x == 0) {
+            int e, first, cnt;
+            group_lookup(p, blockIdx.y, e, first, cnt);
+            s_grp[0] = cnt; s_grp[1] = e;
+            for (int c = 0; c < cnt; c++) {
+                const int pair = p.g_pairs[first + c], t = pair / p.g_n_used, sl = pair % p.g_n_used;
+                s_colact[c] = (uint32_t)((p.g_b_ne1 == 1 ? t : pair) * (long long)p.L.col_bytes);
+                s_coldst[c] = (long long)sl * (long long)p.g_d_nb1 + (long long)t * (long long)p.g_d_nb2;
+            }
+        }
+        __syncthreads();
+        ncols = s_grp[0];
+        if (ncols == 0) return;
+        Wb += (size_t)s_grp[1] * p.g_expert_stride;
+        partb += (size_t)blockIdx.y * p.nranges * MM_COLS * p.N;
+    } else {
+        if (threadIdx.x < MM_COLS) { s_colact[threadIdx.x] = (uint32_t)(threadIdx.x * p.L.col_bytes); s_coldst[threadIdx.x] = (long long)threadIdx.x * (long long)p.dst_stride; }
+        __syncthreads();
+    }
     const int t0 = (int)((long long)p.ntiles * g / p.ngroups), t1 = (int)((long long)p.ntiles * (g + 1) / p.ngroups);
     const int nunits = t1 - t0;
     const int nbk = min(MM_KB, p.nb - r * MM_KB);                 // super-blocks in this K-range
@@ -244,7 +288,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
         for (int u = 0; u < nunits; u++) {
             const int st = u % ns, use = u / ns;
             if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-            const uint8_t *src = p.W + (size_t)((t0 + u) * MM_ROWS + (lane & 15)) * p.rb + (size_t)r * MM_KB * p.bbytes;
+            const uint8_t *src = Wb + (size_t)((t0 + u) * MM_ROWS + (lane & 15)) * p.rb + (size_t)r * MM_KB * p.bbytes;
             const uint32_t extra = (uint32_t)((uintptr_t)src & 15);
             const uint32_t bytes = (extra + piece + 15u) & ~15u;
             uint32_t total = lane < 16 ? bytes : 0;
@@ -256,9 +300,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
             if (u == min(ns, nunits) - 1) {
                 // the weight ring is full: now the activations of this K-range (written by the previous kernel), one bulk copy per column
                 if (p.use_pdl) pdl_wait();
-                if (lane == 0) mbar_arrive_expect_tx(act_full, (uint32_t)p.ncols * (uint32_t)nbk * 256u);
+                if (lane == 0) mbar_arrive_expect_tx(act_full, (uint32_t)ncols * (uint32_t)nbk * 256u);
                 __syncwarp();
-                if (lane < p.ncols) bulk_g2s(aq + (size_t)lane * MM_ASTRIDE, p.act + (size_t)lane * p.L.col_bytes + (size_t)r * MM_KR, (uint32_t)nbk * 256u, act_full);
+                if (lane < ncols) bulk_g2s(aq + (size_t)lane * MM_ASTRIDE, p.act + s_colact[lane] + (size_t)r * MM_KR, (uint32_t)nbk * 256u, act_full);
             }
         }
         return;
@@ -269,16 +313,16 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
         const int q8k = p.L.q8k;
         constexpr int nthr = 2 * MM_MAX_STAGES * 32;
         // token columns beyond ncols (padding of the last n-tile) multiply zeros
-        for (int i = threadIdx.x; i < (NT * 8 - p.ncols) * (MM_KR / 16); i += nthr)
-            *(uint4 *)(aq + (size_t)(p.ncols + i / (MM_KR / 16)) * MM_ASTRIDE + (i % (MM_KR / 16)) * 16) = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < (NT * 8 - ncols) * (MM_KR / 16); i += nthr)
+            *(uint4 *)(aq + (size_t)(ncols + i / (MM_KR / 16)) * MM_ASTRIDE + (i % (MM_KR / 16)) * 16) = make_uint4(0, 0, 0, 0);
         if (q8k) {
             // one (column, super-block) per thread: d and the 8 per-32 sums (pairs of the q8_K per-16 bsums)
             for (int i = threadIdx.x; i < NT * 8 * MM_KB; i += nthr) {
                 const int col = i / MM_KB, b = i % MM_KB;
                 float d = 0.0f;
                 uint4 sv = make_uint4(0, 0, 0, 0);
-                if (col < p.ncols && b < nbk) {
-                    const uint8_t *cb = p.act + (size_t)col * p.L.col_bytes;
+                if (col < ncols && b < nbk) {
+                    const uint8_t *cb = p.act + s_colact[col];
                     d = ((const float *)(cb + p.L.off_d))[r * MM_KB + b];
                     const uint4 *bs = (const uint4 *)(cb + p.L.off_sums) + (size_t)(r * MM_KB + b) * 2;
                     const uint4 x = bs[0], y = bs[1];
@@ -294,7 +338,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
         } else {
             for (int i = threadIdx.x; i < NT * 8 * MM_KB * 8; i += nthr) {
                 const int col = i / (MM_KB * 8), b = i % (MM_KB * 8);
-                ad[i] = (col < p.ncols && b < nbk * 8) ? ((const float *)(p.act + (size_t)col * p.L.col_bytes + p.L.off_d))[r * MM_KB * 8 + b] : 0.0f;
+                ad[i] = (col < ncols && b < nbk * 8) ? ((const float *)(p.act + s_colact[col] + p.L.off_d))[r * MM_KB * 8 + b] : 0.0f;
             }
         }
     }
@@ -305,7 +349,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
     float *cb = comb + pair * (16 * 32);
     mbar_wait(act_full, 0);
     for (int u = pair, use = 0; u < nunits; u += ns, use++) {
-        const uint8_t *src0 = p.W + (size_t)((t0 + u) * MM_ROWS) * p.rb + (size_t)r * MM_KB * p.bbytes;
+        const uint8_t *src0 = Wb + (size_t)((t0 + u) * MM_ROWS) * p.rb + (size_t)r * MM_KB * p.bbytes;
         const uint8_t *stage = ring + (size_t)pair * p.stage_bytes;
         float out[NT][4];
 #pragma unroll
@@ -337,14 +381,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
 #pragma unroll
             for (int cc = 0; cc < 2; cc++) {
                 const int col = nt * 8 + cq + cc;
-                if (col < p.ncols) {
+                if (col < ncols) {
                     if (p.nranges > 1) {
-                        float *pp = p.part + ((size_t)r * MM_COLS + col) * p.N;
+                        float *pp = partb + ((size_t)r * MM_COLS + col) * p.N;
                         pp[row] = out[nt][cc]; pp[row + 8] = out[nt][2 + cc];
                     } else {
-                        float *dp = p.dst + (size_t)col * p.dst_stride;
+                        float *dp = p.dst + s_coldst[col];
                         float r0 = 0.0f, r1 = 0.0f;
-                        if (p.residual) { const float *rp = p.residual + (size_t)col * p.dst_stride; r0 = rp[row]; r1 = rp[row + 8]; }
+                        if (p.residual) { const float *rp = p.residual + s_coldst[col]; r0 = rp[row]; r1 = rp[row + 8]; }
                         dp[row] = out[nt][cc] + r0; dp[row + 8] = out[nt][2 + cc] + r1;
                     }
                 }
@@ -365,16 +409,30 @@ __global__ void __launch_bounds__(256) b200_gemv_mma_reduce_kernel(const float *
     dst[(size_t)col * dst_stride + row] = a;
 }
 
+// grouped: grid = (N / 256, 32 columns, chunks); the chunk's pairs give the destination columns
+__global__ void __launch_bounds__(256) b200_gemv_mma_reduce_grouped_kernel(const MmParams p) {
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
+    int e, first, cnt;
+    group_lookup(p, blockIdx.z, e, first, cnt);
+    const int col = blockIdx.y, row = blockIdx.x * 256 + threadIdx.x;
+    if (col >= cnt || row >= p.N) return;
+    const int pair = p.g_pairs[first + col], t = pair / p.g_n_used, sl = pair % p.g_n_used;
+    const float *pp = p.part + ((size_t)blockIdx.z * p.nranges * MM_COLS + col) * p.N + row;
+    float a = pp[0];
+    for (int r = 1; r < p.nranges; r++) a += pp[(size_t)r * MM_COLS * p.N];
+    p.dst[(size_t)sl * p.g_d_nb1 + (size_t)t * p.g_d_nb2 + row] = a;
+}
+
 template <int TYPE, int NT>
-int launch_t(b200_ctx *ctx, const MmParams &p, int grid, size_t smem) {
+int launch_t(b200_ctx *ctx, const MmParams &p, int grid, size_t smem, int grid_y = 1) {
     auto kern = b200_gemv_mma_kernel<TYPE, NT>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 512));     // 512: the static column maps
         attr_set[ctx->device & 15] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cfg.gridDim = dim3((unsigned)grid, (unsigned)grid_y); cfg.blockDim = dim3(MM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -384,7 +442,8 @@ int launch_t(b200_ctx *ctx, const MmParams &p, int grid, size_t smem) {
     return B200_OK;
 }
 template <int TYPE>
-int launch_type(b200_ctx *ctx, const MmParams &p, int grid, size_t smem) {
+int launch_type(b200_ctx *ctx, const MmParams &p, int grid, size_t smem, int grid_y = 1) {
+    if (p.g_E) return launch_t<TYPE, 4>(ctx, p, grid, smem, grid_y);
     return p.ncols <= 8 ? launch_t<TYPE, 1>(ctx, p, grid, smem) : p.ncols <= 16 ? launch_t<TYPE, 2>(ctx, p, grid, smem) : launch_t<TYPE, 4>(ctx, p, grid, smem);
 }
 
@@ -396,18 +455,16 @@ bool gemv_mma_supported(int type, int64_t N, int64_t K, int64_t M) {
 }
 
 // dst[col * dst_stride + n] = W[n, :] . x[:, col] for `ncols` <= 32 columns pre-quantised in `act` (ActLayout scratch)
-int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int ncols, float *dst, size_t dst_stride, bool stream_once, bool w_const, const float *residual) {
-    MmParams p = {};
-    p.residual = residual;
-    p.stream_once = stream_once ? 1 : 0; p.w_const = w_const ? 1 : 0;
-    p.W = W; p.rb = (uint32_t)rb; p.type = type; p.N = (int)N; p.K = (int)K; p.ncols = ncols;
-    p.act = act; p.L = ActLayout::make(b200_act_mode_q8k(type), K);
-    p.dst = dst; p.dst_stride = dst_stride;
+static int mma_run(b200_ctx *ctx, MmParams &p, int type, int64_t N, int64_t K, int grid_y) {
+    p.type = type; p.N = (int)N; p.K = (int)K;
+    p.L = ActLayout::make(b200_act_mode_q8k(type), K);
     p.nb = (int)(K / 256);
     p.bbytes = type == B200_TYPE_Q4_K ? 144u : type == B200_TYPE_Q5_K ? 176u : type == B200_TYPE_Q6_K ? 210u : type == B200_TYPE_Q4_0 ? 144u : 272u;
     p.nranges = (p.nb + MM_KB - 1) / MM_KB;
     p.ntiles = (int)(N / MM_ROWS);
-    const int G = ctx->sm_count;
+    // dense: the machine is one wave of (tile group, K range) CTAs; grouped: the chunks of all experts share it
+    int G = ctx->sm_count;
+    if (grid_y > 1) { G = (4 * ctx->sm_count + grid_y - 1) / grid_y; if (G > ctx->sm_count) G = ctx->sm_count; if (G < p.nranges) G = p.nranges; }
     p.ngroups = G / p.nranges;
     if (p.ngroups < 1) p.ngroups = 1;
     if (p.ngroups > p.ntiles) p.ngroups = p.ntiles;
@@ -424,24 +481,33 @@ int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_
     p.off_ring = off;
     p.rstride = ((MM_KB * p.bbytes + 15u) & ~15u) + 16;           // + worst-case misalignment of a row start
     p.stage_bytes = (MM_ROWS * p.rstride + 127u) & ~127u;
-    int ns = (int)((ctx->smem_optin - off) / p.stage_bytes);
+    int ns = (int)((ctx->smem_optin - 512 - off) / p.stage_bytes);
     if (ns > MM_MAX_STAGES) ns = MM_MAX_STAGES;
     if (ns < 2) { b200_set_error("gemv_mma: shared memory"); return B200_ERR_FAILED; }
     p.nstages = ns;
     const size_t smem = (size_t)off + (size_t)ns * p.stage_bytes;
     if (p.nranges > 1) {
-        p.part = (float *)ctx->get_scratch(SCRATCH_MISC, (size_t)p.nranges * MM_COLS * N * 4);
+        p.part = (float *)ctx->get_scratch(SCRATCH_MISC, (size_t)grid_y * p.nranges * MM_COLS * N * 4);
         if (!p.part) return B200_ERR_ALLOC;
     }
     const int grid = p.ngroups * p.nranges;
-    int rc;
     switch (type) {
-        case B200_TYPE_Q4_K: rc = launch_type<B200_TYPE_Q4_K>(ctx, p, grid, smem); break;
-        case B200_TYPE_Q5_K: rc = launch_type<B200_TYPE_Q5_K>(ctx, p, grid, smem); break;
-        case B200_TYPE_Q6_K: rc = launch_type<B200_TYPE_Q6_K>(ctx, p, grid, smem); break;
-        case B200_TYPE_Q4_0: rc = launch_type<B200_TYPE_Q4_0>(ctx, p, grid, smem); break;
-        default:             rc = launch_type<B200_TYPE_Q8_0>(ctx, p, grid, smem); break;
+        case B200_TYPE_Q4_K: return launch_type<B200_TYPE_Q4_K>(ctx, p, grid, smem, grid_y);
+        case B200_TYPE_Q5_K: return launch_type<B200_TYPE_Q5_K>(ctx, p, grid, smem, grid_y);
+        case B200_TYPE_Q6_K: return launch_type<B200_TYPE_Q6_K>(ctx, p, grid, smem, grid_y);
+        case B200_TYPE_Q4_0: return launch_type<B200_TYPE_Q4_0>(ctx, p, grid, smem, grid_y);
+        default:             return launch_type<B200_TYPE_Q8_0>(ctx, p, grid, smem, grid_y);
     }
+}
+
+int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int ncols, float *dst, size_t dst_stride, bool stream_once, bool w_const, const float *residual) {
+    MmParams p = {};
+    p.residual = residual;
+    p.stream_once = stream_once ? 1 : 0; p.w_const = w_const ? 1 : 0;
+    p.W = W; p.rb = (uint32_t)rb; p.ncols = ncols;
+    p.act = act;
+    p.dst = dst; p.dst_stride = dst_stride;
+    int rc = mma_run(ctx, p, type, N, K, 1);
     if (rc || p.nranges == 1) return rc;
     const int64_t total = (int64_t)ncols * N;
     cudaLaunchConfig_t cfg = {};
@@ -451,6 +517,29 @@ int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = p.use_pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_gemv_mma_reduce_kernel, (const float *)p.part, p.nranges, (int)N, ncols, dst, dst_stride, residual, p.use_pdl));
+    ctx->launches++;
+    return B200_OK;
+}
+
+// MUL_MAT_ID over pairs grouped by expert on the device: dst[:, slot, tok] = W[expert(pair)] . act[:, column(pair)]; every chunk of
+// <= 32 pairs of one expert streams that expert's matrix once.  No host knowledge of the routing: the grid covers the worst case
+// (g.max_chunks) and chunks beyond the real count exit at once.
+int launch_gemv_mma_grouped(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, const MmGroupDesc &g, float *dst) {
+    MmParams p = {};
+    p.stream_once = 0; p.w_const = 1;
+    p.W = W; p.rb = (uint32_t)rb; p.ncols = MM_COLS;
+    p.act = act; p.dst = dst;
+    p.g_off = g.off; p.g_pairs = g.pairs; p.g_E = g.E; p.g_n_used = g.n_used; p.g_b_ne1 = g.b_ne1;
+    p.g_expert_stride = g.expert_stride; p.g_d_nb1 = g.d_nb1; p.g_d_nb2 = g.d_nb2;
+    int rc = mma_run(ctx, p, type, N, K, g.max_chunks);
+    if (rc || p.nranges == 1) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((N + 255) / 256), MM_COLS, (unsigned)g.max_chunks); cfg.blockDim = dim3(256); cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = p.use_pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_gemv_mma_reduce_grouped_kernel, p));
     ctx->launches++;
     return B200_OK;
 }

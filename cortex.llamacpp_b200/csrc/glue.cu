@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) b200_get_rows_kernel(b200_tensor s, b200_
 // ---------------------------------------------------------------------------------------------- soft_max
 // ggml_compute_forward_soft_max_f32 (ggml-cpu.c:10224-10320): w = x*scale + slope*mask; max; exp(w-max) summed in double
 template <typename MT>
-__global__ void __launch_bounds__(256) b200_soft_max_kernel(b200_tensor x, b200_tensor mask, b200_tensor y, float scale, float max_bias, int has_mask) {
+__global__ void __launch_bounds__(256) b200_soft_max_kernel(b200_tensor x, b200_tensor mask, b200_tensor y, float scale, float max_bias, int has_mask, int exact) {
     __shared__ double shd[8];
     __shared__ float shf[8];
     const int64_t row = blockIdx.x;
@@ -321,12 +321,35 @@ __global__ void __launch_bounds__(256) b200_soft_max_kernel(b200_tensor x, b200_
     }
     mx = block_reduce_max_f(mx, shf);
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < ne00; i += blockDim.x) {
-        const float v = expf(__fsub_rn(yp[i], mx));
-        yp[i] = v;
-        s += (double)v;
+    if (exact) {
+        // cpu-exact mode: ggml_vec_soft_max_f32's AVX2 path (ggml-cpu.c:2261-2271, 2296-2300): ggml_v_expf on full groups of 8, each group
+        // enters the double sum as the float ((v0+v4)+(v2+v6))+((v1+v5)+(v3+v7)), groups in order; leftovers through glibc's expf
+        const int64_t n8 = ne00 & ~(int64_t)7;
+        for (int64_t i = threadIdx.x; i < ne00; i += blockDim.x) {
+            const float d = __fsub_rn(yp[i], mx);
+            yp[i] = i < n8 ? ggml_v_expf_lane(d) : glibc_expf(d);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int64_t i = 0; i < n8; i += 8) {
+                const float s8 = __fadd_rn(__fadd_rn(__fadd_rn(yp[i], yp[i + 4]), __fadd_rn(yp[i + 2], yp[i + 6])),
+                                           __fadd_rn(__fadd_rn(yp[i + 1], yp[i + 5]), __fadd_rn(yp[i + 3], yp[i + 7])));
+                t += (double)s8;
+            }
+            for (int64_t i = n8; i < ne00; i++) t += (double)yp[i];
+            shd[0] = t;
+        }
+        __syncthreads();
+        s = shd[0];
+    } else {
+        for (int64_t i = threadIdx.x; i < ne00; i += blockDim.x) {
+            const float v = expf(__fsub_rn(yp[i], mx));
+            yp[i] = v;
+            s += (double)v;
+        }
+        s = block_reduce_sum_d(s, shd);
     }
-    s = block_reduce_sum_d(s, shd);
     const float inv = (float)(1.0 / s);
     for (int64_t i = threadIdx.x; i < ne00; i += blockDim.x) yp[i] = __fmul_rn(yp[i], inv);
 }
@@ -705,9 +728,9 @@ int op_glue(b200_ctx *ctx, const b200_op *op) {
             if (rows == 0) return B200_OK;
             const int has_mask = op->n_src > 1 && b.data != nullptr;
             if (has_mask && b.type == B200_TYPE_F32)
-                b200_soft_max_kernel<float><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), 1);
+                b200_soft_max_kernel<float><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), 1, ctx->opt_cpu_exact);
             else
-                b200_soft_max_kernel<__half><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), has_mask);
+                b200_soft_max_kernel<__half><<<(unsigned)rows, 256, 0, ctx->stream>>>(a, b, d, f32_param(op, 0), f32_param(op, 1), has_mask, ctx->opt_cpu_exact);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
             return B200_OK;

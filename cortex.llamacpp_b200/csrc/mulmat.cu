@@ -10,6 +10,7 @@
 // MUL_MAT_ID: device-side expert routing -- no host sync on `ids` (the reference copies ids to the host and
 // loops experts there).
 #include "common.cuh"
+#include <algorithm>
 #include <cuda_bf16.h>
 #include "gemm_i8.h"
 
@@ -56,9 +57,42 @@ __global__ void __launch_bounds__(128) b200_mul_mat_float_kernel(b200_tensor w, 
     if (lane == 0) *(float *)((char *)d.data + n * d.nb[0] + m * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]) = acc;
 }
 
+// cpu-exact mode, F32 weights (the MoE router): ggml_vec_dot_f32 of the AVX2 + FMA build (ggml-cpu.c:1454-1494): lane l of accumulator j
+// owns elements 32i + 8j + l; 32 threads = the 4 x 8 accumulator lanes; GGML_F32x8_REDUCE; n % 32 leftovers as float mul + add
+__global__ void __launch_bounds__(128) b200_mul_mat_f32_exact_kernel(b200_tensor w, b200_tensor x, b200_tensor d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int64_t N = d.ne[0], M = d.ne[1];
+    const int64_t total = N * M * d.ne[2] * d.ne[3];
+    if (gw >= total) return;
+    const int64_t n = gw % N, m = (gw / N) % M, i2 = (gw / (N * M)) % d.ne[2], i3 = gw / (N * M * d.ne[2]);
+    const int64_t w2 = i2 / (d.ne[2] / w.ne[2]), w3 = i3 / (d.ne[3] / w.ne[3]);
+    const float *wp = (const float *)((const char *)w.data + n * w.nb[1] + w2 * w.nb[2] + w3 * w.nb[3]);
+    const float *xp = (const float *)((const char *)x.data + m * x.nb[1] + i2 * x.nb[2] + i3 * x.nb[3]);
+    const int64_t K = w.ne[0], np = K & ~(int64_t)31;
+    float acc = 0.0f;                                   // lane = 8 * j + l
+    for (int64_t i = 0; i < np; i += 32) acc = __fmaf_rn(wp[i + lane], xp[i + lane], acc);
+    // (s0 + s2) + (s1 + s3) lane-wise: lanes l, l+16 then l+8
+    float a = __fadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 16));          // lanes 0..7: s0 + s2; lanes 8..15: s1 + s3
+    a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 8));                     // lanes 0..7: x0[l]
+    a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 4));                     // lanes 0..3: t[l] = x0[l] + x0[l + 4]
+    a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 1));                     // lane 0: t0 + t1, lane 2: t2 + t3
+    a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 2));                     // lane 0: (t0 + t1) + (t2 + t3)
+    if (lane == 0) {
+        for (int64_t i = np; i < K; i++) a = __fadd_rn(a, __fmul_rn(wp[i], xp[i]));
+        *(float *)((char *)d.data + n * d.nb[0] + m * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]) = a;
+    }
+}
+
 int mul_mat_float(b200_ctx *ctx, const b200_tensor &w, const b200_tensor &x, const b200_tensor &d) {
     const int64_t total = tensor_nelements(d);
     if (total == 0) return B200_OK;
+    if (ctx->opt_cpu_exact && w.type == B200_TYPE_F32 && w.nb[0] == 4 && x.nb[0] == 4) {
+        b200_mul_mat_f32_exact_kernel<<<(unsigned)((total + 3) / 4), 128, 0, ctx->stream>>>(w, x, d);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return B200_OK;
+    }
     const unsigned grid = (unsigned)((total + 3) / 4);
     switch (w.type) {
         case B200_TYPE_F32:  b200_mul_mat_float_kernel<float><<<grid, 128, 0, ctx->stream>>>(w, x, d); break;
@@ -226,10 +260,78 @@ bool supports_mul_mat_id(const b200_op *op) {
     return true;
 }
 
+// routing tables for the grouped path: counting sort of the (token, slot) pairs by expert, one CTA (pairs <= a few thousand)
+__global__ void __launch_bounds__(1024) b200_moe_group_kernel(const char *ids, uint64_t nb0, uint64_t nb1, int n_used, int n_tok, int E, int32_t *off, int32_t *pairs, int use_pdl) {
+    extern __shared__ int sm_cnt[];            // [E] counts, then [E] cursors
+    if (use_pdl) { pdl_trigger(); pdl_wait(); }
+    int *cnt = sm_cnt, *cur = sm_cnt + E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) cnt[e] = 0;
+    __syncthreads();
+    const int npairs = n_used * n_tok;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const int e = *(const int32_t *)(ids + (uint64_t)(p % n_used) * nb0 + (uint64_t)(p / n_used) * nb1);
+        if (e >= 0 && e < E) atomicAdd(&cnt[e], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0;
+        for (int e = 0; e < E; e++) { off[e] = a; cur[e] = a; a += cnt[e]; }
+        off[E] = a;
+    }
+    __syncthreads();
+    // ascending pair order inside an expert (deterministic tables): thread-strided passes would interleave, so one warp per expert scans
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int e = warp; e < E; e += nw) {
+        int pos = cur[e];
+        for (int p0 = 0; p0 < npairs; p0 += 32) {
+            const int p = p0 + lane;
+            const bool hit = p < npairs && *(const int32_t *)(ids + (uint64_t)(p % n_used) * nb0 + (uint64_t)(p / n_used) * nb1) == e;
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) pairs[pos + __popc(m & ((1u << lane) - 1))] = p;
+            pos += __popc(m);
+        }
+    }
+}
+
 int op_mul_mat_id(b200_ctx *ctx, const b200_op *op) {
     const b200_tensor &as = op->src[0], &b = op->src[1], &ids = op->src[2], &d = op->dst;
     const int64_t K = as.ne[0], N = as.ne[1], n_used = ids.ne[0], n_tok = ids.ne[1];
     const size_t rb = b200_row_bytes(as.type, K);
+    // batches: group the (token, slot) pairs by expert on the device and stream every expert's matrix once per 32 pairs (the reference
+    // copies ids to the host, syncs, and loops experts there: ggml-cuda.cu:1976-2096)
+    if (ctx->opt_cpu_exact && (b.ne[1] == 1 || b.nb[2] == b.ne[1] * b.nb[1])) {
+        // parity mode: same quantised activations, every (token, slot) dot in the reference's SIMD order (exact.cu)
+        const int q8k = b200_act_mode_q8k(as.type);
+        const ActLayout L = ActLayout::make(q8k, K);
+        const int64_t acols = b.ne[1] == 1 ? n_tok : n_used * n_tok;
+        uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)acols);
+        if (!act) return B200_ERR_ALLOC;
+        int rc = launch_quantize_act(ctx, q8k, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], K, acols, act);
+        if (rc) return rc;
+        ExactMoe moe = {(const char *)ids.data, ids.nb[0], ids.nb[1], (int)n_used, (int)b.ne[1], (size_t)as.nb[2], (size_t)(d.nb[1] / 4), (size_t)(d.nb[2] / 4)};
+        return launch_mul_mat_exact(ctx, as.type, (const uint8_t *)as.data, rb, N, K, act, n_used * n_tok, (float *)d.data, 0, &moe);
+    }
+    static const int64_t group_min = getenv("GGML_B200_MOE_GROUP_MIN") ? atoi(getenv("GGML_B200_MOE_GROUP_MIN")) : 9;
+    const int64_t npairs = n_used * n_tok, E = as.ne[2];
+    const bool b_dense = b.ne[1] == 1 || b.nb[2] == b.ne[1] * b.nb[1];
+    if (npairs >= group_min && !ctx->opt_cpu_exact && gemv_mma_supported(as.type, N, K, 32) && b_dense && E <= 1024 && npairs <= (1 << 20) && !(d.nb[1] & 3) && !(d.nb[2] & 3)) {
+        const int q8k = b200_act_mode_q8k(as.type);
+        const ActLayout L = ActLayout::make(q8k, K);
+        const int64_t acols = b.ne[1] == 1 ? n_tok : npairs;
+        uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)acols);
+        int32_t *tab = (int32_t *)ctx->get_scratch(SCRATCH_MOE, (size_t)(E + 1 + npairs) * 4);
+        if (!act || !tab) return B200_ERR_ALLOC;
+        int rc = launch_quantize_act(ctx, q8k, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], K, acols, act);
+        if (rc) return rc;
+        b200_moe_group_kernel<<<1, 1024, (size_t)2 * E * sizeof(int), ctx->stream>>>((const char *)ids.data, ids.nb[0], ids.nb[1], (int)n_used, (int)n_tok, (int)E, tab, tab + E + 1, 0);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        MmGroupDesc g = {};
+        g.off = tab; g.pairs = tab + E + 1; g.E = (int)E; g.n_used = (int)n_used; g.b_ne1 = (int)b.ne[1];
+        g.max_chunks = (int)std::min<int64_t>(npairs, npairs / 32 + E);
+        g.expert_stride = as.nb[2]; g.d_nb1 = d.nb[1] / 4; g.d_nb2 = d.nb[2] / 4;
+        return launch_gemv_mma_grouped(ctx, as.type, (const uint8_t *)as.data, rb, N, K, act, g, (float *)d.data);
+    }
     for (int64_t t = 0; t < n_tok; t++)
         for (int64_t s = 0; s < n_used; s++) {
             const int32_t *idp = (const int32_t *)((const char *)ids.data + s * ids.nb[0] + t * ids.nb[1]);

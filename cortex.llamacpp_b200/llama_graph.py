@@ -107,8 +107,9 @@ class LlamaGraph:
         L, E, H, Hkv, D, FF, V, rope_base, n_expert, n_used = MODELS[model]
         if layers:
             L = layers
-        if n_expert:
-            raise NotImplementedError("MoE graphs are built by the tests directly")
+        self.n_expert, self.n_used = n_expert, n_used
+        if n_expert and tp_world > 1:
+            raise NotImplementedError("tensor-parallel MoE")
         self.model, self.ftype = model, ftype
         self.tp_rank, self.tp_world = tp_rank, tp_world
         self.H_full, self.Hkv_full, self.FF_full = H, Hkv, FF
@@ -127,7 +128,7 @@ class LlamaGraph:
 
         def weight(name, K, N, il, gain=1.0, split=None):
             """K, N are the FULL dimensions; split = None (replicated) | "rows" (column parallel) | "k" (row parallel)"""
-            t = tensor_type(name, ftype, il, L, 0, Hf // Hkvf)
+            t = tensor_type(name, ftype, il, L, n_expert, Hf // Hkvf)
             amp = gain * math.sqrt(3.0 / K)
             if t == F32:
                 buf = ((torch.rand(N * K, device=self.dev, generator=gen) * 2 - 1) * amp).view(torch.uint8)
@@ -145,6 +146,18 @@ class LlamaGraph:
             self.weight_bytes_by_type[t] = self.weight_bytes_by_type.get(t, 0) + nbytes
             return b200.tensor(buf.data_ptr(), t, [K, N], flags=b200.TENSOR_FLAG_WEIGHT)
 
+        def experts(name, K, N, il):
+            """n_expert matrices [K, N] back to back (ggml layout [K, N, n_expert], llama-model.cpp ffn_*_exps)"""
+            t = tensor_type(name, ftype, il, L, n_expert, Hf // Hkvf)
+            buf = device_rand_blocks(torch, t, N * n_expert, K, math.sqrt(3.0 / K), gen, self.dev)
+            self.keep.append(buf)
+            nbytes = n_expert * N * row_size(t, K)
+            self.weight_bytes += nbytes
+            self.weight_bytes_by_type[t] = self.weight_bytes_by_type.get(t, 0) + nbytes
+            self.expert_bytes = getattr(self, "expert_bytes", 0) + nbytes
+            rs = row_size(t, K)
+            return b200.tensor(buf.data_ptr(), t, [K, N, n_expert], nb=[BLOCK[t][1], rs, rs * N, rs * N * n_expert], flags=b200.TENSOR_FLAG_WEIGHT)
+
         def norm():
             buf = (1.0 + 0.02 * torch.randn(E, device=self.dev, generator=gen)).to(torch.float32)
             self.keep.append(buf)
@@ -157,9 +170,14 @@ class LlamaGraph:
                 attn_norm=norm(),
                 wq=weight(p + "attn_q.weight", E, Hf * D, il, split="rows"), wk=weight(p + "attn_k.weight", E, Hkvf * D, il, split="rows"),
                 wv=weight(p + "attn_v.weight", E, Hkvf * D, il, split="rows"), wo=weight(p + "attn_output.weight", Hf * D, E, il, split="k"),
-                ffn_norm=norm(),
-                gate=weight(p + "ffn_gate.weight", E, FFf, il, split="rows"), down=weight(p + "ffn_down.weight", FFf, E, il, split="k"),
-                up=weight(p + "ffn_up.weight", E, FFf, il, split="rows"))
+                ffn_norm=norm())
+            if n_expert:
+                lw.update(gate_inp=weight(p + "ffn_gate_inp.weight", E, n_expert, il, gain=1.0),
+                          gate_exps=experts(p + "ffn_gate_exps.weight", E, FFf, il), down_exps=experts(p + "ffn_down_exps.weight", FFf, E, il),
+                          up_exps=experts(p + "ffn_up_exps.weight", E, FFf, il))
+            else:
+                lw.update(gate=weight(p + "ffn_gate.weight", E, FFf, il, split="rows"), down=weight(p + "ffn_down.weight", FFf, E, il, split="k"),
+                          up=weight(p + "ffn_up.weight", E, FFf, il, split="rows"))
             rs = row_size(self.kv_type, Hkv * D)
             kc = torch.zeros(rs * n_ctx, dtype=torch.uint8, device=self.dev)
             vc = torch.zeros(rs * n_ctx, dtype=torch.uint8, device=self.dev)
@@ -183,7 +201,12 @@ class LlamaGraph:
         self.q = f32buf(H * D * T); self.k = f32buf(Hkv * D * T); self.v = f32buf(Hkv * D * T)
         self.qr = f32buf(H * D * T); self.kr = f32buf(Hkv * D * T)
         self.att = f32buf(H * D * T)
-        self.g = f32buf(FF * T); self.u = f32buf(FF * T); self.gu = f32buf(FF * T); self.tmpE = f32buf(E * T)
+        nu = max(1, n_used)
+        self.g = f32buf(FF * T * nu); self.u = f32buf(FF * T * nu); self.gu = f32buf(FF * T * nu); self.tmpE = f32buf(E * T * nu)
+        if n_expert:
+            self.r_logits = f32buf(n_expert * T); self.r_probs = f32buf(n_expert * T); self.r_w = f32buf(n_used * T); self.r_wn = f32buf(n_used * T)
+            self.r_sum = f32buf(T); self.moe_out = f32buf(E * T)
+            self.r_sel = torch.zeros(n_expert * T, dtype=torch.int32, device=self.dev)
         self.logits = f32buf(V * T)
         torch.cuda.synchronize(self.dev)
 
@@ -255,12 +278,38 @@ class LlamaGraph:
             # FFN
             ops.append(b.make_op(b.OP_RMS_NORM, t(p(self.cur), F32, [E, T]), [ffn_inp], [1e-5]))
             ops.append(b.make_op(b.OP_MUL, t(p(self.cur2), F32, [E, T]), [t(p(self.cur), F32, [E, T]), lw["ffn_norm"]]))
+            nxt = self.resid2 if other is self.resid else self.resid
+            if self.n_expert:
+                # build_moe_ffn (llama-graph.cpp:834-952): router -> softmax -> top-k (argsort view) -> weights (get_rows, normalised) ->
+                # up/gate experts -> silu * up -> down experts -> weighted sum over the used experts
+                nE, nu = self.n_expert, self.n_used
+                ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.r_logits), F32, [nE, T]), [lw["gate_inp"], xn]))
+                ops.append(b.make_op(b.OP_SOFT_MAX, t(p(self.r_probs), F32, [nE, T]), [t(p(self.r_logits), F32, [nE, T]), None], [1.0, 0.0]))
+                ops.append(b.make_op(b.OP_ARGSORT, t(p(self.r_sel), I32, [nE, T]), [t(p(self.r_probs), F32, [nE, T])], [1]))
+                sel = t(p(self.r_sel), I32, [nu, T], [4, nE * 4, nE * 4 * T, nE * 4 * T])          # ggml_top_k = view of the argsort
+                ops.append(b.make_op(b.OP_GET_ROWS, t(p(self.r_w), F32, [1, nu, T]), [t(p(self.r_probs), F32, [1, nE, T]), sel]))
+                ops.append(b.make_op(b.OP_SUM_ROWS, t(p(self.r_sum), F32, [1, T]), [t(p(self.r_w), F32, [nu, T])]))
+                ops.append(b.make_op(b.OP_DIV, t(p(self.r_wn), F32, [nu, T]), [t(p(self.r_w), F32, [nu, T]), t(p(self.r_sum), F32, [1, T])]))
+                x3 = t(p(self.cur2), F32, [E, 1, T])
+                ops.append(b.make_op(b.OP_MUL_MAT_ID, t(p(self.u), F32, [FF, nu, T]), [lw["up_exps"], x3, sel]))
+                ops.append(b.make_op(b.OP_MUL_MAT_ID, t(p(self.g), F32, [FF, nu, T]), [lw["gate_exps"], x3, sel]))
+                ops.append(b.make_op(b.OP_SILU, t(p(self.gu), F32, [FF, nu, T]), [t(p(self.g), F32, [FF, nu, T])]))
+                ops.append(b.make_op(b.OP_MUL, t(p(self.gu), F32, [FF, nu, T]), [t(p(self.u), F32, [FF, nu, T]), t(p(self.gu), F32, [FF, nu, T])]))
+                ops.append(b.make_op(b.OP_MUL_MAT_ID, t(p(self.tmpE), F32, [E, nu, T]), [lw["down_exps"], t(p(self.gu), F32, [FF, nu, T]), sel]))
+                ops.append(b.make_op(b.OP_MUL, t(p(self.tmpE), F32, [E, nu, T]), [t(p(self.tmpE), F32, [E, nu, T]), t(p(self.r_wn), F32, [1, nu, T])]))
+                acc = t(p(self.tmpE), F32, [E, T], [4, E * nu * 4, E * nu * T * 4, E * nu * T * 4])
+                for i in range(1, nu):
+                    ei = t(p(self.tmpE) + i * E * 4, F32, [E, T], [4, E * nu * 4, E * nu * T * 4, E * nu * T * 4])
+                    ops.append(b.make_op(b.OP_ADD, t(p(self.moe_out), F32, [E, T]), [acc, ei]))
+                    acc = t(p(self.moe_out), F32, [E, T])
+                ops.append(b.make_op(b.OP_ADD, t(p(nxt), F32, [E, T]), [acc, ffn_inp]))
+                inp, other = nxt, (self.resid if nxt is self.resid2 else self.resid2)
+                continue
             ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.u), F32, [FF, T]), [lw["up"], xn]))
             ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.g), F32, [FF, T]), [lw["gate"], xn]))
             ops.append(b.make_op(b.OP_SILU, t(p(self.gu), F32, [FF, T]), [t(p(self.g), F32, [FF, T])]))
             ops.append(b.make_op(b.OP_MUL, t(p(self.gu), F32, [FF, T]), [t(p(self.gu), F32, [FF, T]), t(p(self.u), F32, [FF, T])]))
             ops.append(b.make_op(b.OP_MUL_MAT, t(p(self.tmpE), F32, [E, T]), [lw["down"], t(p(self.gu), F32, [FF, T])]))
-            nxt = self.resid2 if other is self.resid else self.resid
             if self.tp_world > 1:
                 ops.append(b.make_op(b.OP_ALLREDUCE, t(p(nxt), F32, [E, T]), [t(p(self.tmpE), F32, [E, T]), ffn_inp]))
             else:

@@ -34,6 +34,44 @@ class HostModel:
         return t, raw[:N * R.row_size(t, K)], K, N
 
 
+ROUTER_MARGINS = []          # filled by moe_ffn: tests use it to tell routing near-ties (where any two builds may pick different experts)
+
+
+def moe_ffn(g, hm, lw, xn):
+    """llm_graph_context::build_moe_ffn (llama-graph.cpp:834-952) with the CPU backend's arithmetic: F32 router matmul, soft_max over the
+    experts, top-k by a descending argsort, weights = probs[selected] / their sum, experts through mul_mat_id, f32 weighted sum"""
+    T = xn.shape[0]
+    nE, nu = g.n_expert, g.n_used
+
+    def raw3(tensor):
+        buf = hm._bytes[tensor.data]
+        t, K, N = tensor.type, tensor.ne[0], tensor.ne[1]
+        return t, _host(buf)[:nE * N * R.row_size(t, K)], K, N
+
+    t_, raw, K, N = hm.w(lw["gate_inp"])
+    logits = R.orc_mul_mat(t_, raw, xn, N, K)                                    # [T, nE]
+    probs = R.orc_soft_max(logits, None, 1.0)
+    order = np.argsort(-probs, axis=1, kind="stable")
+    sel = order[:, :nu].astype(np.int32)                                          # ggml argsort desc; probabilities do not tie
+    srt = np.take_along_axis(probs, order, axis=1)
+    ROUTER_MARGINS.append(srt[:, nu - 1] - srt[:, nu])                            # per token: gap between the last used and the first unused expert
+    w = np.take_along_axis(probs, sel, axis=1)
+    wsum = w.astype(np.float64).sum(axis=1).astype(np.float32)                    # ggml_vec_sum_f32: ggml_float accumulator
+    wn = (w / wsum[:, None]).astype(np.float32)
+    t_, raw, K, N = raw3(lw["up_exps"])
+    up = R.orc_mul_mat_id(t_, raw, xn[:, None, :], sel, N, K, nE)                 # [T, nu, FF]
+    t_, raw, K, N = raw3(lw["gate_exps"])
+    gate = R.orc_mul_mat_id(t_, raw, xn[:, None, :], sel, N, K, nE)
+    par = R.orc_silu_mul(gate, up)
+    t_, raw, K, N = raw3(lw["down_exps"])
+    ex = R.orc_mul_mat_id(t_, raw, par, sel, N, K, nE)                            # [T, nu, E]
+    ex = (ex * wn[:, :, None]).astype(np.float32)
+    out = ex[:, 0]
+    for i in range(1, nu):
+        out = (out + ex[:, i]).astype(np.float32)
+    return out
+
+
 def forward(g, emb, pos, mask, kv_head, n_kv, layers=None, caches=None):
     """emb f32 [T, E], pos i32 [T], mask f32 [Tp, n_kv] (0/-inf) -> (logits f32 [T, V], caches)
 
@@ -81,6 +119,9 @@ def forward(g, emb, pos, mask, kv_head, n_kv, layers=None, caches=None):
         att = R.orc_flash_attn(np.ascontiguousarray(qr.transpose(1, 0, 2)), kb, vb, mask16, D, n_kv, Hkv, kvt, kvt, 1.0 / math.sqrt(D))
         x = mm(lw["wo"], att.reshape(T, H * D)) + x
         xn = R.orc_rms_norm(x, 1e-5) * normw(lw["ffn_norm"])
+        if getattr(g, "n_expert", 0):
+            x = moe_ffn(g, hm, lw, xn) + x
+            continue
         up, gate = mm(lw["up"], xn), mm(lw["gate"], xn)
         x = mm(lw["down"], R.orc_silu_mul(gate, up)) + x
     xn = R.orc_rms_norm(x, 1e-5) * normw(g.output_norm)

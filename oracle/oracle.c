@@ -390,8 +390,21 @@ static int act_type_for(int type) {
     return (type == ORC_TYPE_Q4_0 || type == ORC_TYPE_Q8_0) ? ORC_TYPE_Q8_0 : ORC_TYPE_Q8_K;
 }
 
+/* ggml_vec_dot_f32 as the AVX2 + FMA build computes it (ggml-cpu.c:1454-1494 with GGML_F32_STEP 32, GGML_F32_EPR 8): four 8-lane
+ * accumulators, one FMA per element, GGML_F32x8_REDUCE (:671-689), then the n % 32 leftovers as float mul + add */
 static float dot_f32(const float *a, const float *b, int64_t n) {
-    double s = 0; for (int64_t i = 0; i < n; i++) s += (double)a[i] * b[i]; return (float)s;
+    float sum[4][8];
+    for (int j = 0; j < 4; j++) for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
+    const int64_t np = n & ~(int64_t)31;
+    for (int64_t i = 0; i < np; i += 32)
+        for (int j = 0; j < 4; j++)
+            for (int l = 0; l < 8; l++) sum[j][l] = fmaf(a[i + 8 * j + l], b[i + 8 * j + l], sum[j][l]);
+    float x0[8], t[4];
+    for (int l = 0; l < 8; l++) x0[l] = (sum[0][l] + sum[2][l]) + (sum[1][l] + sum[3][l]);
+    for (int l = 0; l < 4; l++) t[l] = x0[l] + x0[l + 4];
+    float sumf = (t[0] + t[1]) + (t[2] + t[3]);
+    for (int64_t i = np; i < n; i++) { const float pr = a[i] * b[i]; sumf += pr; }
+    return sumf;
 }
 
 void orc_mul_mat(int type, const void *W, const float *x, float *dst, int64_t N, int64_t K, int64_t Mcols) {
@@ -501,18 +514,31 @@ void orc_rope(const float *x, float *y, const int32_t *pos, const float *ff,
     free(cs);
 }
 
-/* ggml_compute_forward_soft_max_f32: y = softmax(x*scale + mask), max-subtracted, sum in double */
+/* ggml_compute_forward_soft_max_f32 (ggml-cpu.c:10224-10320): y = softmax(x*scale + mask), max-subtracted.  The exponentials and
+ * their sum follow ggml_vec_soft_max_f32's AVX2 path (:2261-2271, 2296-2300): full groups of 8 go through ggml_v_expf (polynomial,
+ * not libm) and enter the double sum as ONE float, the horizontal sum ((v0+v4)+(v2+v6))+((v1+v5)+(v3+v7)); the n % 8 leftovers go
+ * through expf one by one */
+static float v_expf_lane(float x);
 void orc_soft_max(const float *x, const uint16_t *mask, float *y, int64_t ncols, int64_t nrows, float scale) {
     for (int64_t r = 0; r < nrows; r++, x += ncols, y += ncols) {
         float mx = -INFINITY;
         for (int64_t i = 0; i < ncols; i++) {
-            y[i] = x[i] * scale + (mask ? orc_f16_to_f32(mask[r * ncols + i]) : 0.0f);
+            float w = x[i] * scale;
+            if (mask) { const float mv = 1.0f * orc_f16_to_f32(mask[r * ncols + i]); w += mv; }
+            y[i] = w;
             if (y[i] > mx) mx = y[i];
         }
         double sum = 0.0;
-        for (int64_t i = 0; i < ncols; i++) { y[i] = expf(y[i] - mx); sum += (double)y[i]; }
+        int64_t i = 0;
+        for (; i + 7 < ncols; i += 8) {
+            float v[8];
+            for (int l = 0; l < 8; l++) { v[l] = v_expf_lane(y[i + l] - mx); y[i + l] = v[l]; }
+            const float s8 = ((v[0] + v[4]) + (v[2] + v[6])) + ((v[1] + v[5]) + (v[3] + v[7]));
+            sum += (double)s8;
+        }
+        for (; i < ncols; i++) { y[i] = expf(y[i] - mx); sum += (double)y[i]; }
         const float inv = (float)(1.0 / sum);
-        for (int64_t i = 0; i < ncols; i++) y[i] *= inv;
+        for (int64_t j = 0; j < ncols; j++) y[j] *= inv;
     }
 }
 

@@ -380,3 +380,14 @@ def ref_k_shift(kbytes, ktype, D, Hkv, n_cells, shift, n_rot, mode, freq_base, f
     C.memmove(_ptr(buf), g.b.ggml_get_data(cur), n)
     g.close()
     return buf
+
+
+def ref_mul_mat_f32(w, x):
+    """w f32 [N, K], x f32 [M, K] -> [M, N] through ggml_mul_mat on the reference CPU backend"""
+    g = RefGraph()
+    N, K = w.shape
+    M = x.shape[0]
+    out = g.b.ggml_mul_mat(g.ctx, g.tensor(F32, [K, N], w.astype(np.float32)), g.tensor(F32, [K, M], x.astype(np.float32)))
+    y = g.run(out, np.float32, (M, N), threads=1)
+    g.close()
+    return y

@@ -38,6 +38,7 @@ def run_steps(b200, ctx, g, schedule, rng, fusion, graphs=0):
 
 
 CASES = [("tiny-d128", f, k) for f in ["q4_k_m", "q4_0", "q5_k_m", "q8_0"] for k in ["f16", "q8_0", "q4_0"]] + [("mid-d128", "q4_k_m", "q8_0"), ("mid-d128", "q4_k_m", "f16")]
+MOE_CASES = [("tiny-moe", "q4_k_m", "q8_0"), ("tiny-moe", "q4_0", "f16"), ("tiny-moe", "q5_k_m", "q4_0")]   # Mixtral-shaped: 4 experts, 2 used
 SCHEDULE = [(5, 0), (1, 5), (2, 6), (4, 8), (1, 12), (3, 13)]        # prompt chunk, then decode-sized ubatches (1..4 tokens)
 # Fast-mode bound.  The fast kernels compute the CPU's integers exactly but add the per-block float terms in their own order; the
 # reference pipeline is chaotic at that level (a 1e-7 difference flips a q8 rounding in the next matmul, each flip is 1/127 of a
@@ -53,7 +54,7 @@ def margin(row):
     return (part[-1] - part[-2]) / np.abs(row).max()
 
 
-@pytest.mark.parametrize("model,ftype,kv", CASES)
+@pytest.mark.parametrize("model,ftype,kv", CASES + MOE_CASES)
 def test_llama_steps_cpu_exact_mode_bit_identical_to_oracle(b200, ctx, model, ftype, kv):
     """option cpu_exact: whole ubatches (prompt chunk + decode steps, every weight format and KV type) must equal the CPU oracle
     forward BIT FOR BIT -- logits identical, hence greedy tokens identical -- because every float sum follows the reference
@@ -99,6 +100,35 @@ def test_llama_steps_fast_mode_fused_and_unfused(b200, ctx, model, ftype, kv):
     for (a, _, la), (b, _, lb), (T, _) in zip(res[0], res[2], SCHEDULE):
         if T <= 4:
             assert lb < la, (T, la, lb)
+    ctx.set_option("fusion", 2)
+
+
+@pytest.mark.parametrize("model,ftype,kv", MOE_CASES)
+def test_moe_steps_fast_mode(b200, ctx, model, ftype, kv):
+    """Mixtral-shaped layers (build_moe_ffn op sequence) in the fast mode: per-pair GEMV routing for decode-sized ubatches, pairs grouped
+    by expert on the device for the 5-token ubatch.  Rows whose router decision is a near-tie in the oracle are exempt from the bound
+    (a different expert is a different function; the cpu-exact test above covers them bit for bit)."""
+    import llama_forward as OF
+    from __graft_entry__ import load_llama_graph
+    lg = load_llama_graph()
+    g = lg.LlamaGraph(b200, model=model, ftype=ftype, kv=kv, n_ctx=256, max_tokens=5)
+    for fusion in (0, 2):
+        for lw in g.layers:
+            lw["k_cache"].zero_(); lw["v_cache"].zero_()
+        OF.ROUTER_MARGINS.clear()
+        outs = run_steps(b200, ctx, g, SCHEDULE, np.random.default_rng(5), fusion)
+        margins = list(OF.ROUTER_MARGINS)                  # one entry per (ubatch, layer)
+        checked = 0
+        for si, ((got, want, _), (T, _)) in enumerate(zip(outs, SCHEDULE)):
+            assert np.isfinite(got).all()
+            tie = np.minimum.reduce(margins[si * g.L:(si + 1) * g.L]) < 0.02
+            for r in range(T):
+                if tie[r]:
+                    continue
+                rel = float(np.abs(got[r] - want[r]).max() / np.abs(want[r]).max())
+                assert rel <= FAST_MODE_BOUND, (fusion, T, r, rel)
+                checked += 1
+        assert checked >= 10, "too many routing near-ties to say anything"
     ctx.set_option("fusion", 2)
 
 

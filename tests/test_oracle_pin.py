@@ -107,9 +107,25 @@ def test_rope_matches_reference_golden(name, kw):
 
 
 def test_soft_max_matches_reference_golden():
+    """bit-exact: ggml_v_expf on full groups of 8 whose horizontal sum enters the double accumulator as one float, expf on leftovers"""
     got = R.orc_soft_max(OPS["sm_x"], OPS["sm_mask"], 0.125)
-    assert _close(got, OPS["sm_y"], 1e-6)
-    assert np.array_equal(got == 0, OPS["sm_y"] == 0)
+    assert np.array_equal(got, OPS["sm_y"]), np.abs(got - OPS["sm_y"]).max()
+    if R.have_ref():
+        rng = np.random.default_rng(5)
+        for n in (8, 13, 4, 100):                        # MoE router widths, leftovers only, mixed
+            x = (rng.standard_normal((7, n)) * 3).astype(np.float32)
+            assert np.array_equal(R.orc_soft_max(x, None, 1.0), R.ref_soft_max(x, None, 1.0)), n
+
+
+def test_f32_weight_matmul_matches_live_reference():
+    """the MoE router (F32 weights): ggml_vec_dot_f32's 4 x 8 FMA lanes + reduce tree + float leftovers, bit for bit"""
+    if not R.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(6)
+    for K, N, M in ((512, 8, 5), (4096, 8, 3), (100, 4, 2)):
+        w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
+        x = rng.standard_normal((M, K)).astype(np.float32)
+        assert np.array_equal(R.orc_mul_mat(R.F32, w.view(np.uint8).reshape(-1), x, N, K), R.ref_mul_mat_f32(w, x)), (K, N, M)
 
 
 def test_silu_mul_matches_reference_golden():

@@ -19,7 +19,7 @@ def lg():
 def test_tp_plan_north_star_models():
     G = lg()
     from make_gguf import MODELS
-    for model, worlds in (("llama3-70b", (2, 4, 8)), ("llama3-8b", (2, 4, 8)), ("mixtral-8x7b", (2, 4, 8))):
+    for model, worlds in (("llama3-70b", (2, 4, 8)), ("llama3-8b", (2, 4, 8)), ("mixtral", (2, 4, 8))):
         if model not in MODELS:
             continue
         L, E, H, Hkv, D, FF = MODELS[model][:6]
