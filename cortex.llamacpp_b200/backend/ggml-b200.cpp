@@ -55,12 +55,17 @@ ggml_guid_t backend_guid() {
 }
 
 // ------------------------------------------------------------------------------------------------ translation
+bool buffer_is_split(ggml_backend_buffer_t buffer);
 void to_b200_tensor(const ggml_tensor *t, b200_tensor &o) {
     memset(&o, 0, sizeof(o));
     if (!t) return;
     o.data = t->data;
     o.type = (int32_t)t->type;
     o.flags = (t->buffer && t->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) ? B200_TENSOR_FLAG_WEIGHT : 0u;
+    if (t->buffer && buffer_is_split(t->buffer)) {          // row-split weight: the b200_split made by split_buffer_init_tensor
+        o.data = t->extra;
+        o.flags |= B200_TENSOR_FLAG_SPLIT | B200_TENSOR_FLAG_WEIGHT;
+    }
     for (int i = 0; i < 4; i++) { o.ne[i] = t->ne[i]; o.nb[i] = t->nb[i]; }
 }
 
@@ -221,6 +226,136 @@ ggml_backend_buffer_type_t device_buffer_type(int device) {
     return &bufts[device];
 }
 
+// ------------------------------------------------------------------------------------------------ split buffer type (tensor parallelism)
+// ggml_backend_split_buffer_type (reference: ggml-cuda.cu:723-1050), the interface llama.cpp uses for --split-mode row
+// (llama-model.cpp:326-355): a weight matrix allocated in this buffer type is cut by ROWS over all B200 devices.  init_tensor allocates
+// one dense shard per device, set_tensor uploads every device's row range straight from the mmap'd file (b200_upload_slice), and
+// MUL_MAT on such a weight runs on all GPUs at once below the C ABI (B200_TENSOR_FLAG_SPLIT, mulmat.cu op_mul_mat_split).
+struct split_buft_ctx {
+    int main_device;
+    float split[B200_MAX_DEVICES + 1];        // cumulative fractions: device d owns [split[d], split[d+1]) of the rows
+    std::string name;
+};
+struct split_extra { b200_split sp; };
+struct split_buffer_ctx {
+    std::vector<split_extra *> extras;
+    ~split_buffer_ctx() {
+        for (split_extra *e : extras) {
+            for (int i = 0; i < e->sp.n_dev; i++) if (e->sp.shard[i]) b200_free(e->sp.device[i], e->sp.shard[i]);
+            delete e;
+        }
+    }
+};
+constexpr int64_t SPLIT_ROUNDING = 128;       // shard boundaries fall on multiples of the GEMM row tile
+void split_rows(const split_buft_ctx *c, const ggml_tensor *t, int n_dev, int64_t *row_low /* [n_dev + 1] */) {
+    const int64_t nrows = ggml_nrows(t);
+    row_low[0] = 0;
+    for (int d = 1; d < n_dev; d++) {
+        int64_t r = (int64_t)(nrows * c->split[d]);
+        r -= r % SPLIT_ROUNDING;
+        row_low[d] = r < row_low[d - 1] ? row_low[d - 1] : r;
+    }
+    row_low[n_dev] = nrows;
+}
+int split_n_dev() { return (int)ggml_backend_reg_dev_count(ggml_backend_b200_reg()); }
+
+const char *split_buft_get_name(ggml_backend_buffer_type_t buft) { return ((split_buft_ctx *)buft->context)->name.c_str(); }
+bool buft_is_split(ggml_backend_buffer_type_t buft) { return buft->iface.get_name == split_buft_get_name; }
+void split_buffer_free(ggml_backend_buffer_t buffer) { delete (split_buffer_ctx *)buffer->context; }
+void *split_buffer_get_base(ggml_backend_buffer_t) { return (void *)0x1000; }      // never dereferenced: the shards live in the tensor extras
+enum ggml_status split_buffer_init_tensor(ggml_backend_buffer_t buffer, ggml_tensor *tensor) {
+    GGML_ASSERT(tensor->view_src == nullptr);                  // views of split tensors are not supported (as in the reference)
+    split_buffer_ctx *bc = (split_buffer_ctx *)buffer->context;
+    const split_buft_ctx *c = (const split_buft_ctx *)buffer->buft->context;
+    split_extra *e = new split_extra();
+    memset(&e->sp, 0, sizeof(e->sp));
+    const int n = split_n_dev();
+    e->sp.n_dev = n;
+    split_rows(c, tensor, n, e->sp.row_low);
+    const size_t rb = ggml_row_size(tensor->type, tensor->ne[0]);
+    for (int d = 0; d < n; d++) {
+        e->sp.device[d] = d;
+        const int64_t nr = e->sp.row_low[d + 1] - e->sp.row_low[d];
+        if (nr <= 0) continue;
+        e->sp.shard[d] = b200_malloc(d, (size_t)nr * rb + 512);           // + slack: kernels read whole 16-byte lines
+        if (!e->sp.shard[d]) { GGML_LOG_ERROR("ggml-b200: split shard of %s on device %d: %s\n", tensor->name, d, b200_last_error()); delete e; return GGML_STATUS_ALLOC_FAILED; }
+        b200_memset(d, (char *)e->sp.shard[d] + (size_t)nr * rb, 0, 512);
+    }
+    bc->extras.push_back(e);
+    tensor->extra = &e->sp;
+    return GGML_STATUS_SUCCESS;
+}
+b200_ctx *upload_ctx(int device);
+void split_buffer_set_tensor(ggml_backend_buffer_t, ggml_tensor *tensor, const void *data, size_t offset, size_t size) {
+    GGML_ASSERT(offset == 0 && size == ggml_nbytes(tensor));   // split tensors are set in their entirety (as in the reference)
+    const b200_split *sp = (const b200_split *)tensor->extra;
+    const size_t rb = ggml_row_size(tensor->type, tensor->ne[0]);
+    for (int d = 0; d < sp->n_dev; d++) {
+        const int64_t nr = sp->row_low[d + 1] - sp->row_low[d];
+        if (nr <= 0) continue;
+        b200_ctx *uc = upload_ctx(sp->device[d]);
+        if (!uc || b200_upload_slice(uc, sp->shard[d], data, rb, sp->row_low[d], nr, 0, rb) != B200_OK)
+            GGML_ABORT("ggml-b200: split set_tensor(%s) on device %d: %s", tensor->name, sp->device[d], b200_last_error());
+    }
+}
+void split_buffer_get_tensor(ggml_backend_buffer_t, const ggml_tensor *tensor, void *data, size_t offset, size_t size) {
+    GGML_ASSERT(offset == 0 && size == ggml_nbytes(tensor));
+    const b200_split *sp = (const b200_split *)tensor->extra;
+    const size_t rb = ggml_row_size(tensor->type, tensor->ne[0]);
+    for (int d = 0; d < sp->n_dev; d++) {
+        const int64_t nr = sp->row_low[d + 1] - sp->row_low[d];
+        if (nr > 0 && b200_memcpy_d2h(sp->device[d], (char *)data + sp->row_low[d] * rb, sp->shard[d], (size_t)nr * rb) != B200_OK)
+            GGML_ABORT("ggml-b200: split get_tensor: %s", b200_last_error());
+    }
+}
+void split_buffer_clear(ggml_backend_buffer_t, uint8_t) {}
+const ggml_backend_buffer_i split_buffer_iface = {
+    /* .free_buffer   = */ split_buffer_free,
+    /* .get_base      = */ split_buffer_get_base,
+    /* .init_tensor   = */ split_buffer_init_tensor,
+    /* .memset_tensor = */ NULL,
+    /* .set_tensor    = */ split_buffer_set_tensor,
+    /* .get_tensor    = */ split_buffer_get_tensor,
+    /* .cpy_tensor    = */ NULL,
+    /* .clear         = */ split_buffer_clear,
+    /* .reset         = */ NULL,
+};
+// by buffer TYPE: llama.cpp probes supports_op with a zero-sized dummy buffer whose interface is empty (llama-model.cpp:232-236)
+bool buffer_is_split(ggml_backend_buffer_t buffer) { return buffer->buft && buft_is_split(buffer->buft); }
+size_t buft_get_alignment(ggml_backend_buffer_type_t);
+bool buft_is_host(ggml_backend_buffer_type_t);
+ggml_backend_buffer_t split_buft_alloc_buffer(ggml_backend_buffer_type_t buft, size_t size) {
+    // the shards are allocated per tensor in init_tensor (their sizes depend on the rounded row split)
+    return ggml_backend_buffer_init(buft, split_buffer_iface, new split_buffer_ctx(), size);
+}
+size_t split_buft_get_alloc_size(ggml_backend_buffer_type_t, const ggml_tensor *tensor) { return ggml_nbytes(tensor) + 512 * (size_t)split_n_dev(); }
+const ggml_backend_buffer_type_i split_buft_iface = {
+    split_buft_get_name, split_buft_alloc_buffer, buft_get_alignment, /* get_max_size */ NULL, split_buft_get_alloc_size, buft_is_host,
+};
+ggml_backend_buffer_type_t split_buffer_type(int main_device, const float *tensor_split) {
+    static std::mutex mu;
+    static std::vector<ggml_backend_buffer_type *> made;
+    std::lock_guard<std::mutex> lock(mu);
+    const int n = split_n_dev();
+    if (main_device < 0 || main_device >= n) return NULL;
+    split_buft_ctx *c = new split_buft_ctx();
+    c->main_device = main_device;
+    float sum = 0.0f;
+    bool all_zero = true;
+    for (int d = 0; d < n && tensor_split; d++) all_zero = all_zero && tensor_split[d] == 0.0f;
+    for (int d = 0; d < n; d++) { c->split[d] = sum; sum += (tensor_split && !all_zero) ? tensor_split[d] : 1.0f; }
+    for (int d = 0; d < n; d++) c->split[d] /= sum;
+    c->split[n] = 1.0f;
+    c->name = "B200" + std::to_string(main_device) + "_Split";
+    for (ggml_backend_buffer_type *b : made) {
+        const split_buft_ctx *o = (const split_buft_ctx *)b->context;
+        if (o->main_device == main_device && memcmp(o->split, c->split, sizeof(float) * (n + 1)) == 0) { delete c; return b; }
+    }
+    ggml_backend_buffer_type *b = new ggml_backend_buffer_type{split_buft_iface, ggml_backend_reg_dev_get(ggml_backend_b200_reg(), main_device), c};
+    made.push_back(b);
+    return b;
+}
+
 // pinned host buffer type (CPU-side weights, the scheduler's CPU compute buffer)
 const char *host_buft_name(ggml_backend_buffer_type_t) { return "B200_Host"; }
 void host_buffer_free(ggml_backend_buffer_t buffer) { b200_host_free(buffer->context); }
@@ -340,12 +475,18 @@ bool dev_supports_op(ggml_backend_dev_t dev, const ggml_tensor *op) {
         if (op->src[i] && op->src[i]->buffer && buft_is_b200(op->src[i]->buffer->buft) &&
             ((buft_ctx *)op->src[i]->buffer->buft->context)->device != d->device) return false;
     }
+    // a row-split weight can only be the src0 of a MUL_MAT driven from its main device (as in the reference, ggml-cuda.cu:3080-3100)
+    for (int i = 0; i < GGML_MAX_SRC; i++) {
+        if (!op->src[i] || !op->src[i]->buffer || !buffer_is_split(op->src[i]->buffer)) continue;
+        if (op->op != GGML_OP_MUL_MAT || i != 0 || ((split_buft_ctx *)op->src[i]->buffer->buft->context)->main_device != d->device) return false;
+    }
     if (is_view_op(op->op)) return true;
     b200_op o;
     if (!translate(op, o)) return false;
     return b200_supports_op(d->device, &o) != 0;
 }
 bool dev_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_type_t buft) {
+    if (buft_is_split(buft)) return ((split_buft_ctx *)buft->context)->main_device == ((device_ctx *)dev->context)->device;
     return buft_is_b200(buft) && ((buft_ctx *)buft->context)->device == ((device_ctx *)dev->context)->device;
 }
 int64_t op_batch_size(const ggml_tensor *op) {
@@ -395,7 +536,9 @@ ggml_backend_feature *get_features(ggml_backend_reg_t) {
 }
 void *reg_get_proc_address(ggml_backend_reg_t, const char *name) {
     if (strcmp(name, "ggml_backend_get_features") == 0) return (void *)get_features;
-    return NULL;    // no split buffer type: tensor parallelism is handled below the C ABI (GGML_B200_TP)
+    // --split-mode row: llama.cpp asks the backend registry for this entry point (llama-model.cpp:326-355, ggml-cuda.cu:3412-3416)
+    if (strcmp(name, "ggml_backend_split_buffer_type") == 0) return (void *)split_buffer_type;
+    return NULL;
 }
 const ggml_backend_reg_i reg_iface = {reg_get_name, reg_get_device_count, reg_get_device, reg_get_proc_address};
 

@@ -34,7 +34,14 @@ void *b200_ctx::get_scratch(int slot, size_t size) {
     if (scratch[slot]) cudaFree(scratch[slot]);
     scratch[slot] = nullptr; scratch_size[slot] = 0;
     void *p = nullptr;
-    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); b200_set_error("scratch alloc of %zu bytes failed", want); return nullptr; }
+    const cudaError_t me = cudaMalloc(&p, want);
+    if (me != cudaSuccess) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        cudaGetLastError();
+        b200_set_error("scratch alloc of %zu bytes failed on device %d (current %d): %s", want, device, cur, cudaGetErrorString(me));
+        return nullptr;
+    }
     scratch[slot] = p; scratch_size[slot] = want;
     return p;
 }
@@ -109,6 +116,11 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     dstep_cache_free(ctx);
     if (ctx->eager_kv_table) cudaFree(ctx->eager_kv_table);
     b200_comm_destroy(ctx);
+    for (int i = 0; i < 16; i++) {
+        if (ctx->split_join[i]) cudaEventDestroy(ctx->split_join[i]);
+        if (ctx->split_peer[i]) { b200_ctx_destroy(ctx->split_peer[i]); cudaSetDevice(ctx->device); }
+    }
+    if (ctx->split_fork) cudaEventDestroy(ctx->split_fork);
     if (ctx->fattn_counters) cudaFree(ctx->fattn_counters);
     for (int i = 0; i < SCRATCH_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
@@ -122,7 +134,7 @@ int64_t b200_kernel_launches(const b200_ctx *ctx) { return ctx->launches; }
 int b200_synchronize(b200_ctx *ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    return B200_OK;
+    return comm_check(ctx);          // a tensor-parallel step whose all-reduce lost a peer fails here instead of returning garbage sums
 }
 
 int b200_set_option(b200_ctx *ctx, const char *key, int value) {

@@ -67,6 +67,7 @@ struct b200_comm {
     uint8_t *peer[MAX_WORLD] = {nullptr};      // mapped exchange buffers of all ranks (peer[rank] == local)
     bool peers_attached = false;
     int oneshot = 1;
+    uint32_t *err_host = nullptr, *err_dev = nullptr;     // mapped pinned word: a kernel that gave up waiting for a peer sets it (comm_check)
 };
 
 namespace {
@@ -83,6 +84,7 @@ struct OneShotParams {
     const float *src; const float *residual; float *dst;
     int n, rank, world;                        // n floats (multiple of 4)
     int use_pdl;
+    uint32_t *err;                             // host-visible error word (peer timeout)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) b200_allreduce_oneshot_kernel(const OneSh
     if (threadIdx.x < p.world) {
         const uint32_t *f = (const uint32_t *)(local + OFF_FLAGS) + ((size_t)set * MAX_WORLD + threadIdx.x) * ONESHOT_CTAS + blockIdx.x;
         const long long t0 = clock64();
-        while ((int)(ld_relaxed_sys(f) - epoch) < 0) { if (clock64() - t0 > (1ll << 32)) break; }     // plain polls ...
+        while ((int)(ld_relaxed_sys(f) - epoch) < 0) { if (clock64() - t0 > (1ll << 32)) { if (p.err) *(volatile uint32_t *)p.err = 1u + threadIdx.x; break; } }     // plain polls ...
         (void)ld_acquire_sys(f);                                                                      // ... one acquire once the flag is there
     }
     __syncthreads();
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) b200_allreduce_ll_kernel(const OneShotPar
             uint4 lo, hi;
             do {
                 lo = ld_v4_sys(slot); hi = ld_v4_sys(slot + 16);
-                if (clock64() - t0 > (1ll << 32)) break;           // a lost peer must not hang the GPU
+                if (clock64() - t0 > (1ll << 32)) { if (p.err) *(volatile uint32_t *)p.err = 1u + r; break; }           // a lost peer must not hang the GPU
             } while (lo.y != epoch || lo.w != epoch || hi.y != epoch || hi.w != epoch);
             const float bx = __uint_as_float(lo.x), by = __uint_as_float(lo.z), bz = __uint_as_float(hi.x), bw = __uint_as_float(hi.z);
             if (r == 0) a = make_float4(bx, by, bz, bw);
@@ -226,6 +228,8 @@ int b200_comm_init(b200_ctx *ctx, const void *id128, int rank, int world) {
     CUDA_TRY(cudaMemset(buf, 0, OFF_SLOTS));
     CUDA_TRY(cudaMemset((uint8_t *)buf + OFF_LL, 0, EXCH_BYTES - OFF_LL));      // LL words must not hold a stale epoch
     c->local = (uint8_t *)buf;
+    if (cudaHostAlloc((void **)&c->err_host, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer((void **)&c->err_dev, c->err_host, 0) == cudaSuccess) *c->err_host = 0;
+    else { cudaGetLastError(); c->err_host = c->err_dev = nullptr; }
     c->peer[rank] = c->local;
     ctx->comm = c;
     return B200_OK;
@@ -270,12 +274,23 @@ int b200_comm_destroy(b200_ctx *ctx) {
     for (int r = 0; r < c->world; r++) if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
     if (c->nccl && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl);
     if (c->local) cudaFree(c->local);
+    if (c->err_host) cudaFreeHost(c->err_host);
     delete c;
     ctx->comm = nullptr;
     return B200_OK;
 }
 
 }  // extern "C"
+
+// called after a stream synchronisation: did an all-reduce give up waiting for a peer?  (the sums it produced are then garbage)
+int comm_check(b200_ctx *ctx) {
+    b200_comm *c = ctx ? ctx->comm : nullptr;
+    if (!c || !c->err_host || *(volatile uint32_t *)c->err_host == 0) return B200_OK;
+    const uint32_t who = *(volatile uint32_t *)c->err_host - 1;
+    *(volatile uint32_t *)c->err_host = 0;
+    b200_set_error("all-reduce: rank %d timed out waiting for rank %u (peer lost or not running the same step)", c->rank, who);
+    return B200_ERR_FAILED;
+}
 
 bool supports_allreduce(const b200_op *op) {
     const b200_tensor &s = op->src[0], &d = op->dst;
@@ -301,7 +316,7 @@ int op_allreduce(b200_ctx *ctx, const b200_op *op) {
     if (world > 1 && c->oneshot && c->peers_attached && aligned && (size_t)n * 4 <= ONESHOT_MAX_BYTES) {
         OneShotParams p = {};
         for (int r = 0; r < world; r++) p.peer[r] = c->peer[r];
-        p.src = src; p.residual = res; p.dst = dst; p.n = (int)n; p.rank = c->rank; p.world = world; p.use_pdl = ctx->opt_pdl;
+        p.src = src; p.residual = res; p.dst = dst; p.n = (int)n; p.rank = c->rank; p.world = world; p.use_pdl = ctx->opt_pdl; p.err = c->err_dev;
         // measured on Llama-3-70B decode (profiles/r1_scale.md): flag-in-data wins at 2 ranks (6.3 vs 8.9 us per all-reduce) and loses
         // at 8 (22 vs 15.9 us: twice the NVLink bytes and world x polling per element), so it is the default for 2 ranks only
         static const int use_ll = getenv("GGML_B200_ALLREDUCE_LL") ? atoi(getenv("GGML_B200_ALLREDUCE_LL")) : -1;

@@ -144,6 +144,11 @@ struct b200_ctx {
     int64_t       fa_map_key[4] = {0, 0, 0, 0};        // m_nb1, n_kv, n_q, QC
     void *        fattn_counters = nullptr;   // split-arrival counters of the fused flash-attention combine (fattn.cu)
     b200_comm *   comm = nullptr;       // tensor-parallel communicator (comm.cu); NULL = single GPU
+    // row-split matmuls driven from ONE host thread (ggml_backend_split_buffer_type): a context + join event per peer device
+    b200_ctx *    split_peer[16] = {nullptr};
+    cudaEvent_t   split_join[16] = {nullptr};
+    cudaEvent_t   split_fork = nullptr;
+    int64_t       split_ops = 0;                // executed row-split matmuls (tests)
     bool          capturing = false;
     void *        prof_buf = nullptr;   // debug: per-CTA timestamps (b200_debug_set_prof)
     int           prof_launch = 0;
@@ -164,6 +169,7 @@ bool supports_flash_attn_ext(const b200_op *op);
 bool supports_glue(const b200_op *op);
 int op_allreduce(b200_ctx *ctx, const b200_op *op);     // comm.cu
 bool supports_allreduce(const b200_op *op);
+int comm_check(b200_ctx *ctx);                          // comm.cu: B200_ERR_FAILED if an all-reduce timed out waiting for a peer
 
 // rope parameters shared by glue.cu and the decode-step kernel (dstep.cu)
 struct RopeParams {

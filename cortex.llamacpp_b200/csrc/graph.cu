@@ -132,7 +132,7 @@ static bool is_vec_f32(const b200_tensor &t, int64_t rows) {   // dense f32 [row
 }
 // a decode-sized quantised matmul the GEMV can take as a segment: W quant rows back to back, x dense [K, T], dst dense [N, T]
 static bool is_decode_mm(const b200_op &o) {
-    if (o.op != B200_OP_MUL_MAT || !supports_mul_mat(&o)) return false;
+    if (o.op != B200_OP_MUL_MAT || (o.src[0].flags & B200_TENSOR_FLAG_SPLIT) || !supports_mul_mat(&o)) return false;
     const b200_tensor &w = o.src[0], &x = o.src[1], &d = o.dst;
     if (!b200_type_is_quant(w.type) || w.ne[2] != 1 || w.ne[3] != 1) return false;
     return is_vec_f32(x, w.ne[0]) && is_vec_f32(d, w.ne[1]) && x.ne[1] == d.ne[1];
@@ -616,6 +616,8 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
     else { list.resize(n_ops); for (int i = 0; i < n_ops; i++) list[i].op = ops[i]; }
 
     if (!ctx->opt_cuda_graphs || n_ops < 8) return run_eager(ctx, list);
+    for (int i = 0; i < n_ops; i++)            // row-split matmuls fork to other devices' streams: launched eagerly
+        if (ops[i].op == B200_OP_MUL_MAT && (ops[i].src[0].flags & B200_TENSOR_FLAG_SPLIT)) return run_eager(ctx, list);
 
     // only decode-sized steps repeat (a prompt ubatch is seen once, and capturing its ~1000 big launches costs more than it saves)
     {

@@ -133,8 +133,21 @@ bool quant_mul_mat_shape_ok(const b200_tensor &w, const b200_tensor &x, const b2
 
 }  // namespace
 
+// row-split weight: the shard of every device is a dense GGUF matrix of its row range
+static bool split_ok(const b200_op *op) {
+    const b200_tensor &w = op->src[0], &x = op->src[1], &d = op->dst;
+    const b200_split *sp = (const b200_split *)w.data;
+    // sp == NULL: llama.cpp probing whether a weight may live in the split buffer type (no shards allocated yet)
+    if ((sp && (sp->n_dev < 1 || sp->n_dev > B200_MAX_SPLIT)) || !b200_type_is_quant(w.type)) return false;
+    if (w.ne[2] != 1 || w.ne[3] != 1 || x.ne[2] != 1 || x.ne[3] != 1) return false;
+    b200_tensor w0 = w;                                   // shape checks against an aligned stand-in for the shards (cudaMalloc'd: 256-byte aligned)
+    w0.data = (void *)(uintptr_t)0x1000; w0.flags &= ~B200_TENSOR_FLAG_SPLIT;
+    return quant_mul_mat_shape_ok(w0, x, d);
+}
+
 bool supports_mul_mat(const b200_op *op) {
     const b200_tensor &w = op->src[0], &x = op->src[1], &d = op->dst;
+    if (w.flags & B200_TENSOR_FLAG_SPLIT) return split_ok(op);
     if (x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
     if (w.type == B200_TYPE_F32 || w.type == B200_TYPE_F16 || w.type == B200_TYPE_BF16) {
         return w.ne[2] > 0 && w.ne[3] > 0 && d.ne[2] % w.ne[2] == 0 && d.ne[3] % w.ne[3] == 0;
@@ -142,8 +155,61 @@ bool supports_mul_mat(const b200_op *op) {
     return quant_mul_mat_shape_ok(w, x, d);
 }
 
+// MUL_MAT over a row-split weight (replaces the split path of ggml_cuda_op_mul_mat, ggml-cuda.cu:1363-1671): fork on the main stream,
+// every device multiplies its shard into its row range of dst -- activations read from and results written to the MAIN device's memory
+// through NVLink peer access, no staging copies -- and the main stream joins.  Each dst element is produced by the same kernels as on
+// one GPU, so the result does not depend on the split.
+static int op_mul_mat_split(b200_ctx *ctx, const b200_op *op) {
+    const b200_tensor &w = op->src[0];
+    const b200_split *sp = (const b200_split *)w.data;
+    if (!sp) { b200_set_error("mul_mat split: no shard table"); return B200_ERR_FAILED; }
+    if (!ctx->split_fork) CUDA_TRY(cudaEventCreateWithFlags(&ctx->split_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ctx->split_fork, ctx->stream));
+    int rc = B200_OK;
+    for (int i = 0; i < sp->n_dev && !rc; i++) {
+        const int64_t r0 = sp->row_low[i], nr = sp->row_low[i + 1] - r0;
+        if (nr <= 0) continue;
+        const int dev = sp->device[i];
+        b200_op sub = *op;
+        sub.src[0].data = sp->shard[i]; sub.src[0].flags &= ~B200_TENSOR_FLAG_SPLIT; sub.src[0].ne[1] = nr;
+        sub.src[0].nb[2] = sub.src[0].nb[1] * nr; sub.src[0].nb[3] = sub.src[0].nb[2];
+        sub.dst.data = (char *)op->dst.data + r0 * 4; sub.dst.ne[0] = nr;
+        if (dev == ctx->device) { rc = op_mul_mat(ctx, &sub); continue; }
+        if (dev < 0 || dev >= 16) { b200_set_error("mul_mat split: device %d", dev); return B200_ERR_FAILED; }
+        b200_ctx *pc = ctx->split_peer[dev];
+        if (!pc) {
+            pc = b200_ctx_create(dev);
+            if (!pc) return B200_ERR_FAILED;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, dev, ctx->device);
+            if (!can) { b200_set_error("mul_mat split: device %d cannot access device %d memory", dev, ctx->device); b200_ctx_destroy(pc); return B200_ERR_FAILED; }
+            cudaSetDevice(dev);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctx->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { b200_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); b200_ctx_destroy(pc); return B200_ERR_FAILED; }
+            cudaGetLastError();
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->split_join[dev], cudaEventDisableTiming));
+            pc->opt_pdl = 0; pc->opt_cuda_graphs = 0;
+            ctx->split_peer[dev] = pc;
+        }
+        pc->opt_cpu_exact = ctx->opt_cpu_exact;
+        CUDA_TRY(cudaSetDevice(dev));
+        CUDA_TRY(cudaStreamWaitEvent(pc->stream, ctx->split_fork, 0));
+        rc = op_mul_mat(pc, &sub);
+        if (!rc) {
+            CUDA_TRY(cudaEventRecord(ctx->split_join[dev], pc->stream));
+            CUDA_TRY(cudaSetDevice(ctx->device));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->split_join[dev], 0));
+            ctx->launches += 1;
+        }
+        cudaSetDevice(ctx->device);
+    }
+    ctx->split_ops++;
+    return rc;
+}
+
 int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     const b200_tensor &w = op->src[0], &x = op->src[1], &d = op->dst;
+    if (w.flags & B200_TENSOR_FLAG_SPLIT) return op_mul_mat_split(ctx, op);
     if (!b200_type_is_quant(w.type)) return mul_mat_float(ctx, w, x, d);
     if (!quant_mul_mat_shape_ok(w, x, d)) { b200_set_error("mul_mat: unsupported layout"); return B200_ERR_UNSUPPORTED; }
     const int64_t K = w.ne[0], N = w.ne[1], M = x.ne[1];

@@ -72,6 +72,17 @@ typedef enum b200_op_id {
 
 #define B200_MAX_SRC 4
 #define B200_TENSOR_FLAG_WEIGHT 1u   /* tensor lives in a weights buffer: constant across graph launches */
+/* src0 of a MUL_MAT is a row-split weight (ggml_backend_split_buffer_type, ggml-cuda.cu:723-1050): `data` points to a b200_split in
+ * host memory owned by the caller; device d holds rows [row_low[d], row_low[d+1]) of the GGUF matrix as a dense shard.  The matmul runs
+ * on every shard's GPU at once and the row ranges of dst land in the main device's memory through NVLink peer stores. */
+#define B200_TENSOR_FLAG_SPLIT 2u
+#define B200_MAX_SPLIT 16
+typedef struct b200_split {
+    int32_t n_dev;
+    int32_t device[B200_MAX_SPLIT];
+    void *  shard[B200_MAX_SPLIT];
+    int64_t row_low[B200_MAX_SPLIT + 1];
+} b200_split;
 
 typedef struct b200_tensor {
     void *   data;           /* device pointer (already offset to the tensor/view start) */

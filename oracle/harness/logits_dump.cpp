@@ -50,6 +50,10 @@ int main(int argc, char **argv) {
     llama_backend_init();
     llama_model_params mp = llama_model_default_params();
     mp.n_gpu_layers = ngl;
+    if (const char *sm = getenv("LOGITS_DUMP_SPLIT_MODE")) {      // "row": weights row-split over all GPUs (ggml_backend_split_buffer_type), "none": main GPU only
+        if (!strcmp(sm, "row")) mp.split_mode = LLAMA_SPLIT_MODE_ROW;
+        else if (!strcmp(sm, "none")) mp.split_mode = LLAMA_SPLIT_MODE_NONE;
+    }
     llama_model *model = llama_model_load_from_file(model_path, mp);
     if (!model) return 1;
     llama_context_params cp = llama_context_default_params();

@@ -155,3 +155,27 @@ def test_no_cpu_fallback_splits():
     bad = [ln for ln in node_lines if "GET_ROWS" not in ln]
     print("SPLITS", len(split_lines), "cpu", len(cpu_splits), "cpu nodes not get_rows:", len(bad))
     assert not bad, bad[:5]
+
+
+def test_split_mode_row_through_llama_cpp_matches_reference():
+    """tensor parallelism behind the reference's own API: llama.cpp's --split-mode row asks the backend registry for
+    `ggml_backend_split_buffer_type` (llama-model.cpp:326-355), allocates the weight matrices in it, and MUL_MAT on a row-split weight
+    runs on every GPU at once (mulmat.cu op_mul_mat_split).  Every dst element is produced by the same kernels as on one GPU, so in
+    the parity mode the logits stay BIT-IDENTICAL to the reference CPU backend.  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    need_tools()
+    gguf = gguf_for("llama3-8b", "q4_k_m", 2)
+    cpu, _, _ = dump(gguf, "split_cpu", 0, N_PROMPT, 24, "q8_0", False, 10)
+    env = {"GGML_B200_CPU_EXACT": "1", "LOGITS_DUMP_SPLIT_MODE": "row"}
+    gpu, _, err = dump(gguf, "split_gpu", 99, N_PROMPT, 24, "q8_0", False, 10, env)
+    assert "_Split" in err, "llama.cpp did not allocate the weights in the split buffer type:\n" + err[-1500:]
+    rel = rel_err(cpu, gpu)
+    print("PARITY split-mode row (2 GPUs) max_rel_err", float(rel.max()))
+    assert np.array_equal(cpu, gpu), float(rel.max())
+    # fast mode: same envelope as on one GPU
+    fast, _, _ = dump(gguf, "split_fast", 99, N_PROMPT, 24, "q8_0", False, 10, {"LOGITS_DUMP_SPLIT_MODE": "row"})
+    one, _, _ = dump(gguf, "split_one", 99, N_PROMPT, 24, "q8_0", False, 10, {"LOGITS_DUMP_SPLIT_MODE": "none"})
+    assert rel_err(cpu, fast).max() <= 5e-2
+    assert np.array_equal(fast, one), "row-split fast mode must equal the single-GPU fast mode (same kernels per dst element)"
