@@ -299,7 +299,7 @@ def main():
     ctx.set_option("debug_skip", 0)
     achieved = alg / (k_ms / 1e3) / 1e9
     traffic = None
-    tp_file = os.path.join(ROOT, "profiles", "r1_ncu_bs1_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+    tp_file = os.path.join(ROOT, "profiles", "r2_ncu_bs1_traffic.json")      # dram bytes per launch, all 129 GEMV launches of a step (committed ncu capture: same population as algorithmic_bytes_per_launch_avg)
     if os.path.exists(tp_file):
         try:
             traffic = json.load(open(tp_file))["dram_bytes_per_launch_avg"]
@@ -434,9 +434,15 @@ def batch_legs(a, b200, lg, L, ctx, local, peak):
         bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
     except Exception:
         pass
+    i8_peak, i8_note = 2 * bf16, "2 x measured bf16 burst (no int8 number in MEASURED_PEAKS.json)"
+    try:                                     # measured on this pool's B200 with a bare tcgen05.mma kind::i8 loop (tools/micro/i8_peak.cu)
+        i8_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r2_i8_peak.json")))["int8_tops"])
+        i8_note = "measured: bare tcgen05.mma kind::i8 loop, 148 CTAs (profiles/r2_i8_peak.txt)"
+    except Exception:
+        pass
     out["prefill_pp512"] = {"value": PP / (ms / 1e3), "unit": "tok/s", "ms_per_ubatch": ms, "gpu_launches_per_ubatch": launches, "flops_per_ubatch": flops,
-                            "achieved_tops": flops / (ms / 1e3) / 1e12, "peak_tops": 2 * bf16, "peak_note": "2 x measured bf16 burst (no int8 number in MEASURED_PEAKS.json)",
-                            "tensor_frac": flops / (ms / 1e3) / 1e12 / (2 * bf16),
+                            "achieved_tops": flops / (ms / 1e3) / 1e12, "peak_tops": i8_peak, "peak_note": i8_note,
+                            "tensor_frac": flops / (ms / 1e3) / 1e12 / i8_peak,
                             "assert_finite": bool(torch.isfinite(g.logits[:g.V]).all().item())}
     g.keep.clear(); g.layers.clear()
     torch.cuda.empty_cache()

@@ -201,9 +201,16 @@ __device__ __forceinline__ void convert_half(const uint8_t *blk, int h, int r, u
             }
         }
     } else {
-        // Q6_K: half h = elements [128h, 128h+128): ql[64h..64h+63], qh[32h..32h+31], scales[8h..8h+7] (ggml-quants.c:1690-1719)
+        // Q6_K: half h = elements [128h, 128h+128): ql[64h..64h+63], qh[32h..32h+31], scales[8h..8h+7] (ggml-quants.c:1690-1719).
+        // Signed quants v = q - 32 in [-32, 31] times the int8 scale: a = sc * v in [-4064, 4096] = 128 * hi + lo with lo in [0, 127] and
+        // hi = a >> 7 in [-32, 32]: the CPU's integer sum_j scale_j * sum (q - 32) a comes out of the tensor core directly, no offset term.
+        // Word-wise: 4 elements per 32-bit word of ql / qh (blocks are only 2-byte aligned: 16-bit loads).
         const uint8_t *ql = blk + 64 * h, *qh = blk + 128 + 32 * h;
         const int8_t *scp = (const int8_t *)(blk + 192 + 8 * h);
+        auto ld32 = [](const uint8_t *p) { return (uint32_t)*(const unsigned short *)p | ((uint32_t)*(const unsigned short *)(p + 2) << 16); };
+        uint32_t qhw[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) qhw[i] = ld32(qh + 4 * i);
 #pragma unroll
         for (int t = 0; t < 4; t++) {                         // quadrant t: elements 32t .. 32t+31 of the half
 #pragma unroll
@@ -212,17 +219,15 @@ __device__ __forceinline__ void convert_half(const uint8_t *blk, int h, int r, u
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int wd = 0; wd < 4; wd++) {
-                    uint32_t hw = 0, lw = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int l = 16 * c16 + 4 * wd + e;                       // 0..31
-                        const int lb = ql[l + 32 * (t & 1)];
-                        const int q = ((t < 2 ? lb & 0x0f : lb >> 4) | (((qh[l] >> (2 * t)) & 3) << 4));     // 0..63 (offset -32 handled in the epilogue)
-                        const int a = sc * q;                                      // [-8064, 8001]
-                        hw |= (uint32_t)((a >> 7) & 0xff) << (8 * e);
-                        lw |= (uint32_t)(a & 127) << (8 * e);
-                    }
-                    hi[wd] = hw; lo[wd] = lw;
+                    const int l = 16 * c16 + 4 * wd;          // byte index 0..31 inside the quadrant
+                    const uint32_t lw = ld32(ql + l + 32 * (t & 1));
+                    const uint32_t q4 = ((t < 2 ? lw : lw >> 4) & 0x0f0f0f0fu) | (((qhw[l >> 2] >> (2 * t)) & 0x03030303u) << 4);    // 4 x (0..63)
+                    // two 16-bit lanes per multiply: (q - 32) * sc as signed 16-bit lanes of a 32-bit product is not carry-free, so go through
+                    // the unsigned product and subtract 32 * sc per lane: a = q * sc - 32 * sc, each lane handled as a signed 16-bit value
+                    const int e0 = (int)(q4 & 0xffu) * sc - 32 * sc, e1 = (int)((q4 >> 8) & 0xffu) * sc - 32 * sc;
+                    const int e2 = (int)((q4 >> 16) & 0xffu) * sc - 32 * sc, e3 = (int)(q4 >> 24) * sc - 32 * sc;
+                    hi[wd] = (uint32_t)((e0 >> 7) & 0xff) | (uint32_t)((e1 >> 7) & 0xff) << 8 | (uint32_t)((e2 >> 7) & 0xff) << 16 | (uint32_t)((e3 >> 7) & 0xff) << 24;
+                    lo[wd] = (uint32_t)(e0 & 127) | (uint32_t)(e1 & 127) << 8 | (uint32_t)(e2 & 127) << 16 | (uint32_t)(e3 & 127) << 24;
                 }
                 const int k0 = 32 * t + 16 * c16;
                 *(uint4 *)(a_hi + canon_off(r, k0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
             tc_fence_after();
             const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
             const size_t rowb = (size_t)b * p.Mpad + tok0;
-            const float dd = m.d, dm = m.dmin;
+            const float dd = m.d, ndm = -m.dmin;
 #pragma unroll
             for (int c0 = 0; c0 < TN; c0 += 32) {
                 if (PARTIAL && c0 > last_c0) continue;     // token columns beyond M (a 32-slot decode ubatch fills a quarter of the tile)
@@ -376,20 +381,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) b200_gemm_i8_kernel(const Gem
                     int P = ((int)hi[j] << 7) + (int)lo[j];
                     const float da = __ldg(Bdv + rowb + c);
                     if (TYPE == B200_TYPE_Q6_K) {
-                        const uint4 s0 = __ldg((const uint4 *)(Bs16v + (rowb + c) * 16)), s1 = __ldg((const uint4 *)(Bs16v + (rowb + c) * 16 + 8));
-                        int off = 0;
-                        off = dp2a_lo_(s0.x, m.sc[0], off); off = dp2a_hi_(s0.y, m.sc[0], off);
-                        off = dp2a_lo_(s0.z, m.sc[1], off); off = dp2a_hi_(s0.w, m.sc[1], off);
-                        off = dp2a_lo_(s1.x, m.sc[2], off); off = dp2a_hi_(s1.y, m.sc[2], off);
-                        off = dp2a_lo_(s1.z, m.sc[3], off); off = dp2a_hi_(s1.w, m.sc[3], off);
-                        P -= 32 * off;                      // sum scale_j * sum (q-32) a  ==  sum scale_j q a - 32 sum scale_j bsum_j
-                        out[c] += (dd * da) * (float)P;
+                        out[c] = fmaf(dd * da, (float)P, out[c]);          // signed quants: no offset term (convert_half)
                     } else {
                         const uint4 s = __ldg((const uint4 *)(Bs32v + (rowb + c) * 8));
                         int Mv = 0;
                         Mv = dp2a_lo_(s.x, m.m0123, Mv); Mv = dp2a_hi_(s.y, m.m0123, Mv);
                         Mv = dp2a_lo_(s.z, m.m4567, Mv); Mv = dp2a_hi_(s.w, m.m4567, Mv);
-                        out[c] += (dd * da) * (float)P - (dm * da) * (float)Mv;
+                        out[c] = fmaf(da, fmaf(dd, (float)P, ndm * (float)Mv), out[c]);
                     }
                 }
             }

@@ -85,6 +85,11 @@ int main(int argc, char **argv) {
             const int j = batch.n_tokens++;
             batch.token[j] = next(); batch.pos[j] = i; batch.n_seq_id[j] = 1; batch.seq_id[j][0] = p; batch.logits[j] = !bench || i == n_prompt - 1;
         }
+    if (bench && n_warm > 0) {            // like llama-bench: one untimed pass first (module load, first-use allocations), then an empty cache again
+        if (llama_decode(ctx, batch) != 0) { fprintf(stderr, "prefill warm-up failed\n"); return 1; }
+        llama_synchronize(ctx);
+        llama_kv_self_clear(ctx);
+    }
     double t0 = now_ms();
     if (llama_decode(ctx, batch) != 0) { fprintf(stderr, "prefill decode failed\n"); return 1; }
     llama_synchronize(ctx);
