@@ -611,6 +611,15 @@ extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) 
             b200_set_error("graph op %d (id %d) not supported", i, ops[i].op);
             return B200_ERR_UNSUPPORTED;
         }
+    if (g_fuse_debug >= 2) {                 // op list as the backend received it (one line per op: id, dst shape, src0 shape)
+        static int dumped = 0;
+        if (dumped++ < 3)
+            for (int i = 0; i < n_ops && i < 64; i++)
+                fprintf(stderr, "[b200 ops] %3d op=%2d dst=[%lld,%lld,%lld] t%d src0=[%lld,%lld,%lld] t%d src1=[%lld,%lld,%lld] t%d\n", i, ops[i].op,
+                        (long long)ops[i].dst.ne[0], (long long)ops[i].dst.ne[1], (long long)ops[i].dst.ne[2], ops[i].dst.type,
+                        (long long)ops[i].src[0].ne[0], (long long)ops[i].src[0].ne[1], (long long)ops[i].src[0].ne[2], ops[i].src[0].type,
+                        (long long)ops[i].src[1].ne[0], (long long)ops[i].src[1].ne[1], (long long)ops[i].src[1].ne[2], ops[i].src[1].type);
+    }
     std::vector<ExecNode> list;
     if (ctx->opt_fusion) { int frc = fuse(ctx, ops, n_ops, list); if (frc) return frc; }
     else { list.resize(n_ops); for (int i = 0; i < n_ops; i++) list[i].op = ops[i]; }

@@ -8,7 +8,7 @@ for cfg in "llama3-8b q4_k_m f16" "llama3-8b q4_k_m q8_0" "tinyllama q4_0 f16" "
   G=/tmp/rc_$1_$2.gguf
   [ -f $G ] || python tools/make_gguf.py --model $1 --ftype $2 --out $G 2>/dev/null
   for be in cuda b200; do
-    if [ $be = cuda ]; then export GGML_BACKEND_PATH=$PWD/oracle/_ref/libggml-cuda.so; else export GGML_BACKEND_PATH=$PWD/cortex.llamacpp_b200/libggml-b200.so; fi
+    if [ $be = cuda ]; then export GGML_BACKEND_PATH=$PWD/oracle/_ref/cuda/libggml-cuda.so; else export GGML_BACKEND_PATH=$PWD/cortex.llamacpp_b200/libggml-b200.so; fi
     R=$(LOGITS_DUMP_WARMUP=4 GGML_B200_GRAPHS=1 timeout 600 ./oracle/_ref/logits_dump $G - 99 512 64 $3 1 4 2>/tmp/err.txt | grep "^{" | tail -1)
     [ -z "$R" ] && R="FAILED: $(tail -3 /tmp/err.txt | tr '\n' ' ')"
     echo "$1 $2 kv=$3 backend=$be $R" | tee -a $OUT
