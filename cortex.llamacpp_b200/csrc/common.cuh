@@ -211,6 +211,10 @@ int launch_gemv(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int
 bool gemv_mma_supported(int type, int64_t N, int64_t K, int64_t M);
 int launch_gemv_mma(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, int ncols,
                     float *dst, size_t dst_stride, bool stream_once, bool w_const, const float *residual = nullptr);
+// prompt-batch GEMM on mma.sync s8 for all five formats (gemm_mma.cu)
+bool gemm_mma_supported(int type, int64_t N, int64_t K, int64_t M);
+int gemm_mma_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, int64_t M, float *dst,
+                 size_t dst_stride);
 // MUL_MAT_ID routing tables built on the device (mulmat.cu) for the grouped small-batch kernel
 struct MmGroupDesc {
     const int32_t *off, *pairs;          // [E + 1] first pair of every expert; pair ids (token * n_used + slot) sorted by expert

@@ -254,6 +254,21 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     // continuous-batching decode (9..32 columns): weight-streaming mma.sync kernel (gemv_mma.cu); q4_0 / q8_0, which the tcgen05
     // GEMM does not decode, go through it in chunks of 32 columns at any batch size
     static const int64_t mma_max_m = getenv("GGML_B200_MMA_MAX_M") ? atoi(getenv("GGML_B200_MMA_MAX_M")) : 32;
+    // prompt batches: the mma.sync tile GEMM (gemm_mma.cu, all five formats); GGML_B200_PREFER_TCGEN05=1 sends K-quants to the tcgen05
+    // GEMM instead (gemm_i8.cu: correct, but its CUDA-core stages keep it below the mma.sync kernel -- DESIGN.md 8)
+    static const int prefer_tc = getenv("GGML_B200_PREFER_TCGEN05") ? atoi(getenv("GGML_B200_PREFER_TCGEN05")) : 0;
+    if (M > mma_max_m && gemm_mma_supported(w.type, N, K, M) && !(prefer_tc && gemm_i8_supported(w.type, N, K, M))) {
+        for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+                const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+                const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+                const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+                float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+                int rc = gemm_mma_run(ctx, w.type, wp, rb, N, K, xp, x.nb[1], M, dp, d.nb[1] / 4);
+                if (rc) return rc;
+            }
+        return B200_OK;
+    }
     if (gemv_mma_supported(w.type, N, K, M) && (M <= mma_max_m || !gemm_i8_supported(w.type, N, K, M))) {
         uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)M);
         if (!act) return B200_ERR_ALLOC;
