@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
 
     if (warp == 2 * MM_MAX_STAGES) {
         // ---------------------------------------------------------------- producer: lane l < 16 copies row l of every unit
-        if (lane < ns) { mbar_init(&full[lane], 1); mbar_init(&empty[lane], 2); }
+        if (lane < ns) { mbar_init(&full[lane], 32); mbar_init(&empty[lane], 2); }
         if (lane == 0) mbar_init(act_full, 1);
         mbar_fence_init();
         __syncwarp();
@@ -288,15 +288,18 @@ __global__ void __launch_bounds__(MM_THREADS, 1) b200_gemv_mma_kernel(const MmPa
         for (int u = 0; u < nunits; u++) {
             const int st = u % ns, use = u / ns;
             if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-            const uint8_t *src = Wb + (size_t)((t0 + u) * MM_ROWS + (lane & 15)) * p.rb + (size_t)r * MM_KB * p.bbytes;
-            const uint32_t extra = (uint32_t)((uintptr_t)src & 15);
-            const uint32_t bytes = (extra + piece + 15u) & ~15u;
-            uint32_t total = lane < 16 ? bytes : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            if (lane == 0) mbar_arrive_expect_tx(&full[st], total);
-            __syncwarp();
-            if (lane < 16) bulk_g2s_hint(ring + (size_t)st * p.stage_bytes + (size_t)lane * p.rstride, src - extra, bytes, &full[st], pol);
+            // 16 row pieces of ~1-2 KB: 16-byte cp.async chunks (two lanes per row) completing on the stage's mbarrier.  One bulk copy per
+            // piece costs ~60 ns of TMA issue each -- 1 us per 18 KB stage, a 2.7 TB/s ceiling for the whole chip (profiles/r2_ncu_summaries.md)
+            {
+                const uint8_t *src = Wb + (size_t)((t0 + u) * MM_ROWS + (lane >> 1)) * p.rb + (size_t)r * MM_KB * p.bbytes;
+                const uint32_t extra = (uint32_t)((uintptr_t)src & 15);
+                const int nch = (int)((extra + piece + 15u) >> 4);
+                const uint32_t dsts = smem_u32(ring + (size_t)st * p.stage_bytes + (size_t)(lane >> 1) * p.rstride);
+                src -= extra;
+                for (int ch = lane & 1; ch < nch; ch += 2)
+                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dsts + ch * 16), "l"(src + ch * 16), "l"(pol) : "memory");
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[st])) : "memory");
+            }
             if (u == min(ns, nunits) - 1) {
                 // the weight ring is full: now the activations of this K-range (written by the previous kernel), one bulk copy per column
                 if (p.use_pdl) pdl_wait();

@@ -15,3 +15,4 @@ run() { # model ftype kv npar nprompt ngen
 }
 run llama3-8b q4_k_m q8_0 32 64 32
 
+run mixtral q4_k_m f16 1 512 32
