@@ -87,6 +87,186 @@ __global__ void __launch_bounds__(256) b200_gemm_mma_pack_kernel(const float *__
     *(uint2 *)(im + (size_t)t * G_BSTRIDE + lane * 8) = qp;
 }
 
+// one 256-k super-block of a warp tile: 2 m-tiles (rows R, R+8 of each from rowp[mt][h], raw GGUF block bytes) x NTW n-tiles of 8 tokens
+// starting at token `tokbase` of the stage image (b_lane: this lane's ldmatrix address, bd / bs: block scales and per-32 sums)
+template <int TYPE, int NTW>
+__device__ __forceinline__ void sb_compute(const uint8_t *const (&rowp)[2][2], uint32_t b_lane, const float *bd, const int16_t *bs, int tokbase, int lane,
+                                           float (&out)[2][NTW][4]) {
+    const int kq = (lane & 3) * 4, cq = (lane & 3) * 2;
+    if (TYPE == B200_TYPE_Q4_K || TYPE == B200_TYPE_Q5_K) {
+        int P[2][NTW][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NTW; nt++) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0;
+        uint32_t sc_lo[2][2], sc_hi[2][2], mn_lo[2][2], mn_hi[2][2];
+        float dd[2][2], dm[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint4 hd = *(const uint4 *)rowp[mt][h];
+                sc_lo[mt][h] = hd.y & 0x3f3f3f3fu; mn_lo[mt][h] = hd.z & 0x3f3f3f3fu;
+                sc_hi[mt][h] = (hd.w & 0x0f0f0f0fu) | ((hd.y >> 2) & 0x30303030u);
+                mn_hi[mt][h] = ((hd.w >> 4) & 0x0f0f0f0fu) | ((hd.z >> 2) & 0x30303030u);
+                dd[mt][h] = hf(hd.x); dm[mt][h] = -hf(hd.x >> 16);
+            }
+        constexpr int QO = TYPE == B200_TYPE_Q5_K ? 48 : 16;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t w[2][2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    w[mt][h][0] = *(const uint32_t *)(rowp[mt][h] + QO + 32 * g + kq);
+                    w[mt][h][1] = *(const uint32_t *)(rowp[mt][h] + QO + 32 * g + 16 + kq);
+                }
+#pragma unroll
+            for (int sub = 0; sub < 2; sub++) {
+                const int j = 2 * g + sub;
+                uint32_t a[2][4]; int s[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        uint32_t x0 = sub ? (w[mt][h][0] >> 4) & 0x0f0f0f0fu : w[mt][h][0] & 0x0f0f0f0fu;
+                        uint32_t x1 = sub ? (w[mt][h][1] >> 4) & 0x0f0f0f0fu : w[mt][h][1] & 0x0f0f0f0fu;
+                        if (TYPE == B200_TYPE_Q5_K) {
+                            const uint32_t hb0 = *(const uint32_t *)(rowp[mt][h] + 16 + kq), hb1 = *(const uint32_t *)(rowp[mt][h] + 32 + kq);
+                            x0 |= ((hb0 >> j) & 0x01010101u) << 4; x1 |= ((hb1 >> j) & 0x01010101u) << 4;
+                        }
+                        a[mt][h] = x0; a[mt][2 + h] = x1;
+                        s[mt][h] = (int)(((j < 4 ? sc_lo[mt][h] : sc_hi[mt][h]) >> (8 * (j & 3))) & 0xffu);
+                    }
+                }
+#pragma unroll
+                for (int np = 0; np < NTW / 2; np++) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm4(b0, b1, b2, b3, b_lane + (uint32_t)(np * 16) * G_BSTRIDE + (uint32_t)(j * 32));
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        int c[4];
+                        imma32(c, a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                        P[mt][2 * np][0] += s[mt][0] * c[0]; P[mt][2 * np][1] += s[mt][0] * c[1]; P[mt][2 * np][2] += s[mt][1] * c[2]; P[mt][2 * np][3] += s[mt][1] * c[3];
+                        imma32(c, a[mt][0], a[mt][1], a[mt][2], a[mt][3], b2, b3);
+                        P[mt][2 * np + 1][0] += s[mt][0] * c[0]; P[mt][2 * np + 1][1] += s[mt][0] * c[1]; P[mt][2 * np + 1][2] += s[mt][1] * c[2]; P[mt][2 * np + 1][3] += s[mt][1] * c[3];
+                    }
+                }
+            }
+        }
+        // fold the super-block: out += da * (d * P - dmin * M), M = sum_j m_j * (sum of the token's quants over sub-block j)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int tok = tokbase + nt * 8 + cq + cc;
+                const uint4 sv = *(const uint4 *)(bs + tok * 8);
+                const float da = bd[tok];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        int Mv = __dp2a_lo((int)sv.x, (int)mn_lo[mt][h], 0); Mv = __dp2a_hi((int)sv.y, (int)mn_lo[mt][h], Mv);
+                        Mv = __dp2a_lo((int)sv.z, (int)mn_hi[mt][h], Mv); Mv = __dp2a_hi((int)sv.w, (int)mn_hi[mt][h], Mv);
+                        out[mt][nt][2 * h + cc] = fmaf(da, fmaf(dd[mt][h], (float)P[mt][nt][2 * h + cc], dm[mt][h] * (float)Mv), out[mt][nt][2 * h + cc]);
+                    }
+            }
+    } else if (TYPE == B200_TYPE_Q6_K) {
+        int P[2][NTW][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NTW; nt++) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int j = 4 * hh + t;
+                uint32_t a[2][4]; int sA[2][2], sB[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint8_t *bp = rowp[mt][h];
+                        const uint32_t l0 = lds2(bp + 64 * hh + 32 * (t & 1) + kq), l1 = lds2(bp + 64 * hh + 32 * (t & 1) + 16 + kq);
+                        const uint32_t q0 = lds2(bp + 128 + 32 * hh + kq), q1 = lds2(bp + 128 + 32 * hh + 16 + kq);
+                        a[mt][h]     = __vsub4(((t < 2 ? l0 : l0 >> 4) & 0x0f0f0f0fu) | (((q0 >> (2 * t)) & 0x03030303u) << 4), 0x20202020u);
+                        a[mt][2 + h] = __vsub4(((t < 2 ? l1 : l1 >> 4) & 0x0f0f0f0fu) | (((q1 >> (2 * t)) & 0x03030303u) << 4), 0x20202020u);
+                        sA[mt][h] = (int)(int8_t)bp[192 + 2 * j]; sB[mt][h] = (int)(int8_t)bp[193 + 2 * j];
+                    }
+#pragma unroll
+                for (int np = 0; np < NTW / 2; np++) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm4(b0, b1, b2, b3, b_lane + (uint32_t)(np * 16) * G_BSTRIDE + (uint32_t)(j * 32));
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        int c[4], e[4];
+                        imma16(c, a[mt][0], a[mt][1], b0); imma16(e, a[mt][2], a[mt][3], b1);
+                        P[mt][2 * np][0] += sA[mt][0] * c[0] + sB[mt][0] * e[0]; P[mt][2 * np][1] += sA[mt][0] * c[1] + sB[mt][0] * e[1];
+                        P[mt][2 * np][2] += sA[mt][1] * c[2] + sB[mt][1] * e[2]; P[mt][2 * np][3] += sA[mt][1] * c[3] + sB[mt][1] * e[3];
+                        imma16(c, a[mt][0], a[mt][1], b2); imma16(e, a[mt][2], a[mt][3], b3);
+                        P[mt][2 * np + 1][0] += sA[mt][0] * c[0] + sB[mt][0] * e[0]; P[mt][2 * np + 1][1] += sA[mt][0] * c[1] + sB[mt][0] * e[1];
+                        P[mt][2 * np + 1][2] += sA[mt][1] * c[2] + sB[mt][1] * e[2]; P[mt][2 * np + 1][3] += sA[mt][1] * c[3] + sB[mt][1] * e[3];
+                    }
+                }
+            }
+        }
+        float dd[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) dd[mt][h] = hf(*(const unsigned short *)(rowp[mt][h] + 208));
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const float da = bd[tokbase + nt * 8 + cq + cc];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) out[mt][nt][2 * h + cc] = fmaf(dd[mt][h] * da, (float)P[mt][nt][2 * h + cc], out[mt][nt][2 * h + cc]);
+            }
+    } else {
+        // q4_0 (18 B) / q8_0 (34 B) blocks of 32: one float scale per (row, block) and per (token, block)
+        constexpr int SB = TYPE == B200_TYPE_Q4_0 ? 18 : 34;
+#pragma unroll 2
+        for (int j = 0; j < 8; j++) {
+            uint32_t a[2][4]; float dw[2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint8_t *bp = rowp[mt][h] + j * SB;
+                    dw[mt][h] = hf(*(const unsigned short *)bp);
+                    if (TYPE == B200_TYPE_Q4_0) {
+                        const uint32_t wv = lds2(bp + 2 + kq);
+                        a[mt][h] = __vsub4(wv & 0x0f0f0f0fu, 0x08080808u); a[mt][2 + h] = __vsub4((wv >> 4) & 0x0f0f0f0fu, 0x08080808u);
+                    } else {
+                        a[mt][h] = lds2(bp + 2 + kq); a[mt][2 + h] = lds2(bp + 18 + kq);
+                    }
+                }
+#pragma unroll
+            for (int np = 0; np < NTW / 2; np++) {
+                uint32_t b0, b1, b2, b3;
+                ldsm4(b0, b1, b2, b3, b_lane + (uint32_t)(np * 16) * G_BSTRIDE + (uint32_t)(j * 32));
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int nt = 2 * np + q;
+                    const float da0 = bd[(tokbase + nt * 8 + cq) * 8 + j], da1 = bd[(tokbase + nt * 8 + cq + 1) * 8 + j];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        int c[4];
+                        imma32(c, a[mt][0], a[mt][1], a[mt][2], a[mt][3], q ? b2 : b0, q ? b3 : b1);
+                        out[mt][nt][0] = fmaf((float)c[0], dw[mt][0] * da0, out[mt][nt][0]); out[mt][nt][1] = fmaf((float)c[1], dw[mt][0] * da1, out[mt][nt][1]);
+                        out[mt][nt][2] = fmaf((float)c[2], dw[mt][1] * da0, out[mt][nt][2]); out[mt][nt][3] = fmaf((float)c[3], dw[mt][1] * da1, out[mt][nt][3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------- the GEMM
 template <int TYPE>
 __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GParams p) {
@@ -136,7 +316,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GPara
     };
     // ---------------------------------------------------------------- consumers: warp (wm, wn) owns rows wm*32.. (2 m-tiles) x tokens wn*64.. (8 n-tiles)
     const int wm = warp & 3, wn = warp >> 2;
-    const int R = lane >> 2, kq = (lane & 3) * 4, cq = (lane & 3) * 2;
+    const int R = lane >> 2, cq = (lane & 3) * 2;
     int it = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         const int ks = item % p.ksplit, rt = (item / p.ksplit) % p.nrt, tt = item / (p.ksplit * p.nrt);
@@ -166,178 +346,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GPara
                     const uintptr_t g = (uintptr_t)(p.W + (size_t)(rt * GT_M + r) * p.rb + (size_t)b * p.bbytes);
                     rowp[mt][h] = stage + (size_t)r * p.rstride + (g & 15);
                 }
-            if (TYPE == B200_TYPE_Q4_K || TYPE == B200_TYPE_Q5_K) {
-                int P[2][8][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0;
-                uint32_t sc_lo[2][2], sc_hi[2][2], mn_lo[2][2], mn_hi[2][2];
-                float dd[2][2], dm[2][2];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint4 hd = *(const uint4 *)rowp[mt][h];
-                        sc_lo[mt][h] = hd.y & 0x3f3f3f3fu; mn_lo[mt][h] = hd.z & 0x3f3f3f3fu;
-                        sc_hi[mt][h] = (hd.w & 0x0f0f0f0fu) | ((hd.y >> 2) & 0x30303030u);
-                        mn_hi[mt][h] = ((hd.w >> 4) & 0x0f0f0f0fu) | ((hd.z >> 2) & 0x30303030u);
-                        dd[mt][h] = hf(hd.x); dm[mt][h] = -hf(hd.x >> 16);
-                    }
-                constexpr int QO = TYPE == B200_TYPE_Q5_K ? 48 : 16;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    uint32_t w[2][2][2];
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            w[mt][h][0] = *(const uint32_t *)(rowp[mt][h] + QO + 32 * g + kq);
-                            w[mt][h][1] = *(const uint32_t *)(rowp[mt][h] + QO + 32 * g + 16 + kq);
-                        }
-#pragma unroll
-                    for (int sub = 0; sub < 2; sub++) {
-                        const int j = 2 * g + sub;
-                        uint32_t a[2][4]; int s[2][2];
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++) {
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                uint32_t x0 = sub ? (w[mt][h][0] >> 4) & 0x0f0f0f0fu : w[mt][h][0] & 0x0f0f0f0fu;
-                                uint32_t x1 = sub ? (w[mt][h][1] >> 4) & 0x0f0f0f0fu : w[mt][h][1] & 0x0f0f0f0fu;
-                                if (TYPE == B200_TYPE_Q5_K) {
-                                    const uint32_t hb0 = *(const uint32_t *)(rowp[mt][h] + 16 + kq), hb1 = *(const uint32_t *)(rowp[mt][h] + 32 + kq);
-                                    x0 |= ((hb0 >> j) & 0x01010101u) << 4; x1 |= ((hb1 >> j) & 0x01010101u) << 4;
-                                }
-                                a[mt][h] = x0; a[mt][2 + h] = x1;
-                                s[mt][h] = (int)(((j < 4 ? sc_lo[mt][h] : sc_hi[mt][h]) >> (8 * (j & 3))) & 0xffu);
-                            }
-                        }
-#pragma unroll
-                        for (int np = 0; np < 4; np++) {
-                            uint32_t b0, b1, b2, b3;
-                            ldsm4(b0, b1, b2, b3, b_lane + (uint32_t)(np * 16) * G_BSTRIDE + (uint32_t)(j * 32));
-#pragma unroll
-                            for (int mt = 0; mt < 2; mt++) {
-                                int c[4];
-                                imma32(c, a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
-                                P[mt][2 * np][0] += s[mt][0] * c[0]; P[mt][2 * np][1] += s[mt][0] * c[1]; P[mt][2 * np][2] += s[mt][1] * c[2]; P[mt][2 * np][3] += s[mt][1] * c[3];
-                                imma32(c, a[mt][0], a[mt][1], a[mt][2], a[mt][3], b2, b3);
-                                P[mt][2 * np + 1][0] += s[mt][0] * c[0]; P[mt][2 * np + 1][1] += s[mt][0] * c[1]; P[mt][2 * np + 1][2] += s[mt][1] * c[2]; P[mt][2 * np + 1][3] += s[mt][1] * c[3];
-                            }
-                        }
-                    }
-                }
-                // fold the super-block: out += da * (d * P - dmin * M), M = sum_j m_j * (sum of the token's quants over sub-block j)
-#pragma unroll
-                for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-                    for (int cc = 0; cc < 2; cc++) {
-                        const int tok = wn * 64 + nt * 8 + cq + cc;
-                        const uint4 sv = *(const uint4 *)(bs + tok * 8);
-                        const float da = bd[tok];
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                int Mv = __dp2a_lo((int)sv.x, (int)mn_lo[mt][h], 0); Mv = __dp2a_hi((int)sv.y, (int)mn_lo[mt][h], Mv);
-                                Mv = __dp2a_lo((int)sv.z, (int)mn_hi[mt][h], Mv); Mv = __dp2a_hi((int)sv.w, (int)mn_hi[mt][h], Mv);
-                                out[mt][nt][2 * h + cc] = fmaf(da, fmaf(dd[mt][h], (float)P[mt][nt][2 * h + cc], dm[mt][h] * (float)Mv), out[mt][nt][2 * h + cc]);
-                            }
-                    }
-            } else if (TYPE == B200_TYPE_Q6_K) {
-                int P[2][8][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0;
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const int j = 4 * hh + t;
-                        uint32_t a[2][4]; int sA[2][2], sB[2][2];
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                const uint8_t *bp = rowp[mt][h];
-                                const uint32_t l0 = lds2(bp + 64 * hh + 32 * (t & 1) + kq), l1 = lds2(bp + 64 * hh + 32 * (t & 1) + 16 + kq);
-                                const uint32_t q0 = lds2(bp + 128 + 32 * hh + kq), q1 = lds2(bp + 128 + 32 * hh + 16 + kq);
-                                a[mt][h]     = __vsub4(((t < 2 ? l0 : l0 >> 4) & 0x0f0f0f0fu) | (((q0 >> (2 * t)) & 0x03030303u) << 4), 0x20202020u);
-                                a[mt][2 + h] = __vsub4(((t < 2 ? l1 : l1 >> 4) & 0x0f0f0f0fu) | (((q1 >> (2 * t)) & 0x03030303u) << 4), 0x20202020u);
-                                sA[mt][h] = (int)(int8_t)bp[192 + 2 * j]; sB[mt][h] = (int)(int8_t)bp[193 + 2 * j];
-                            }
-#pragma unroll
-                        for (int np = 0; np < 4; np++) {
-                            uint32_t b0, b1, b2, b3;
-                            ldsm4(b0, b1, b2, b3, b_lane + (uint32_t)(np * 16) * G_BSTRIDE + (uint32_t)(j * 32));
-#pragma unroll
-                            for (int mt = 0; mt < 2; mt++) {
-                                int c[4], e[4];
-                                imma16(c, a[mt][0], a[mt][1], b0); imma16(e, a[mt][2], a[mt][3], b1);
-                                P[mt][2 * np][0] += sA[mt][0] * c[0] + sB[mt][0] * e[0]; P[mt][2 * np][1] += sA[mt][0] * c[1] + sB[mt][0] * e[1];
-                                P[mt][2 * np][2] += sA[mt][1] * c[2] + sB[mt][1] * e[2]; P[mt][2 * np][3] += sA[mt][1] * c[3] + sB[mt][1] * e[3];
-                                imma16(c, a[mt][0], a[mt][1], b2); imma16(e, a[mt][2], a[mt][3], b3);
-                                P[mt][2 * np + 1][0] += sA[mt][0] * c[0] + sB[mt][0] * e[0]; P[mt][2 * np + 1][1] += sA[mt][0] * c[1] + sB[mt][0] * e[1];
-                                P[mt][2 * np + 1][2] += sA[mt][1] * c[2] + sB[mt][1] * e[2]; P[mt][2 * np + 1][3] += sA[mt][1] * c[3] + sB[mt][1] * e[3];
-                            }
-                        }
-                    }
-                }
-                float dd[2][2];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int h = 0; h < 2; h++) dd[mt][h] = hf(*(const unsigned short *)(rowp[mt][h] + 208));
-#pragma unroll
-                for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-                    for (int cc = 0; cc < 2; cc++) {
-                        const float da = bd[wn * 64 + nt * 8 + cq + cc];
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                            for (int h = 0; h < 2; h++) out[mt][nt][2 * h + cc] = fmaf(dd[mt][h] * da, (float)P[mt][nt][2 * h + cc], out[mt][nt][2 * h + cc]);
-                    }
-            } else {
-                // q4_0 (18 B) / q8_0 (34 B) blocks of 32: one float scale per (row, block) and per (token, block)
-                constexpr int SB = TYPE == B200_TYPE_Q4_0 ? 18 : 34;
-#pragma unroll 2
-                for (int j = 0; j < 8; j++) {
-                    uint32_t a[2][4]; float dw[2][2];
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const uint8_t *bp = rowp[mt][h] + j * SB;
-                            dw[mt][h] = hf(*(const unsigned short *)bp);
-                            if (TYPE == B200_TYPE_Q4_0) {
-                                const uint32_t wv = lds2(bp + 2 + kq);
-                                a[mt][h] = __vsub4(wv & 0x0f0f0f0fu, 0x08080808u); a[mt][2 + h] = __vsub4((wv >> 4) & 0x0f0f0f0fu, 0x08080808u);
-                            } else {
-                                a[mt][h] = lds2(bp + 2 + kq); a[mt][2 + h] = lds2(bp + 18 + kq);
-                            }
-                        }
-#pragma unroll
-                    for (int np = 0; np < 4; np++) {
-                        uint32_t b0, b1, b2, b3;
-                        ldsm4(b0, b1, b2, b3, b_lane + (uint32_t)(np * 16) * G_BSTRIDE + (uint32_t)(j * 32));
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            const int nt = 2 * np + q;
-                            const float da0 = bd[(wn * 64 + nt * 8 + cq) * 8 + j], da1 = bd[(wn * 64 + nt * 8 + cq + 1) * 8 + j];
-#pragma unroll
-                            for (int mt = 0; mt < 2; mt++) {
-                                int c[4];
-                                imma32(c, a[mt][0], a[mt][1], a[mt][2], a[mt][3], q ? b2 : b0, q ? b3 : b1);
-                                out[mt][nt][0] = fmaf((float)c[0], dw[mt][0] * da0, out[mt][nt][0]); out[mt][nt][1] = fmaf((float)c[1], dw[mt][0] * da1, out[mt][nt][1]);
-                                out[mt][nt][2] = fmaf((float)c[2], dw[mt][1] * da0, out[mt][nt][2]); out[mt][nt][3] = fmaf((float)c[3], dw[mt][1] * da1, out[mt][nt][3]);
-                            }
-                        }
-                    }
-                }
-            }
+            sb_compute<TYPE, 8>(rowp, b_lane, bd, bs, wn * 64, lane, out);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
         }

@@ -602,10 +602,43 @@ static int upload_kv_table(b200_ctx *ctx, const GraphCacheEntry &e, const b200_o
     return B200_OK;
 }
 
+// the replay test shared by the fast path and the capture path: entry whose key equals `key` (and, without the indirection table, whose
+// KV-store destinations are the same pointers)
+static GraphCacheEntry *find_entry(GraphCache &gc, const b200_op *ops, int n_ops, const std::vector<b200_op> &key, const std::vector<int> &kv_idx) {
+    for (auto &e : gc.entries) {
+        if ((int)e.key.size() != n_ops || memcmp(e.key.data(), key.data(), sizeof(b200_op) * (size_t)n_ops) != 0) continue;
+        if (!e.indirect) {                           // exact pointers required
+            bool same = e.kv_ptrs.size() == kv_idx.size();
+            for (size_t j = 0; same && j < kv_idx.size(); j++) same = e.kv_ptrs[j] == ops[kv_idx[j]].dst.data;
+            if (!same) continue;
+        }
+        return &e;
+    }
+    return nullptr;
+}
+
 extern "C" int b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops) {
     if (!ctx || (!ops && n_ops)) return B200_ERR_FAILED;
     CUDA_TRY(cudaSetDevice(ctx->device));
     ctx->fa_map_valid = false;            // the mask may have been rewritten between calls
+    // ---- fast path: a decode step whose op list (modulo the KV-store destinations) has a captured graph is replayed before any
+    //      per-op work (support checks, pattern matching): ~1000 ops per token are otherwise re-validated for nothing ----
+    if (ctx->opt_cuda_graphs && n_ops >= 8 && ctx->graph_cache && !ctx->graph_cache->entries.empty()) {
+        GraphCache &gc = *ctx->graph_cache;
+        std::vector<b200_op> &key = gc.scratch_key;
+        key.assign(ops, ops + n_ops);
+        std::vector<int> &kv_idx = gc.scratch_idx;
+        kv_idx.clear();
+        for (int i = 0; i < n_ops; i++) if (is_kv_store(ops[i])) { kv_idx.push_back(i); key[i].dst.data = nullptr; }
+        GraphCacheEntry *e = find_entry(gc, ops, n_ops, key, kv_idx);
+        if (e && e->exec) {
+            if (e->indirect) { int rc = upload_kv_table(ctx, *e, ops); if (rc) return rc; }
+            CUDA_TRY(cudaGraphLaunch(e->exec, ctx->stream));
+            ctx->launches += 1;
+            e->hits++;
+            return B200_OK;
+        }
+    }
     for (int i = 0; i < n_ops; i++)
         if (!b200_supports_op(ctx->device, &ops[i])) {
             b200_set_error("graph op %d (id %d) not supported", i, ops[i].op);
