@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
@@ -234,11 +234,11 @@ def main():
     n_before = ctx.launches()
     step(); ctx.sync()
     launches_eager = ctx.launches() - n_before              # kernels of one step (graph replay launches the same nodes)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(W):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     L.b200_event_record(ctx.h, e0)
     for _ in range(K):
         step()
@@ -272,7 +272,6 @@ def main():
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    clocks = sampler.summary()
     e2e = {"value": world * K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": g.E * 4 + 4 + h_mask.numel() * 4, "d2h_bytes_per_step": g.V * 4,
            "path": "b200_memcpy_h2d_async x3 -> b200_graph_compute -> b200_memcpy_d2h_async -> b200_synchronize (C ABI, pinned host buffers)"}
     assert np.isfinite(h_logits.numpy()).all(), "non-finite logits"
@@ -311,6 +310,7 @@ def main():
                 "whole_step": {"algorithmic_bytes": sb["total"], "achieved_gbs": sb["total"] * (K / (ms / 1e3)) / 1e9,
                                "frac": sb["total"] * (K / (ms / 1e3)) / 1e9 / peak, "breakdown": sb}}
 
+    clocks = sampler.summary()               # sampled from the first warm-up step through the value, e2e and roofline legs: always under load
     line = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 x int4..6 block dots (q8_K/q8_0 activations), f32 accumulate", "data": "synthetic",
@@ -365,7 +365,7 @@ def main():
                 line.update({"metric": TP_METRIC, "value": tp["value"], "ms_per_step": tp["ms_per_step"], "scaling": "strong",
                              "config": {"workload": tp_workload(a.tp_model, world), "l2": "inputs larger than L2: %.2f GB of weight shards streamed per GPU per step" % (tp["per_gpu_bytes_per_step"] / 1e9),
                                         "cuda_graphs": a.graphs, "pdl": a.pdl, "fusion": a.fusion, "parallelism": "tp%d" % world},
-                             "e2e": tp["e2e"], "gpu_launches": tp["gpu_launches_per_step"] * K * world,
+                             "e2e": tp["e2e"], "clocks": tp["clocks"] if tp["clocks"].get("sm_mhz") else line["clocks"], "gpu_launches": tp["gpu_launches_per_step"] * K * world,
                              "roofline": {"bound": "hbm", "kernel": "b200_gemv_bs1_kernel over each GPU's weight shard (whole TP step incl. the %d all-reduces)" % tp["n_allreduce"],
                                           "achieved": tp["per_gpu_achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": tp["per_gpu_hbm_frac"], "traffic": None}})
         except Exception as ex:
@@ -478,6 +478,8 @@ def tp_leg(a, b200, lg, L, ctx, rank, world, local, peak):
     e0, e1 = L.b200_event_create(local), L.b200_event_create(local)
     W, K = max(a.warmup, 3), a.steps
     n0 = ctx.launches()
+    tp_sampler = ClockSampler(local)
+    tp_sampler.start()
     b200.check(L.b200_graph_compute(ctx.h, arr, len(ops)), "tp step"); ctx.sync()
     launches = ctx.launches() - n0
     for _ in range(W):
@@ -540,7 +542,7 @@ def tp_leg(a, b200, lg, L, ctx, rank, world, local, peak):
            "path": "per rank: b200_memcpy_h2d_async x3 -> b200_graph_compute (sharded step, B200_OP_ALLREDUCE over NVLink) -> b200_memcpy_d2h_async -> b200_synchronize"}
     sb = g.step_bytes(1, n_kv)
     tok_s = K / (ms / 1e3)
-    out = {"e2e": e2e, "n_allreduce": 2 * g.L, "model": "%s %s row-split over %d GPUs (random-init shards of one common-seed model)" % (a.tp_model, FTYPE, world), "world": world,
+    out = {"clocks": tp_sampler.summary(), "e2e": e2e, "n_allreduce": 2 * g.L, "model": "%s %s row-split over %d GPUs (random-init shards of one common-seed model)" % (a.tp_model, FTYPE, world), "world": world,
            "value": tok_s, "unit": "tok/s", "scaling": "strong", "ms_per_step": ms / K, "steps": K, "warmup": W,
            "allreduce": "B200_OP_ALLREDUCE x%d per step: one-shot peer-memory kernel over NVLink (f32 [E] = %d bytes), residual add fused" % (2 * g.L, g.E * 4),
            "gpu_launches_per_step": int(launches), "logits_identical_on_all_ranks": bool(flag.item()),
