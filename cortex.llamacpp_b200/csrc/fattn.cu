@@ -35,6 +35,7 @@ struct FaParams {
     float *dst;
     float *part;                 // [tile][split][16][D + 2]
     int *counters;               // [tile] arrivals of the KV splits (self-resetting); NULL: separate combine kernel
+    int cluster;                 // 1: the KV splits of a tile form a thread-block cluster and are merged through distributed shared memory (no partial buffer, no combine kernel)
     const int *map; int map_stride;   // live-tile map [n_coltiles][1 + n_kv / 32]: count, then the indices of the 32-position tiles with any unmasked cell
     int n_q, n_kv, H, Hkv, gq, HG, QC, n_headtiles, n_coltiles, n_splits, kv_per_split;
     float scale, softcap, max_bias, m0, m1;
@@ -56,6 +57,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void cp_async16(void *s, const void *g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g));
 }
+__device__ __forceinline__ uint32_t fa_mapa(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ float fa_ld_cluster(uint32_t addr) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void fa_cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -435,11 +439,47 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
         const bool valid = (r / p.HG) < p.QC && col < p.n_q && hin < p.gq;
         if (p.n_splits == 1) {
             if (valid) p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = val / L;
+        } else if (p.cluster) {
+            float *cx = co + NWARP * 16 * D;                   // this split's merged tile [16][D + 2], read by cluster rank 0
+            cx[r * (D + 2) + d] = val;
+            if (d == 0) { cx[r * (D + 2) + D] = M; cx[r * (D + 2) + D + 1] = L; }
         } else {
             float *pp = p.part + (((uint64_t)tile_id * p.n_splits + split) * 16 + r) * (D + 2);
             pp[d] = val;
             if (d == 0) { pp[D] = M; pp[D + 1] = L; }
         }
+    }
+    // ---- cluster mode: the splits of this tile are the CTAs of one cluster; rank 0 merges them (log-sum-exp, fixed split order) straight
+    //      out of the other CTAs' shared memory.  One launch instead of two and no partial round trip through global memory.
+    if (p.n_splits > 1 && p.cluster) {
+        float *cx = co + NWARP * 16 * D;
+        float *fac = cx + 16 * (D + 2);                        // [16][8] per-split weights exp(M_sp - M) / Lsum of every row
+        fa_cluster_sync();
+        if (split == 0) {
+            const uint32_t cx_s = smem_u32(cx);
+            if (threadIdx.x < 16) {
+                const int r = threadIdx.x;
+                float Ms[8], Mx = -INFINITY, Lsum = 0.0f;
+                for (int sp = 0; sp < p.n_splits; sp++) { Ms[sp] = fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + D) * 4, sp)); Mx = fmaxf(Mx, Ms[sp]); }
+                for (int sp = 0; sp < p.n_splits; sp++) {
+                    const float f = Ms[sp] == -INFINITY ? 0.0f : expf(Ms[sp] - Mx);
+                    Lsum += fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + D + 1) * 4, sp)) * f;
+                    fac[r * 8 + sp] = f;
+                }
+                fac[16 * 8 + r] = Lsum;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
+                const int r = e / D, d = e % D;
+                const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+                if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) continue;
+                float acc = 0.0f;
+                for (int sp = 0; sp < p.n_splits; sp++) acc += fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + d) * 4, sp)) * fac[r * 8 + sp];
+                p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / fac[16 * 8 + r];
+            }
+        }
+        fa_cluster_sync();                                     // nobody leaves while rank 0 still reads its shared memory
+        return;
     }
     // ---- the LAST split of a tile to arrive merges all splits (log-sum-exp, fixed split order => deterministic):
     //      saves the combine kernel and its launch boundary on the decode critical path ----
@@ -845,7 +885,7 @@ int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     constexpr int LD = D + 8;
     constexpr int RAWK = KT != KV_F16 ? BK * (KT == KV_Q8_0 ? 34 : 18) * (D / 32) : 0, RAWV = VT != KV_F16 ? BK * (VT == KV_Q8_0 ? 34 : 18) * (D / 32) : 0;
     constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4 + RAWK + RAWV;
-    constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D) * 4;
+    constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D + 16 * (D + 2) + 16 * 8 + 16) * 4;      // warp merge + cluster merge areas
     constexpr int SMEM = NWARP * WARP_BYTES > COMBINE_BYTES ? NWARP * WARP_BYTES : COMBINE_BYTES;
     auto kern = b200_fattn_kernel<D, KT, VT>;
     static bool attr_set[16] = {false};
@@ -853,18 +893,21 @@ int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set[ctx->device & 15] = true;
     }
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (p.cluster) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = (unsigned)p.n_splits; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.n_splits, (unsigned)n_tiles);
     cfg.blockDim = dim3(NWARP * 32);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = ctx->stream;
     cfg.attrs = attr;
-    cfg.numAttrs = p.use_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ctx->launches++;
+    if (p.cluster) return B200_OK;
+    cfg.numAttrs = p.use_pdl ? 1 : 0;
     if (p.n_splits > 1 && !p.counters) {
         cfg.gridDim = dim3((unsigned)((n_tiles * 16 + 3) / 4));
         cfg.blockDim = dim3(128);
@@ -1032,7 +1075,10 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     p.kv_per_split = ((p.n_kv + ns - 1) / ns + unit - 1) / unit * unit;
     ns = (p.n_kv + p.kv_per_split - 1) / p.kv_per_split;
     p.n_splits = ns;
-    if (ns > 1) {
+    // 2..8 splits CAN form one thread-block cluster per tile and merge through distributed shared memory (one launch, no partials; opt-in)
+    static const int use_cluster = getenv("GGML_B200_FA_CLUSTER") ? atoi(getenv("GGML_B200_FA_CLUSTER")) : 0;   // measured slower than the PDL combine kernel (511 vs 529 tok/s bs1): opt-in
+    p.cluster = use_cluster && ns >= 2 && ns <= 8;
+    if (ns > 1 && !p.cluster) {
         // sized by its upper bound (n_tiles * ns <= 4 * sm_count + n_tiles) so that a growing n_kv never reallocates it under
         // captured graphs
         p.part = (float *)ctx->get_scratch(SCRATCH_FATTN, (size_t)(4 * ctx->sm_count + n_tiles) * 16 * (D + 2) * 4);

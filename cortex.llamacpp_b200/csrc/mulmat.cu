@@ -4,11 +4,15 @@
 // Semantics follow the CPU oracle (ggml_compute_forward_mul_mat, ggml-cpu.c:8708-8900): src1 rows are
 // quantised to the weight type's vec_dot_type (q8_0 for Q4_0/Q8_0, q8_K for K-quants, f16/bf16 for
 // 16-bit float weights) and every dst element is one dot product.
-//   quantised W, M <= GEMV_MAX_COLS : quantise (quant.cu) + streaming GEMV (gemv.cu)
-//   quantised W, M  > GEMV_MAX_COLS : quantise + tcgen05 int8 GEMM (gemm_i8.cu) when available, else GEMV in column chunks
-//   F32/F16/BF16 W                  : warp-per-row float kernel below (router, small test shapes)
-// MUL_MAT_ID: device-side expert routing -- no host sync on `ids` (the reference copies ids to the host and
-// loops experts there).
+//   quantised W, M <= 4      : streaming GEMV, activation quantisation in its prologue (gemv.cu, gemv_bs1.cu)
+//   quantised W, 5 <= M <= 32: quantise (quant.cu) + small-batch mma.sync kernel (gemv_mma.cu)
+//   quantised W, M > 32      : prompt-batch GEMM on mma.sync (gemm_mma.cu, all five formats); GGML_B200_PREFER_TCGEN05=1: tcgen05 int8 GEMM
+//                              (gemm_i8.cu, K-quants); shapes neither takes (N % 128, K % 256): GEMV in column chunks
+//   row-split W (B200_TENSOR_FLAG_SPLIT): every shard's GPU at once (op_mul_mat_split)
+//   F32/F16/BF16 W           : warp-per-row float kernel below (MoE router, small test shapes)
+//   cpu_exact mode           : exact.cu (the reference AVX2 build's summation order)
+// MUL_MAT_ID: device-side expert routing -- no host sync on `ids` (the reference copies ids to the host and loops experts there):
+// one GEMV per (token, slot) for decode-sized batches, pairs grouped by expert on the device + grouped gemv_mma for batches.
 #include "common.cuh"
 #include <algorithm>
 #include <cuda_bf16.h>
@@ -322,9 +326,9 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
 
 // ---------------------------------------------------------------------------------------------------
 // MUL_MAT_ID (ggml_compute_forward_mul_mat_id, ggml-cpu.c:8902-...): dst[:, slot, tok] = as[ids[slot, tok]] . b[:, slot % b_ne1, tok]
-// The expert index is read ON THE DEVICE by the GEMV (no D2H copy of ids + stream sync as in ggml-cuda.cu:1976-1979), so
-// the op is capturable in a CUDA graph.  One streaming GEMV per (token, slot); a grouped tcgen05 GEMM takes the large
-// batches (gemm_i8.cu) when the tokens-per-expert counts make it worthwhile.
+// The expert index is read ON THE DEVICE (no D2H copy of ids + stream sync as in ggml-cuda.cu:1976-1979), so the op is capturable in a
+// CUDA graph.  Up to 8 (token, slot) pairs: one streaming GEMV per pair; more: b200_moe_group_kernel counting-sorts the pairs by expert
+// and launch_gemv_mma_grouped streams every expert's matrix once per 32 pairs (gemv_mma.cu).
 // ---------------------------------------------------------------------------------------------------
 bool supports_mul_mat_id(const b200_op *op) {
     const b200_tensor &as = op->src[0], &b = op->src[1], &ids = op->src[2], &d = op->dst;
