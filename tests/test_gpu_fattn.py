@@ -91,6 +91,7 @@ CASES = [
     # D, H, Hkv, n_q, n_kv
     (128, 32, 8, 1, 256), (128, 32, 8, 1, 4096), (128, 32, 32, 1, 512), (128, 64, 8, 1, 1024), (64, 32, 4, 1, 512),
     (128, 32, 8, 3, 512), (128, 32, 8, 32, 1024), (128, 8, 8, 35, 512), (64, 32, 4, 7, 256), (128, 16, 1, 2, 512),
+    (128, 8, 2, 128, 256), (128, 8, 2, 512, 640), (64, 8, 2, 250, 512),        # prompt-sized query blocks (causal mask: the live-tile map path)
 ]
 
 
