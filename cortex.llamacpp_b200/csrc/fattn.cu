@@ -139,6 +139,115 @@ __device__ __forceinline__ void fetch_raw(uint8_t *rawbuf, const char *g, uint64
     }
 }
 
+// merge the per-warp results of a CTA (cm / cl / co in shared memory, rows r of the tile; fixed warp order), then write the result, the
+// split partial, or merge the splits (cluster / last-arriver variants).  Shared by the 16-row kernel and the few-row kernel.
+template <int D>
+__device__ __forceinline__ void fa_merge_store(const FaParams &p, uint8_t *fsm, int ht, int hk, int c0, int split) {
+    float *cm = (float *)fsm;             // [NWARP][16] max
+    float *cl = cm + NWARP * 16;          // [NWARP][16] sum
+    float *co = cl + NWARP * 16;          // [NWARP][16][D]
+    __syncthreads();
+    const int tile_id = blockIdx.y;
+    for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
+        const int r = e / D, d = e % D;
+        {   // rows of the 16-row tile that hold no query (a bs1 decode step fills 4 of 16): nothing to merge or store
+            const int hin_ = ht * p.HG + r % p.HG, col_ = c0 + r / p.HG;
+            if (!((r / p.HG) < p.QC && col_ < p.n_q && hin_ < p.gq)) continue;
+        }
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) M = fmaxf(M, cm[w * 16 + r]);
+        float val = 0.0f, L = 0.0f;
+        if (M != -INFINITY) {
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) {
+                const float mw = cm[w * 16 + r];
+                const float f = mw == -INFINITY ? 0.0f : expf(mw - M);
+                val += co[(w * 16 + r) * D + d] * f;
+                L += cl[w * 16 + r] * f;
+            }
+        }
+        const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+        const bool valid = (r / p.HG) < p.QC && col < p.n_q && hin < p.gq;
+        if (p.n_splits == 1) {
+            if (valid) p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = val / L;
+        } else if (p.cluster) {
+            float *cx = co + NWARP * 16 * D;                   // this split's merged tile [16][D + 2], read by cluster rank 0
+            cx[r * (D + 2) + d] = val;
+            if (d == 0) { cx[r * (D + 2) + D] = M; cx[r * (D + 2) + D + 1] = L; }
+        } else {
+            float *pp = p.part + (((uint64_t)tile_id * p.n_splits + split) * 16 + r) * (D + 2);
+            pp[d] = val;
+            if (d == 0) { pp[D] = M; pp[D + 1] = L; }
+        }
+    }
+    // ---- cluster mode: the splits of this tile are the CTAs of one cluster; rank 0 merges them (log-sum-exp, fixed split order) straight
+    //      out of the other CTAs' shared memory.  One launch instead of two and no partial round trip through global memory.
+    if (p.n_splits > 1 && p.cluster) {
+        float *cx = co + NWARP * 16 * D;
+        float *fac = cx + 16 * (D + 2);                        // [16][8] per-split weights exp(M_sp - M) / Lsum of every row
+        fa_cluster_sync();
+        if (split == 0) {
+            const uint32_t cx_s = smem_u32(cx);
+            if (threadIdx.x < 16) {
+                const int r = threadIdx.x;
+                float Ms[8], Mx = -INFINITY, Lsum = 0.0f;
+                for (int sp = 0; sp < p.n_splits; sp++) { Ms[sp] = fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + D) * 4, sp)); Mx = fmaxf(Mx, Ms[sp]); }
+                for (int sp = 0; sp < p.n_splits; sp++) {
+                    const float f = Ms[sp] == -INFINITY ? 0.0f : expf(Ms[sp] - Mx);
+                    Lsum += fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + D + 1) * 4, sp)) * f;
+                    fac[r * 8 + sp] = f;
+                }
+                fac[16 * 8 + r] = Lsum;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
+                const int r = e / D, d = e % D;
+                const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+                if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) continue;
+                float acc = 0.0f;
+                for (int sp = 0; sp < p.n_splits; sp++) acc += fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + d) * 4, sp)) * fac[r * 8 + sp];
+                p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / fac[16 * 8 + r];
+            }
+        }
+        fa_cluster_sync();                                     // nobody leaves while rank 0 still reads its shared memory
+        return;
+    }
+    // ---- the LAST split of a tile to arrive merges all splits (log-sum-exp, fixed split order => deterministic):
+    //      saves the combine kernel and its launch boundary on the decode critical path ----
+    if (p.n_splits > 1 && p.counters) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int prev = atomicAdd(&p.counters[tile_id], 1);
+            s_last = prev == p.n_splits - 1;
+            if (s_last) p.counters[tile_id] = 0;           // ready for the next launch (CUDA-graph replay)
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const float *base = p.part + (uint64_t)tile_id * p.n_splits * 16 * (D + 2);
+        const uint64_t sstride = (uint64_t)16 * (D + 2);
+        for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
+            const int r = e / D, d = e % D;
+            const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
+            if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) continue;
+            const float *rp = base + (uint64_t)r * (D + 2);
+            float M = -INFINITY;
+            for (int sp = 0; sp < p.n_splits; sp++) M = fmaxf(M, __ldcg(rp + sp * sstride + D));
+            float Lsum = 0.0f, acc = 0.0f;
+            for (int sp = 0; sp < p.n_splits; sp++) {
+                const float ms = __ldcg(rp + sp * sstride + D);
+                const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+                Lsum += __ldcg(rp + sp * sstride + D + 1) * f;
+                acc += __ldcg(rp + sp * sstride + d) * f;
+            }
+            p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / Lsum;
+        }
+    }
+}
+
 template <int D, int KT, int VT>
 __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParams p) {
     constexpr int LD = D + 8;
@@ -414,106 +523,239 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_kernel(const FaParam
             *(float2 *)(co + (warp * 16 + r) * D + d) = make_float2(o[t][2 * i] * PV_UNSCALE, o[t][2 * i + 1] * PV_UNSCALE);
         }
     }
-    __syncthreads();
-    const int tile_id = blockIdx.y;
-    for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
-        const int r = e / D, d = e % D;
-        {   // rows of the 16-row tile that hold no query (a bs1 decode step fills 4 of 16): nothing to merge or store
-            const int hin_ = ht * p.HG + r % p.HG, col_ = c0 + r / p.HG;
-            if (!((r / p.HG) < p.QC && col_ < p.n_q && hin_ < p.gq)) continue;
-        }
-        float M = -INFINITY;
+    fa_merge_store<D>(p, fsm, ht, hk, c0, split);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Few-row attention (decode, and continuous-batching steps where every KV tile is live for ONE query column): tile = one KV head x
+// one query column, rows = the gq <= 8 heads of the GQA group.  The 16-row kernel above would run 16-row MMA tiles with 4 live
+// rows; here the products are transposed so that the KV cells are the MMA M dimension and the (<= 8) heads the N = 8 dimension:
+//     S^T [32 cells x 8]  = K [32 x D] . Q^T [D x 8]            2 x D/16 mma.m16n8k16  (16 for D = 128, instead of 32)
+//     O^T [D x 8]        += V^T [D x 32] . P^T [32 x 8]         D/16 x 2             (16, instead of 64)
+// P^T leaves the first product in the accumulator layout (cell = lane/4, head = 2*(lane%4)) and enters the second as a B operand
+// (cell = 2*(lane%4), head = lane/4): one 512-byte trip through shared memory per tile.  Arithmetic as in the 16-row kernel: exact
+// integer K.Q per 32-block for quantised K, f32 online softmax, P as an f16 hi+lo pair, quantised V kept integer with its block
+// scales folded into P.  Same splits, live-tile map, partial layout and combine kernel (rows r < gq of a 16-row slot).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int D, int KT, int VT>
+__global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_rows8_kernel(const FaParams p) {
+    constexpr int LD = D + 8;
+    constexpr int NKS = D / 16, NB = D / 32, NMD = D / 16;
+    constexpr bool KQ = KT != KV_F16, VQ = VT != KV_F16;
+    constexpr int PLD = 40;                      // halves per head row of the P^T staging buffer
+    extern __shared__ __align__(128) uint8_t fsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.use_pdl) { pdl_trigger(); pdl_wait(); }
+    constexpr int RAWK = KQ ? BK * (KT == KV_Q8_0 ? 34 : 18) * NB : 0, RAWV = VQ ? BK * (VT == KV_Q8_0 ? 34 : 18) * NB : 0;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * NB * 4 + RAWK + RAWV + 2 * 8 * PLD * 2;
+    __half *sK = (__half *)(fsm + warp * WARP_BYTES);
+    __half *sV = sK + BK * LD;
+    float *sKs = (float *)(sV + BK * LD);
+    float *sVs = sKs + BK * NB;
+    uint8_t *rawK = (uint8_t *)(sVs + BK * NB), *rawV = rawK + RAWK;
+    __half *sPh = (__half *)(rawV + RAWV), *sPl = sPh + 8 * PLD;
+
+    const int split = blockIdx.x;
+    const int col = blockIdx.y % p.n_q, hk = blockIdx.y / p.n_q;       // tile = (kv head, query column); c0 = col, QC = 1, HG = gq
+    const int n_b = lane >> 2, q4 = lane & 3;                           // B-operand layout: head n_b, k pair q4
+    const int R = lane >> 2, n0 = 2 * (lane & 3);                       // accumulator layout: cell / dim row R (+8), heads n0, n0 + 1
+
+    // ---- Q^T fragments (B operand), converted like the CPU converts Q for K's vec_dot_type ---------------------------------
+    uint32_t qb[NKS][2];
+    float dqc[2][NB];                          // q8_0 scales of heads n0, n0 + 1 (quantised K only)
+    {
+        float qv[NKS][4];
+        const bool hv = n_b < p.gq;
+        const float *qp = (const float *)(p.q + (uint64_t)col * p.q_nb1 + (uint64_t)(hk * p.gq + (hv ? n_b : 0)) * p.q_nb2);
 #pragma unroll
-        for (int w = 0; w < NWARP; w++) M = fmaxf(M, cm[w * 16 + r]);
-        float val = 0.0f, L = 0.0f;
-        if (M != -INFINITY) {
+        for (int ks = 0; ks < NKS; ks++) {
+            const int kb = ks * 16 + q4 * 2;
+            if (hv) { const float2 a = *(const float2 *)(qp + kb), b = *(const float2 *)(qp + kb + 8); qv[ks][0] = a.x; qv[ks][1] = a.y; qv[ks][2] = b.x; qv[ks][3] = b.y; }
+            else qv[ks][0] = qv[ks][1] = qv[ks][2] = qv[ks][3] = 0.0f;
+        }
+        float dq[NB];
+        if (KQ) {
 #pragma unroll
-            for (int w = 0; w < NWARP; w++) {
-                const float mw = cm[w * 16 + r];
-                const float f = mw == -INFINITY ? 0.0f : expf(mw - M);
-                val += co[(w * 16 + r) * D + d] * f;
-                L += cl[w * 16 + r] * f;
-            }
-        }
-        const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
-        const bool valid = (r / p.HG) < p.QC && col < p.n_q && hin < p.gq;
-        if (p.n_splits == 1) {
-            if (valid) p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = val / L;
-        } else if (p.cluster) {
-            float *cx = co + NWARP * 16 * D;                   // this split's merged tile [16][D + 2], read by cluster rank 0
-            cx[r * (D + 2) + d] = val;
-            if (d == 0) { cx[r * (D + 2) + D] = M; cx[r * (D + 2) + D + 1] = L; }
-        } else {
-            float *pp = p.part + (((uint64_t)tile_id * p.n_splits + split) * 16 + r) * (D + 2);
-            pp[d] = val;
-            if (d == 0) { pp[D] = M; pp[D + 1] = L; }
-        }
-    }
-    // ---- cluster mode: the splits of this tile are the CTAs of one cluster; rank 0 merges them (log-sum-exp, fixed split order) straight
-    //      out of the other CTAs' shared memory.  One launch instead of two and no partial round trip through global memory.
-    if (p.n_splits > 1 && p.cluster) {
-        float *cx = co + NWARP * 16 * D;
-        float *fac = cx + 16 * (D + 2);                        // [16][8] per-split weights exp(M_sp - M) / Lsum of every row
-        fa_cluster_sync();
-        if (split == 0) {
-            const uint32_t cx_s = smem_u32(cx);
-            if (threadIdx.x < 16) {
-                const int r = threadIdx.x;
-                float Ms[8], Mx = -INFINITY, Lsum = 0.0f;
-                for (int sp = 0; sp < p.n_splits; sp++) { Ms[sp] = fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + D) * 4, sp)); Mx = fmaxf(Mx, Ms[sp]); }
-                for (int sp = 0; sp < p.n_splits; sp++) {
-                    const float f = Ms[sp] == -INFINITY ? 0.0f : expf(Ms[sp] - Mx);
-                    Lsum += fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + D + 1) * 4, sp)) * f;
-                    fac[r * 8 + sp] = f;
+            for (int b = 0; b < NB; b++) {
+                float amax = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 4; e++) amax = fmaxf(amax, fmaxf(fabsf(qv[2 * b][e]), fabsf(qv[2 * b + 1][e])));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                const float d = __fdiv_rn(amax, 127.0f);
+                const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+                dq[b] = __half2float(__float2half_rn(d));
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    qv[2 * b][e] = (float)__float2int_rn(__fmul_rn(qv[2 * b][e], id));
+                    qv[2 * b + 1][e] = (float)__float2int_rn(__fmul_rn(qv[2 * b + 1][e], id));
                 }
-                fac[16 * 8 + r] = Lsum;
             }
-            __syncthreads();
-            for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
-                const int r = e / D, d = e % D;
-                const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
-                if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) continue;
-                float acc = 0.0f;
-                for (int sp = 0; sp < p.n_splits; sp++) acc += fa_ld_cluster(fa_mapa(cx_s + (uint32_t)(r * (D + 2) + d) * 4, sp)) * fac[r * 8 + sp];
-                p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / fac[16 * 8 + r];
-            }
+#pragma unroll
+            for (int b = 0; b < NB; b++) { dqc[0][b] = __shfl_sync(0xffffffffu, dq[b], 4 * n0); dqc[1][b] = __shfl_sync(0xffffffffu, dq[b], 4 * (n0 + 1)); }
         }
-        fa_cluster_sync();                                     // nobody leaves while rank 0 still reads its shared memory
-        return;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ks++) { qb[ks][0] = pack_h2(qv[ks][0], qv[ks][1]); qb[ks][1] = pack_h2(qv[ks][2], qv[ks][3]); }
     }
-    // ---- the LAST split of a tile to arrive merges all splits (log-sum-exp, fixed split order => deterministic):
-    //      saves the combine kernel and its launch boundary on the decode critical path ----
-    if (p.n_splits > 1 && p.counters) {
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int prev = atomicAdd(&p.counters[tile_id], 1);
-            s_last = prev == p.n_splits - 1;
-            if (s_last) p.counters[tile_id] = 0;           // ready for the next launch (CUDA-graph replay)
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        const float *base = p.part + (uint64_t)tile_id * p.n_splits * 16 * (D + 2);
-        const uint64_t sstride = (uint64_t)16 * (D + 2);
-        for (int e = threadIdx.x; e < 16 * D; e += NWARP * 32) {
-            const int r = e / D, d = e % D;
-            const int hin = ht * p.HG + r % p.HG, col = c0 + r / p.HG;
-            if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) continue;
-            const float *rp = base + (uint64_t)r * (D + 2);
-            float M = -INFINITY;
-            for (int sp = 0; sp < p.n_splits; sp++) M = fmaxf(M, __ldcg(rp + sp * sstride + D));
-            float Lsum = 0.0f, acc = 0.0f;
-            for (int sp = 0; sp < p.n_splits; sp++) {
-                const float ms = __ldcg(rp + sp * sstride + D);
-                const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
-                Lsum += __ldcg(rp + sp * sstride + D + 1) * f;
-                acc += __ldcg(rp + sp * sstride + d) * f;
-            }
-            p.dst[((uint64_t)col * p.H + hk * p.gq + hin) * D + d] = acc / Lsum;
+    float slope[2] = {1.0f, 1.0f};
+    if (p.max_bias > 0.0f) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int h = hk * p.gq + n0 + i;
+            slope[i] = h < p.n_head_log2 ? powf(p.m0, (float)(h + 1)) : powf(p.m1, (float)(2 * (h - p.n_head_log2) + 1));
         }
     }
+    float o[NMD][4];
+#pragma unroll
+    for (int t = 0; t < NMD; t++) o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.0f;
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.0f, 0.0f};
+
+    const char *kbase = p.k + (uint64_t)hk * p.k_nb2;
+    const char *vbase = p.v + (uint64_t)hk * p.v_nb2;
+    const char *mrowp = p.mask ? p.mask + (uint64_t)col * p.m_nb1 : nullptr;
+    const int kv_begin = split * p.kv_per_split, kv_end = min(p.n_kv, kv_begin + p.kv_per_split);
+    const int *mp = p.map ? p.map + (size_t)col * p.map_stride : nullptr;
+    int it_begin = kv_begin / BK, it_end = kv_end / BK;
+    if (mp) { const int cnt = mp[0]; it_begin = (int)((long long)split * cnt / p.n_splits); it_end = (int)((long long)(split + 1) * cnt / p.n_splits); }
+    constexpr bool PREFETCH = KQ && VQ;
+    if (PREFETCH && mp && it_begin + warp < it_end) {
+        const int kvf = mp[1 + it_begin + warp] * BK;
+        fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kvf, lane);
+        fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kvf, lane);
+    }
+    for (int it = it_begin + warp; it < it_end; it += NWARP) {
+        const int kv0 = (mp ? mp[1 + it] : it) * BK;
+        if (mrowp && !mp) {                       // skip a tile that is fully masked for this column
+            const __half mv = *(const __half *)(mrowp + (uint64_t)(kv0 + lane) * 2);
+            if (!__any_sync(0xffffffffu, !(__hisinf(mv) && __half2float(mv) < 0.0f))) continue;
+        }
+        __syncwarp();
+        if (!(PREFETCH && mp)) {
+            if (KQ) fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kv0, lane);
+            if (VQ) fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kv0, lane);
+        }
+        if (KQ || VQ) { cp_async_wait_all(); __syncwarp(); }
+        stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane, rawK, 1.0f);
+        stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane, rawV, PV_SCALE);
+        if (KT == KV_F16 || VT == KV_F16) cp_async_wait_all();
+        __syncwarp();
+        if (PREFETCH && mp && it + NWARP < it_end) {
+            const int kvn = mp[1 + it + NWARP] * BK;
+            fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kvn, lane);
+            fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kvn, lane);
+        }
+        // ---- S^T = K Q^T: s[mt] = {cell R: heads n0, n0+1; cell R+8: heads n0, n0+1} of cells mt*16.. -------------------------
+        float s[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            s[mt][0] = s[mt][1] = s[mt][2] = s[mt][3] = 0.0f;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int ks = 2 * b; ks < 2 * b + 2; ks++) {
+                    uint32_t a[4];
+                    ldsm_x4(a[0], a[1], a[2], a[3], sK + (mt * 16 + (lane & 15)) * LD + ks * 16 + (lane >> 4) * 8);
+                    if (KQ) mma16816(t, a, qb[ks][0], qb[ks][1]); else mma16816(s[mt], a, qb[ks][0], qb[ks][1]);
+                }
+                if (KQ) {
+                    const float dk0 = sKs[(mt * 16 + R) * NB + b], dk1 = sKs[(mt * 16 + R + 8) * NB + b];
+                    s[mt][0] += t[0] * (dk0 * dqc[0][b]); s[mt][1] += t[1] * (dk0 * dqc[1][b]);
+                    s[mt][2] += t[2] * (dk1 * dqc[0][b]); s[mt][3] += t[3] * (dk1 * dqc[1][b]);
+                }
+            }
+        }
+        // ---- scale, softcap, mask (one query column: the mask depends on the cell only), online softmax per head ------------------
+        float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float mv = mrowp ? __half2float(*(const __half *)(mrowp + (uint64_t)(kv0 + mt * 16 + R + 8 * h) * 2)) : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    float v = s[mt][2 * h + i] * p.scale;
+                    if (p.softcap != 0.0f) v = p.softcap * tanhf(v);
+                    if (mrowp) v += slope[i] * mv;
+                    s[mt][2 * h + i] = v;
+                    tmax[i] = fmaxf(tmax[i], v);
+                }
+            }
+        float corr[2], muse[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            tmax[i] = fmaxf(tmax[i], __shfl_xor_sync(0xffffffffu, tmax[i], 4));
+            tmax[i] = fmaxf(tmax[i], __shfl_xor_sync(0xffffffffu, tmax[i], 8));
+            tmax[i] = fmaxf(tmax[i], __shfl_xor_sync(0xffffffffu, tmax[i], 16));
+            const float mnew = fmaxf(mrow[i], tmax[i]);
+            muse[i] = mnew == -INFINITY ? 0.0f : mnew;
+            corr[i] = mrow[i] == -INFINITY ? 0.0f : expf(mrow[i] - muse[i]);
+            mrow[i] = mnew;
+            lrow[i] *= corr[i];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float pe = expf(s[mt][e] - muse[e & 1]); s[mt][e] = pe; lrow[e & 1] += pe; }
+        if (__any_sync(0xffffffffu, corr[0] != 1.0f || corr[1] != 1.0f)) {
+#pragma unroll
+            for (int t = 0; t < NMD; t++) { o[t][0] *= corr[0]; o[t][1] *= corr[1]; o[t][2] *= corr[0]; o[t][3] *= corr[1]; }
+        }
+        // ---- O^T += V^T P^T: P^T through shared memory into the B layout, f16 hi + lo; quantised V: block scale folded into P ----
+#pragma unroll
+        for (int b = 0; b < (VQ ? NB : 1); b++) {
+            __syncwarp();
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int cell = mt * 16 + R + 8 * h;
+                    const float dv = VQ ? sVs[cell * NB + b] : PV_SCALE;       // (quantised V: PV_SCALE is folded into the staged scales)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const float w = s[mt][2 * h + i] * dv;
+                        const __half hi = __float2half_rn(w);
+                        sPh[(n0 + i) * PLD + cell] = hi;
+                        sPl[(n0 + i) * PLD + cell] = __float2half_rn(w - __half2float(hi));
+                    }
+                }
+            __syncwarp();
+            uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++) {
+                bh[kk][0] = *(const uint32_t *)(sPh + n_b * PLD + kk * 16 + q4 * 2); bh[kk][1] = *(const uint32_t *)(sPh + n_b * PLD + kk * 16 + 8 + q4 * 2);
+                bl[kk][0] = *(const uint32_t *)(sPl + n_b * PLD + kk * 16 + q4 * 2); bl[kk][1] = *(const uint32_t *)(sPl + n_b * PLD + kk * 16 + 8 + q4 * 2);
+            }
+            const int md0 = VQ ? 2 * b : 0, md1 = VQ ? 2 * b + 2 : NMD;
+#pragma unroll
+            for (int md = md0; md < md1; md++)
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    uint32_t a[4];
+                    ldsm_x4_t(a[0], a[1], a[2], a[3], sV + (kk * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * LD + md * 16 + ((lane >> 3) & 1) * 8);
+                    mma16816(o[md], a, bh[kk][0], bh[kk][1]);
+                    mma16816(o[md], a, bl[kk][0], bl[kk][1]);
+                }
+        }
+    }
+    // ---- hand the per-warp results to the common merge: rows r = head n of the 16-row slot ------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        lrow[i] += __shfl_xor_sync(0xffffffffu, lrow[i], 4);
+        lrow[i] += __shfl_xor_sync(0xffffffffu, lrow[i], 8);
+        lrow[i] += __shfl_xor_sync(0xffffffffu, lrow[i], 16);
+    }
+    __syncthreads();                      // staging buffers are dead from here on
+    float *cm = (float *)fsm, *cl = cm + NWARP * 16, *co = cl + NWARP * 16;
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) { cm[warp * 16 + n0 + i] = mrow[i]; cl[warp * 16 + n0 + i] = lrow[i]; }
+    }
+#pragma unroll
+    for (int t = 0; t < NMD; t++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) co[(warp * 16 + n0 + (e & 1)) * D + t * 16 + R + 8 * (e >> 1)] = o[t][e] * PV_UNSCALE;
+    fa_merge_store<D>(p, fsm, 0, hk, col, split);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -880,14 +1122,14 @@ __global__ void __launch_bounds__(128) b200_fattn_f16acc_kernel(const FaParams p
 
 int kv_kind(int type) { return type == B200_TYPE_F16 ? KV_F16 : type == B200_TYPE_Q8_0 ? KV_Q8_0 : type == B200_TYPE_Q4_0 ? KV_Q4_0 : -1; }
 
-template <int D, int KT, int VT>
+template <int D, int KT, int VT, bool ROWS8 = false>
 int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     constexpr int LD = D + 8;
     constexpr int RAWK = KT != KV_F16 ? BK * (KT == KV_Q8_0 ? 34 : 18) * (D / 32) : 0, RAWV = VT != KV_F16 ? BK * (VT == KV_Q8_0 ? 34 : 18) * (D / 32) : 0;
-    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4 + RAWK + RAWV;
+    constexpr int WARP_BYTES = 2 * BK * LD * 2 + 2 * BK * (D / 32) * 4 + RAWK + RAWV + (ROWS8 ? 2 * 8 * 40 * 2 : 0);
     constexpr int COMBINE_BYTES = (2 * NWARP * 16 + NWARP * 16 * D + 16 * (D + 2) + 16 * 8 + 16) * 4;      // warp merge + cluster merge areas
     constexpr int SMEM = NWARP * WARP_BYTES > COMBINE_BYTES ? NWARP * WARP_BYTES : COMBINE_BYTES;
-    auto kern = b200_fattn_kernel<D, KT, VT>;
+    auto kern = ROWS8 ? b200_fattn_rows8_kernel<D, KT, VT> : b200_fattn_kernel<D, KT, VT>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -919,12 +1161,12 @@ int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
 }
 
 template <int D>
-int launch_fa_types(b200_ctx *ctx, const FaParams &p, int n_tiles, int kt, int vt) {
-    if (kt == KV_F16 && vt == KV_F16) return launch_fa<D, KV_F16, KV_F16>(ctx, p, n_tiles);
+int launch_fa_types(b200_ctx *ctx, const FaParams &p, int n_tiles, int kt, int vt, bool rows8) {
+    if (kt == KV_F16 && vt == KV_F16) return rows8 ? launch_fa<D, KV_F16, KV_F16, true>(ctx, p, n_tiles) : launch_fa<D, KV_F16, KV_F16>(ctx, p, n_tiles);
     if (D == 128) {
         if constexpr (D == 128) {
-            if (kt == KV_Q8_0 && vt == KV_Q8_0) return launch_fa<128, KV_Q8_0, KV_Q8_0>(ctx, p, n_tiles);
-            if (kt == KV_Q4_0 && vt == KV_Q4_0) return launch_fa<128, KV_Q4_0, KV_Q4_0>(ctx, p, n_tiles);
+            if (kt == KV_Q8_0 && vt == KV_Q8_0) return rows8 ? launch_fa<128, KV_Q8_0, KV_Q8_0, true>(ctx, p, n_tiles) : launch_fa<128, KV_Q8_0, KV_Q8_0>(ctx, p, n_tiles);
+            if (kt == KV_Q4_0 && vt == KV_Q4_0) return rows8 ? launch_fa<128, KV_Q4_0, KV_Q4_0, true>(ctx, p, n_tiles) : launch_fa<128, KV_Q4_0, KV_Q4_0>(ctx, p, n_tiles);
         }
     }
     b200_set_error("flash_attn: K/V type combination not built");
@@ -983,6 +1225,10 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     p.use_pdl = ctx->opt_pdl;
     p.m0 = powf(2.0f, -(p.max_bias) / p.n_head_log2);
     p.m1 = powf(2.0f, -(p.max_bias / 2.0f) / p.n_head_log2);
+    // decode and continuous-batching steps: the few-row kernel (tile = one KV head x one column, the GQA group's heads as the MMA N = 8)
+    static const int use_rows8 = getenv("GGML_B200_FA_ROWS8") ? atoi(getenv("GGML_B200_FA_ROWS8")) : 1;
+    const bool rows8 = use_rows8 && !ctx->opt_cpu_exact && p.gq <= 8 && p.n_q <= 32 && kv_kind(k.type) == kv_kind(v.type) && kv_kind(k.type) >= 0;
+    if (rows8) { p.HG = p.gq; p.QC = 1; p.n_headtiles = 1; p.n_coltiles = p.n_q; }
     const int n_tiles = p.Hkv * p.n_headtiles * p.n_coltiles;
     if (n_tiles == 0 || p.n_q == 0) return B200_OK;
     // parity mode: reproduce the CPU's fp16 V accumulator (see b200_fattn_f16acc_kernel)
@@ -1068,7 +1314,8 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
     const int unit = NWARP * BK;
     const int max_splits = (p.n_kv + unit - 1) / unit;
     int ns = (3 * ctx->sm_count + n_tiles - 1) / n_tiles;
-    if (p.map) ns = (2 * ctx->sm_count) / n_tiles;      // live tiles are shared evenly: one full wave of the 2 resident CTAs per SM (the per-warp
+    if (p.map) ns = (2 * ctx->sm_count) / n_tiles;
+    if (rows8) ns = (2 * ctx->sm_count) / n_tiles;            // one wave of the 2 resident CTAs per SM; a full batch needs no split at all      // live tiles are shared evenly: one full wave of the 2 resident CTAs per SM (the per-warp
                                                         // set-up -- Q fragments, merge -- costs about as much as one KV tile)
     if (ns > max_splits) ns = max_splits;
     if (ns < 1) ns = 1;
@@ -1095,8 +1342,8 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
         }
     }
     const int kt = kv_kind(k.type), vt = kv_kind(v.type);
-    if (D == 128) return launch_fa_types<128>(ctx, p, n_tiles, kt, vt);
-    if (D == 64) return launch_fa_types<64>(ctx, p, n_tiles, kt, vt);
+    if (D == 128) return launch_fa_types<128>(ctx, p, n_tiles, kt, vt, rows8);
+    if (D == 64) return launch_fa_types<64>(ctx, p, n_tiles, kt, vt, rows8);
     b200_set_error("flash_attn: D=%d", D);
     return B200_ERR_UNSUPPORTED;
 }

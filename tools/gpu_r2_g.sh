@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 1200 python -m pytest tests/test_gpu_fattn.py -x -q -m gpu 2>&1 | tail -4
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:rows8 -s 2 -c 1 -o gpurun_out/r2g_rows8 -f python tools/batched_prof.py bs32 2 1 > /dev/null 2>&1
+ls -la gpurun_out/r2g_rows8.ncu-rep
