@@ -221,6 +221,7 @@ struct MmGroupDesc {
     int E, n_used, b_ne1, max_chunks;    // max_chunks: upper bound of sum_e ceil(count_e / 32) = grid.y
     size_t expert_stride, d_nb1, d_nb2;  // bytes between expert matrices; dst element strides of slot and token
 };
+int gemm_mma_run_grouped(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, const MmGroupDesc &g, float *dst);
 int launch_gemv_mma_grouped(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const uint8_t *act, const MmGroupDesc &g, float *dst);
 int launch_act_prologue(b200_ctx *ctx, int mode, const float *x, size_t x_stride_bytes, const float *x2, float eps, int64_t K, int ncols, int q8k,
                         uint8_t *scratch);

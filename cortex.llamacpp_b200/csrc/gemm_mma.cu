@@ -38,7 +38,20 @@ struct GParams {
     float *part;                                       // [ksplit][M][N] when ksplit > 1
     int nsb, ntile, nrt, ksplit, sb_per_split, nitems;
     int nstages; uint32_t stage_bytes, a_bytes, rstride;
+    // grouped (MUL_MAT_ID) mode: a "token tile" is a chunk of <= 128 (token, slot) pairs routed to one expert
+    const int32_t *g_off, *g_pairs; int g_E, g_n_used, g_b_ne1, g_chunks;       // g_E == 0: dense
+    size_t g_expert_stride, g_d_nb1, g_d_nb2;
 };
+
+// grouped mode: chunk -> (expert, first pair, pairs in the chunk; 0 = the chunk does not exist)
+__device__ __forceinline__ void g_lookup(const GParams &p, int chunk, int &e, int &first, int &cnt) {
+    cnt = 0; first = 0;
+    for (e = 0; e < p.g_E; e++) {
+        const int o0 = p.g_off[e], n = p.g_off[e + 1] - o0, nch = (n + GT_N - 1) / GT_N;
+        if (chunk < nch) { first = o0 + chunk * GT_N; cnt = min(GT_N, n - chunk * GT_N); return; }
+        chunk -= nch;
+    }
+}
 
 __device__ __forceinline__ void ldsm4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t saddr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
@@ -267,6 +280,42 @@ __device__ __forceinline__ void sb_compute(const uint8_t *const (&rowp)[2][2], u
     }
 }
 
+// grouped: one warp per (chunk slot, super-block); the slot's pair gives the activation column
+__global__ void __launch_bounds__(256) b200_gemm_mma_pack_grouped_kernel(const float *__restrict__ x, size_t x_stride, GParams p, uint8_t *__restrict__ img) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gw >= (int64_t)p.g_chunks * GT_N * p.nsb) return;
+    const int b = (int)(gw % p.nsb), slot = (int)(gw / p.nsb), chunk = slot / GT_N, t = slot % GT_N;
+    int e, first, cnt;
+    g_lookup(p, chunk, e, first, cnt);
+    if (cnt == 0) return;
+    uint8_t *im = img + ((size_t)chunk * p.nsb + b) * img_bytes(p.q8k);
+    float v[8];
+    if (t < cnt) {
+        const int pair = p.g_pairs[first + t];
+        const int64_t colidx = p.g_b_ne1 == 1 ? pair / p.g_n_used : pair;
+        const float *xp = (const float *)((const char *)x + (size_t)colidx * x_stride) + b * 256 + lane * 8;
+        const float4 a = *(const float4 *)xp, c = *(const float4 *)(xp + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0.0f;
+    }
+    uint2 qp;
+    if (p.q8k) {
+        float d; int pair;
+        warp_quant_q8k(v, lane, qp, d, pair);
+        const int s32 = pair + __shfl_down_sync(0xffffffffu, pair, 2);
+        if ((lane & 3) == 0) ((int16_t *)(im + img_off_s(1)))[t * 8 + (lane >> 2)] = (int16_t)s32;
+        if (lane == 0) ((float *)(im + img_off_d()))[t] = d;
+    } else {
+        float d16; int bsum;
+        warp_quant_q80(v, qp, d16, bsum);
+        if ((lane & 3) == 0) ((float *)(im + img_off_d()))[t * 8 + (lane >> 2)] = d16;
+    }
+    *(uint2 *)(im + (size_t)t * G_BSTRIDE + lane * 8) = qp;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- the GEMM
 template <int TYPE>
 __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GParams p) {
@@ -292,10 +341,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GPara
     auto produce_upto = [&](int limit) {
         while (p_item < p.nitems && p_it < limit) {
             const int rt = (p_item / p.ksplit) % p.nrt, tt = p_item / (p.ksplit * p.nrt);
+            const uint8_t *Wb = p.W;
+            if (p.g_E) {                    // grouped: token tile tt = chunk of one expert; chunks beyond the routed pairs do not exist
+                int e, first, cnt;
+                g_lookup(p, tt, e, first, cnt);
+                if (cnt == 0) { p_item += gridDim.x; if (p_item < p.nitems) { p_b = 0; p_b1 = p.nsb; } continue; }
+                Wb += (size_t)e * p.g_expert_stride;
+            }
             const int st = p_it % ns, use = p_it / ns;
             if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
             uint8_t *stage = ring + (size_t)st * p.stage_bytes;
-            const uint8_t *wbase = p.W + (size_t)(rt * GT_M) * p.rb + (size_t)p_b * p.bbytes;
+            const uint8_t *wbase = Wb + (size_t)(rt * GT_M) * p.rb + (size_t)p_b * p.bbytes;
             for (int c = threadIdx.x; c < GT_M * CPR; c += G_THREADS) {
                 const int r = c / CPR, ch = c % CPR;
                 const uint8_t *src = wbase + (size_t)r * p.rb;
@@ -321,6 +377,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GPara
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         const int ks = item % p.ksplit, rt = (item / p.ksplit) % p.nrt, tt = item / (p.ksplit * p.nrt);
         const int sb0 = ks * p.sb_per_split, sb1 = min(p.nsb, sb0 + p.sb_per_split);
+        const uint8_t *Wc = p.W;
+        int g_first = 0, g_cnt = GT_N;
+        if (p.g_E) {
+            int e;
+            g_lookup(p, tt, e, g_first, g_cnt);
+            if (g_cnt == 0) continue;
+            Wc += (size_t)e * p.g_expert_stride;
+        }
         float out[2][8][4];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
@@ -343,7 +407,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GPara
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int r = wm * 32 + mt * 16 + h * 8 + R;
-                    const uintptr_t g = (uintptr_t)(p.W + (size_t)(rt * GT_M + r) * p.rb + (size_t)b * p.bbytes);
+                    const uintptr_t g = (uintptr_t)(Wc + (size_t)(rt * GT_M + r) * p.rb + (size_t)b * p.bbytes);
                     rowp[mt][h] = stage + (size_t)r * p.rstride + (g & 15);
                 }
             sb_compute<TYPE, 8>(rowp, b_lane, bd, bs, wn * 64, lane, out);
@@ -357,8 +421,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) b200_gemm_mma_kernel(const GPara
         for (int nt = 0; nt < 8; nt++)
 #pragma unroll
             for (int cc = 0; cc < 2; cc++) {
-                const int tok = tt * GT_N + wn * 64 + nt * 8 + cq + cc;
-                if (tok < p.M) {
+                const int tl = wn * 64 + nt * 8 + cq + cc, tok = tt * GT_N + tl;
+                if (p.g_E) {
+                    if (tl < g_cnt) {
+                        const int pair = p.g_pairs[g_first + tl];
+                        float *dp = p.dst + (size_t)(pair % p.g_n_used) * p.g_d_nb1 + (size_t)(pair / p.g_n_used) * p.g_d_nb2 + rt * GT_M + wm * 32 + R;
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) { dp[mt * 16] = out[mt][nt][cc]; dp[mt * 16 + 8] = out[mt][nt][2 + cc]; }
+                    }
+                } else if (tok < p.M) {
                     float *dp = base + (size_t)tok * stride + rt * GT_M + wm * 32 + R;
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++) { dp[mt * 16] = out[mt][nt][cc]; dp[mt * 16 + 8] = out[mt][nt][2 + cc]; }
@@ -449,4 +520,44 @@ int gemm_mma_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
+}
+
+// MUL_MAT_ID for prompt batches: the (token, slot) pairs counting-sorted by expert on the device (mulmat.cu) become token tiles of <= 128
+// pairs per expert; every tile runs the same GEMM against its expert's matrix.  g.max_chunks: upper bound of sum_e ceil(count_e / 128).
+int gemm_mma_run_grouped(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, const MmGroupDesc &g, float *dst) {
+    GParams p = {};
+    p.W = W; p.rb = (uint32_t)rb; p.type = type; p.N = (int)N; p.K = (int)K; p.M = 0; p.q8k = b200_act_mode_q8k(type);
+    p.bbytes = type == B200_TYPE_Q4_K ? 144u : type == B200_TYPE_Q5_K ? 176u : type == B200_TYPE_Q6_K ? 210u : type == B200_TYPE_Q4_0 ? 144u : 272u;
+    p.nsb = (int)(K / 256); p.ntile = g.max_chunks; p.nrt = (int)(N / GT_M);
+    p.dst = dst;
+    p.g_off = g.off; p.g_pairs = g.pairs; p.g_E = g.E; p.g_n_used = g.n_used; p.g_b_ne1 = g.b_ne1; p.g_chunks = g.max_chunks;
+    p.g_expert_stride = g.expert_stride; p.g_d_nb1 = g.d_nb1; p.g_d_nb2 = g.d_nb2;
+    const uint32_t ibytes = img_bytes(p.q8k);
+    uint8_t *img = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, (size_t)p.ntile * p.nsb * ibytes);
+    if (!img) return B200_ERR_ALLOC;
+    p.img = img;
+    {
+        const int64_t warps = (int64_t)p.ntile * GT_N * p.nsb;
+        b200_gemm_mma_pack_grouped_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(x, x_stride, p, img);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    p.rstride = ((p.bbytes + 15u) & ~15u) + 16;
+    p.a_bytes = (GT_M * p.rstride + 127u) & ~127u;
+    p.stage_bytes = p.a_bytes + ibytes;
+    int ns = (int)((ctx->smem_optin - 128) / p.stage_bytes);
+    if (ns > 4) ns = 4;
+    if (ns < 2) { b200_set_error("gemm_mma: shared memory"); return B200_ERR_FAILED; }
+    p.nstages = ns;
+    p.ksplit = 1; p.sb_per_split = p.nsb;
+    p.nitems = p.nrt * p.ntile;
+    const int grid = p.nitems < ctx->sm_count ? p.nitems : ctx->sm_count;
+    const size_t smem = 128 + (size_t)ns * p.stage_bytes;
+    switch (type) {
+        case B200_TYPE_Q4_K: return launch_g<B200_TYPE_Q4_K>(ctx, p, grid, smem);
+        case B200_TYPE_Q5_K: return launch_g<B200_TYPE_Q5_K>(ctx, p, grid, smem);
+        case B200_TYPE_Q6_K: return launch_g<B200_TYPE_Q6_K>(ctx, p, grid, smem);
+        case B200_TYPE_Q4_0: return launch_g<B200_TYPE_Q4_0>(ctx, p, grid, smem);
+        default:             return launch_g<B200_TYPE_Q8_0>(ctx, p, grid, smem);
+    }
 }

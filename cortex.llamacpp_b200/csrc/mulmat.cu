@@ -403,18 +403,24 @@ int op_mul_mat_id(b200_ctx *ctx, const b200_op *op) {
         const int q8k = b200_act_mode_q8k(as.type);
         const ActLayout L = ActLayout::make(q8k, K);
         const int64_t acols = b.ne[1] == 1 ? n_tok : npairs;
-        uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)acols);
         int32_t *tab = (int32_t *)ctx->get_scratch(SCRATCH_MOE, (size_t)(E + 1 + npairs) * 4);
-        if (!act || !tab) return B200_ERR_ALLOC;
-        int rc = launch_quantize_act(ctx, q8k, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], K, acols, act);
-        if (rc) return rc;
+        if (!tab) return B200_ERR_ALLOC;
         b200_moe_group_kernel<<<1, 1024, (size_t)2 * E * sizeof(int), ctx->stream>>>((const char *)ids.data, ids.nb[0], ids.nb[1], (int)n_used, (int)n_tok, (int)E, tab, tab + E + 1, 0);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         MmGroupDesc g = {};
         g.off = tab; g.pairs = tab + E + 1; g.E = (int)E; g.n_used = (int)n_used; g.b_ne1 = (int)b.ne[1];
-        g.max_chunks = (int)std::min<int64_t>(npairs, npairs / 32 + E);
         g.expert_stride = as.nb[2]; g.d_nb1 = d.nb[1] / 4; g.d_nb2 = d.nb[2] / 4;
+        // prompt batches (>= 32 pairs per expert on average): token tiles of 128 pairs per expert through the tile GEMM (gemm_mma.cu)
+        if (npairs >= 32 * E && gemm_mma_supported(as.type, N, K, 128)) {
+            g.max_chunks = (int)std::min<int64_t>(npairs, npairs / 128 + E);
+            return gemm_mma_run_grouped(ctx, as.type, (const uint8_t *)as.data, rb, N, K, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], g, (float *)d.data);
+        }
+        uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)acols);
+        if (!act) return B200_ERR_ALLOC;
+        int rc = launch_quantize_act(ctx, q8k, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], K, acols, act);
+        if (rc) return rc;
+        g.max_chunks = (int)std::min<int64_t>(npairs, npairs / 32 + E);
         return launch_gemv_mma_grouped(ctx, as.type, (const uint8_t *)as.data, rb, N, K, act, g, (float *)d.data);
     }
     for (int64_t t = 0; t < n_tok; t++)

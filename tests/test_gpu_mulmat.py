@@ -247,6 +247,37 @@ def test_mul_mat_id_grouped_by_expert_on_device(b200, ctx, t, b_ne1, n_tok, K):
     assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("t", [R.Q4_K, R.Q6_K, R.Q5_K, R.Q4_0, R.Q8_0])
+@pytest.mark.parametrize("b_ne1,n_tok,K", [(1, 200, 1024), (2, 160, 2304)])
+def test_mul_mat_id_prompt_batch_grouped_gemm(b200, ctx, t, b_ne1, n_tok, K):
+    """MoE prompt batches (>= 32 pairs per expert on average): the pairs of an expert form token tiles of 128 for the mma.sync tile GEMM
+    (gemm_mma.cu grouped mode); unbalanced routing -> one expert with several tiles, experts with a ragged or no tile"""
+    rng = np.random.default_rng(31 + t + b_ne1 + n_tok)
+    n_expert, n_used, N = 8, 2, 256
+    As = rand_quant_rows(t, n_expert * N, K, rng)
+    b = rng.standard_normal((n_tok, b_ne1, K)).astype(np.float32)
+    w = np.array([10, 4, 2, 1, 1, 0.5, 0.5, 0.0])
+    sel = np.stack([np.concatenate([c := rng.choice(n_expert, n_used, replace=False, p=w / w.sum()), np.setdiff1d(np.arange(n_expert), c)])
+                    for _ in range(n_tok)]).astype(np.int32)
+    ids = np.ascontiguousarray(sel[:, :n_used])
+    Ad = dev_bytes(As.size + 256, 0)
+    Ad[:As.size] = to_dev(As)
+    bd, seld = to_dev(b), to_dev(sel)
+    out = dev_bytes(n_tok * n_used * N * 4, 0xFF)
+    op = b200.make_op(b200.OP_MUL_MAT_ID, b200.tensor(out.data_ptr(), b200.F32, [N, n_used, n_tok]),
+                      [b200.tensor(Ad.data_ptr(), t, [K, N, n_expert], flags=1), b200.tensor(bd.data_ptr(), b200.F32, [K, b_ne1, n_tok]),
+                       b200.tensor(seld.data_ptr(), b200.I32, [n_used, n_tok], [4, n_expert * 4, n_expert * 4 * n_tok, n_expert * 4 * n_tok])])
+    assert b200.supports(op)
+    l0 = ctx.launches()
+    ctx.compute_op(op)
+    ctx.sync()
+    assert ctx.launches() - l0 == 3, "group + pack + grouped GEMM"
+    got = out.cpu().numpy().view(np.float32).reshape(n_tok, n_used, N)
+    want = R.orc_mul_mat_id(t, As, b, ids, N, K, n_expert)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
 # ----------------------------------------------------------------------------- cpu-exact mode (exact.cu)
 @pytest.mark.parametrize("t", R.QUANT_TYPES)
 def test_cpu_exact_mode_bit_identical_to_reference_golden(b200, ctx, t):

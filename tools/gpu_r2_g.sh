@@ -1,3 +1,3 @@
 #!/bin/bash
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rows8 -s 2 -c 1 -o gpurun_out/r2g_rows8 -f python tools/batched_prof.py bs32 2 1 > /dev/null 2>&1
-ls -la gpurun_out/r2g_rows8.ncu-rep
+timeout 1200 python -m pytest tests/test_gpu_mulmat.py tests/test_gpu_gemm.py -x -q -m gpu -k "mul_mat_id or gemm" 2>&1 | tail -5
+timeout 900 python tools/bench_configs.py mixtral:q4_k_m 2>/dev/null | cut -c1-420
