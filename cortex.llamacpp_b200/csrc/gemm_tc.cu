@@ -1,0 +1,570 @@
+// gemm_tc.cu -- K-quant matmul for token batches (continuous-batching decode steps up to prompt ubatches) on the 5th-generation
+// tensor cores: tcgen05.mma kind::f16 with EXACT-INTEGER f16 operands, f32 accumulators in TMEM.
+//
+// Replaces mul_mat_q (ggml-cuda/mmq.cuh:2501-2657: mma.sync m16n8k32 on q8_1 activations, float fix-up per 32-k block) and, behind
+// it, the CPU's ggml_vec_dot_q{4,5,6}_K_q8_K (ggml-cpu-quants.c) whose per-super-block integers it reproduces:
+//   * activations: quantised once per matmul to q8_K exactly like quantize_row_q8_K_ref (quant_warp.cuh) by a pack kernel that writes
+//     the int8 quants AS f16 INTEGERS into the tensor core's canonical K-major layout -- one contiguous image per (token tile,
+//     super-block) = four 64-k operand stages + a 16-column tile of the per-16 quant sums (for the min term) -- and the block scale d;
+//   * weights stay GGUF blocks in HBM.  The expander warps stage the raw blocks of 128 rows with 16-byte cp.async (completion on an
+//     mbarrier), then turn every 4/5/6-bit quant times its 6-bit (Q4_K/Q5_K) or int8 (Q6_K) sub-block scale into ONE f16 operand
+//     element w' = sc_j * q: <= 1953, exactly representable, built with the 0x6400 magic-number trick (PRMT + one HFMA2 per two
+//     weights).  Q6_K's |sc * (q - 32)| reaches 4064 (12 bits), so it is written as two exact operand tiles
+//     2*sc*((q >> 1) - 16) and sc*(q & 1) that accumulate into the same TMEM columns;
+//   * per 256-k super-block the tensor core accumulates  P = sum_j sc_j sum_l q_jl a_jl  (16 MMAs of K = 16) and, for Q4_K/Q5_K,
+//     the min term  Mn = sum_j m_j * bsum_j  as ONE extra K = 16 MMA (operand rows: the 6-bit mins twice, the per-16 activation
+//     sums) into a second accumulator.  All values are integers below 2^24 in f32: the CPU's integers, bit for bit;
+//   * the drain warps read both accumulators (tcgen05.ld), and fold  d_a * (d_w * P - dmin_w * Mn)  into f32 registers: three
+//     flops per element per super-block, nothing else -- no hi/lo operand split, no dp2a, no int->float conversion.
+// The round-1 kind::i8 kernel (gemm_i8.cu) needed two operand tiles + two accumulators + a 16-instruction drain per element; the
+// mma.sync kernel (gemm_mma.cu) is bounded by the legacy IMMA pipe and its 4 IMAD per IMMA.  Both stay selectable.
+// Roofline: tensor pipe (f16: half the int8 rate) for prompt batches, HBM for <= 32 tokens.  Algorithmic work: 2*N*K*M.
+#include "common.cuh"
+#include "quant_warp.cuh"
+#include "tc05.cuh"
+#include "gemm_tc.h"
+
+namespace {
+
+constexpr int TM = 128;                 // weight rows per CTA tile (MMA M = TMEM lanes)
+// k per operand stage: 128 (two stages per super-block) for Q4_K / Q5_K, 64 for Q6_K whose weights need two operand tiles per stage
+__host__ __device__ constexpr int stage_k(bool q6) { return q6 ? 64 : 128; }
+constexpr int N_EXP = 8, N_DRAIN = 8;   // expander / drain warps; warp 0: activation producer, warp 1: MMA issuer
+constexpr int TC_THREADS = (2 + N_EXP + N_DRAIN) * 32;
+__host__ __device__ constexpr uint32_t main_bytes(int ks) { return (uint32_t)(TM * ks * 2); }      // one f16 operand tile of 128 rows: 16 / 32 KB
+constexpr uint32_t MIN_BYTES = TM * 16 * 2;             // the min-term tile of 128 rows: 4 KB
+// canonical K-major no-swizzle layout: 8 rows x 16 bytes = one 128-byte core matrix; K-adjacent core matrices 128 bytes apart (LBO),
+// 8-row groups (chunks per row) * 128 bytes apart (SBO)
+constexpr uint32_t LBO = 128, SBO_MIN = 2 * 128;
+__host__ __device__ constexpr uint32_t sbo_main(int ks) { return (uint32_t)(ks / 8) * 128u; }
+
+// activation image of one (token tile, super-block): [stage 0: tn x 2 ks B][min tile: tn x 32 B][stage 1]..[stage 256 / ks - 1]
+__host__ __device__ inline uint32_t img_bytes(int tn) { return (uint32_t)tn * 544u; }
+__host__ __device__ inline uint32_t img_stage_off(int tn, int s, int ks) { return s == 0 ? 0u : (uint32_t)tn * (32u + 2u * (uint32_t)ks * (uint32_t)s); }
+
+struct TcParams {
+    const uint8_t *W; uint32_t rb; int N, K, M, Mpad, nsb;
+    const uint8_t *img;                 // [token tile][nsb] images
+    const float *Bd;                    // [nsb][Mpad] q8_K block scales
+    float *dst; size_t dst_stride;      // dst[tok * dst_stride + row]
+    int sb_per_split; float *part;      // split-K: blockIdx.z covers super-blocks [z * sb_per_split, ...), partials [z][M][N]
+    int na, nb, rs;                     // weight-operand ring depth, activation-operand ring depth (64-k stages), raw ring depth (super-blocks)
+    uint32_t a_slot, b_slot, rstride;
+    unsigned long long *prof;           // optional in-kernel timeline of CTA 0 (GGML_B200_TC_PROF=1): [3 roles][256] clock64 stamps
+    int dbg;                            // timing experiments (GGML_B200_TC_DBG): 1 skip expansion, 2 skip MMAs, 4 skip drain math, 8 skip the proxy fence
+};
+
+// a hang on the GPU box costs a whole lease: every wait in this kernel gives up (trap -> launch failure) after ~1 s.  No printf: a
+// kernel that can print pays for the FIFO set-up at every launch.
+__device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
+// one lane of a fully converged warp.  The single-thread roles run their loops WARP-UNIFORMLY and predicate only the issue on this: inside
+// an `if (lane == 0)` region the compiler cannot prove the tcgen05 / bulk-copy operands uniform and wraps every instruction in an
+// R2UR + ELECT + BRA.U.ANY waterfall -- ~170 dependent SASS instructions per operand stage, which bounded the whole kernel
+// (profiles/r2_gemm_tc.md)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- activation pack
+// one warp per (token, super-block); lane owns 8 consecutive elements
+__global__ void __launch_bounds__(256) b200_gemm_tc_pack_kernel(const float *__restrict__ x, size_t x_stride, int K, int M, int Mpad, int nsb, int tn, int ks,
+                                                                uint8_t *__restrict__ img, float *__restrict__ Bd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gw >= (int64_t)Mpad * nsb) return;
+    const int b = (int)(gw % nsb), tok = (int)(gw / nsb), tile = tok / tn, n = tok % tn;
+    float v[8];
+    if (tok < M) {
+        const float *xp = (const float *)((const char *)x + (size_t)tok * x_stride) + b * 256 + lane * 8;
+        const float4 a = *(const float4 *)xp, c = *(const float4 *)(xp + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0.0f;
+    }
+    uint2 qp; float d; int pair;
+    warp_quant_q8k(v, lane, qp, d, pair);              // pair: valid in even lanes = bsum of the 16-group lane / 2
+    uint8_t *im = img + ((size_t)tile * nsb + b) * img_bytes(tn);
+    const int s = lane * 8 / ks, c = (lane * 8 % ks) >> 3;     // operand stage, 16-byte chunk inside the stage row
+    const int8_t *q = (const int8_t *)&qp;
+    __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __halves2half2(__int2half_rn(q[2 * j]), __int2half_rn(q[2 * j + 1]));
+    *(uint4 *)(im + img_stage_off(tn, s, ks) + (uint32_t)(n >> 3) * sbo_main(ks) + (uint32_t)c * LBO + (uint32_t)(n & 7) * 16) = *(const uint4 *)h;
+    if ((lane & 1) == 0) {
+        const int i = lane >> 1;                       // 16-group of the super-block = K column of the min tile
+        *(__half *)(im + (uint32_t)tn * 2u * (uint32_t)ks + (uint32_t)(n >> 3) * SBO_MIN + (uint32_t)(i >> 3) * LBO + (uint32_t)(n & 7) * 16 + (uint32_t)(i & 7) * 2) = __int2half_rn(pair);
+    }
+    if (lane == 0) Bd[(size_t)b * Mpad + tok] = d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- weight expansion
+__device__ __forceinline__ __half2 u32_h2(uint32_t u) { return *(const __half2 *)&u; }
+__device__ __forceinline__ uint32_t h2_u32(__half2 h) { return *(const uint32_t *)&h; }
+// bytes (2p, 2p+1) of `w` (each < 1024) -> half2 of the integers 1024 + byte
+__device__ __forceinline__ __half2 magic_pair(uint32_t w, int p) { return u32_h2(__byte_perm(w, 0x64646464u, p ? 0x4342 : 0x4140)); }
+
+// 8 words from a 2-byte aligned shared-memory address
+__device__ __forceinline__ void lds8_unaligned(const uint8_t *p, uint32_t (&w)[8]) {
+    const uint32_t *q = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 2) * 8;
+    uint32_t t[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[i] = q[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = __funnelshift_r(t[i], t[i + 1], sh);
+}
+
+struct KHeader { uint32_t sc_lo, sc_hi, m_lo, m_hi; float d, dmin; };      // Q4_K / Q5_K: 6-bit scales and mins as bytes (get_scale_min_k4, ggml-quants.c:631)
+__device__ __forceinline__ KHeader read_kheader(const uint8_t *blk) {
+    const uint4 h = *(const uint4 *)blk;                                   // d, dmin, scales[12]
+    KHeader k;
+    k.d = half_bits_to_float(h.x); k.dmin = half_bits_to_float(h.x >> 16);
+    k.sc_lo = h.y & 0x3f3f3f3fu; k.m_lo = h.z & 0x3f3f3f3fu;
+    k.sc_hi = (h.w & 0x0f0f0f0fu) | ((h.y >> 2) & 0x30303030u);
+    k.m_hi = ((h.w >> 4) & 0x0f0f0f0fu) | ((h.z >> 2) & 0x30303030u);
+    return k;
+}
+
+// min-term operand row: columns i = 0..15 hold m_{i / 2} (the activation side holds the per-16 quant sums)
+__device__ __forceinline__ void write_min_row(const KHeader &k, int r, uint8_t *a_min) {
+    const __half2 off = __floats2half2_rn(-1024.0f, -1024.0f);
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t src = j < 4 ? k.m_lo : k.m_hi;
+        o[j] = h2_u32(__hadd2(u32_h2(__byte_perm(src, 0x64646464u, 0x4040 | (j & 3) | ((j & 3) << 8))), off));
+    }
+    uint8_t *p = a_min + (uint32_t)(r >> 3) * SBO_MIN + (uint32_t)(r & 7) * 16;
+    *(uint4 *)p = make_uint4(o[0], o[1], o[2], o[3]);
+    *(uint4 *)(p + LBO) = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// Q4_K / Q5_K, 128-k stages: thread (row r, half h) expands the 32-byte quant group 2 s + h of stage s = sub-blocks j = 2 (2 s + h) (low
+// nibbles) and j + 1 (high nibbles), 64 weights, into chunks 8 h .. 8 h + 7 of the operand row
+template <bool Q5>
+__device__ __forceinline__ void expand_k45(const uint8_t *blk, const KHeader &k, const uint32_t (&qh)[8], int s, int h, int r, uint8_t *a_main) {
+    const int grp = 2 * s + h;
+    const uint4 *qs = (const uint4 *)(blk + (Q5 ? 48 : 16) + 32 * grp);
+    const uint4 q0 = qs[0], q1 = qs[1];
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const uint32_t scw = s ? k.sc_hi : k.sc_lo;            // sub-blocks 4 s .. 4 s + 3 live in one scale word
+    uint8_t *dst = a_main + (uint32_t)(r >> 3) * sbo_main(128) + (uint32_t)(8 * h) * LBO + (uint32_t)(r & 7) * 16;
+#pragma unroll
+    for (int nib = 0; nib < 2; nib++) {
+        const int j = 2 * grp + nib;
+        const __half sch = __int2half_rn((int)((scw >> (8 * (2 * h + nib))) & 0xffu));
+        const __half2 sc2 = __half2half2(sch), nsc2 = __half2half2(__hmul(sch, __float2half_rn(-1024.0f)));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int wi = 2 * c + e;
+                uint32_t n4 = (nib ? w[wi] >> 4 : w[wi]) & 0x0f0f0f0fu;
+                if (Q5) n4 |= ((qh[wi] >> j) & 0x01010101u) << 4;
+                o[2 * e]     = h2_u32(__hfma2(magic_pair(n4, 0), sc2, nsc2));
+                o[2 * e + 1] = h2_u32(__hfma2(magic_pair(n4, 1), sc2, nsc2));
+            }
+            *(uint4 *)(dst + (uint32_t)(4 * nib + c) * LBO) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// Q6_K: thread (r, h) expands quadrant t = 2 (s & 1) + h of half hf = s >> 1 (ggml-quants.c:1690-1719) into the two exact tiles
+__device__ __forceinline__ void expand_q6k(const uint8_t *blk, int s, int h, int r, uint8_t *a_even, uint8_t *a_odd) {
+    const int hf = s >> 1, t = 2 * (s & 1) + h;
+    uint32_t ql[8], qh[8];
+    lds8_unaligned(blk + 64 * hf + 32 * h, ql);
+    lds8_unaligned(blk + 128 + 32 * hf, qh);
+    const uint32_t scw = *(const unsigned short *)(blk + 192 + 8 * hf + 2 * t);
+    const __half m1040 = __float2half_rn(-1040.0f), m1024 = __float2half_rn(-1024.0f);
+    const __half2 o1040 = __half2half2(m1040), o1024 = __half2half2(m1024);
+    const uint32_t off = (uint32_t)(r >> 3) * sbo_main(64) + (uint32_t)(4 * h) * LBO + (uint32_t)(r & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int sci = (int)(int8_t)(c < 2 ? (scw & 0xffu) : (scw >> 8));         // 16-element scale group of this chunk pair
+        const __half sch = __int2half_rn(sci);
+        const __half2 sc2 = __half2half2(sch), sc2x2 = __hadd2(sc2, sc2);
+        uint32_t ev[4], od[4];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int wi = 2 * c + e;
+            const uint32_t q4 = ((ql[wi] >> (4 * (s & 1))) & 0x0f0f0f0fu) | (((qh[wi] >> (2 * t)) & 0x03030303u) << 4);     // 4 x (0..63)
+            const uint32_t vh = (q4 >> 1) & 0x1f1f1f1fu, vl = q4 & 0x01010101u;
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                ev[2 * e + p] = h2_u32(__hmul2(__hadd2(magic_pair(vh, p), o1040), sc2x2));       // 2 sc ((q >> 1) - 16): |.| <= 4064, even
+                od[2 * e + p] = h2_u32(__hmul2(__hadd2(magic_pair(vl, p), o1024), sc2));         // sc (q & 1)
+            }
+        }
+        *(uint4 *)(a_even + off + (uint32_t)c * LBO) = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+        *(uint4 *)(a_odd + off + (uint32_t)c * LBO) = make_uint4(od[0], od[1], od[2], od[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- the GEMM
+struct TcBars {
+    uint64_t raw_full[8], raw_empty[8], a_full[4], a_empty[4], b_full[16], b_empty[16], acc_full[2], acc_empty[2];
+    uint32_t tmem_base, pad[3];
+};
+
+template <int TYPE, int TN>
+__global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcParams p) {
+    constexpr bool Q6 = TYPE == B200_TYPE_Q6_K, Q5 = TYPE == B200_TYPE_Q5_K;
+    constexpr int BLK = TYPE == B200_TYPE_Q4_K ? 144 : TYPE == B200_TYPE_Q5_K ? 176 : 210;
+    constexpr int CPR = TYPE == B200_TYPE_Q4_K ? 9 : TYPE == B200_TYPE_Q5_K ? 11 : 14;       // 16-byte chunks per staged row piece (Q6_K: phase <= 14, + 210)
+    constexpr int KS = stage_k(Q6), SPS = 256 / KS, LG_SPS = Q6 ? 2 : 1;                        // k per stage, stages per super-block
+    constexpr uint32_t MAIN_BYTES = main_bytes(KS), SBO_MAIN = sbo_main(KS);
+    constexpr int CH = TN / 2;                                                                // token columns per drain thread
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    uint8_t *a_ring = tsm;
+    uint8_t *b_ring = a_ring + (size_t)p.na * p.a_slot;
+    uint8_t *raw = b_ring + (size_t)p.nb * p.b_slot;
+    float2 *meta = (float2 *)(raw + (size_t)p.rs * TM * p.rstride);       // [4][TM]: (d, dmin) of the row's super-block
+    TcBars *S = (TcBars *)(meta + 4 * TM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * TM, tok0 = blockIdx.y * TN;
+    const int sb0 = (int)blockIdx.z * p.sb_per_split;
+    const int nsb = min(p.sb_per_split, p.nsb - sb0);
+    const int na = p.na, nb = p.nb, rs = p.rs;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; i++) { mbar_init(&S->raw_full[i], N_EXP * 32); mbar_init(&S->raw_empty[i], N_EXP); }
+        for (int i = 0; i < 4; i++) { mbar_init(&S->a_full[i], N_EXP); mbar_init(&S->a_empty[i], 1); }
+        for (int i = 0; i < 16; i++) { mbar_init(&S->b_full[i], 1); mbar_init(&S->b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&S->acc_full[i], 1); mbar_init(&S->acc_empty[i], N_DRAIN); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&S->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S->tmem_base;
+#define TPROF(role, idx) do { if (p.prof && lane == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (idx) < 256) p.prof[(role) * 256 + (idx)] = (unsigned long long)clock64(); } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ activation producer: one bulk copy per operand stage
+        {
+            const uint8_t *src = p.img + ((size_t)blockIdx.y * p.nsb + sb0) * img_bytes(TN);
+            int slot = 0, use = 0;                     // ring position of stage g: slot = g % nb, use = g / nb (kept incrementally: nb is a run-time value)
+            for (int g = 0; g < SPS * nsb; g++) {
+                const int b = g >> LG_SPS, s = g & (SPS - 1);
+                if (p.dbg & 32) break;
+                if (use > 0) tc_wait(&S->b_empty[slot], (use - 1) & 1);
+                const uint32_t bytes = (uint32_t)TN * (2u * KS + ((s == 0 && !Q6) ? 32u : 0u));
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&S->b_full[slot], bytes);
+                    bulk_g2s(b_ring + (size_t)slot * p.b_slot, src + (size_t)b * img_bytes(TN) + img_stage_off(TN, s, KS), bytes, &S->b_full[slot]);
+                }
+                __syncwarp();
+                if (++slot == nb) { slot = 0; use++; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+        {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);      // f16 x f16 -> f32, K-major A and B
+            int slot = 0, use = 0, bslot = 0, buse = 0;
+            const uint64_t dm = make_desc(0, LBO, SBO_MAIN), dn = make_desc(0, LBO, SBO_MIN);      // descriptors = these + (address >> 4)
+            for (int g = 0; g < SPS * nsb; g++) {
+                const int b = g >> LG_SPS, s = g & (SPS - 1), pr = b & 1;
+                if (s == 0 && b >= 2) tc_wait(&S->acc_empty[pr], ((b >> 1) - 1) & 1);
+                TPROF(0, 4 * g);
+                tc_wait(&S->a_full[slot], use & 1);
+                TPROF(0, 4 * g + 1);
+                if (!(p.dbg & 32)) tc_wait(&S->b_full[bslot], buse & 1);
+                TPROF(0, 4 * g + 2);
+                tc_fence_after();
+                if (elect_one()) {
+                const uint32_t aa = smem_u32(a_ring + (size_t)slot * p.a_slot), bb = smem_u32(b_ring + (size_t)bslot * p.b_slot);
+                const uint32_t d_main = tmem + (uint32_t)pr * (2 * TN), d_min = d_main + TN;
+#pragma unroll
+                for (int ks = 0; ks < KS / 16 && !(p.dbg & 2); ks++) {
+                    const uint64_t bd = dm + ((bb + ks * 2 * LBO) >> 4);
+                    mma_f16(d_main, dm + ((aa + ks * 2 * LBO) >> 4), bd, idesc, (s | ks) ? 1u : 0u);
+                    if (Q6) mma_f16(d_main, dm + ((aa + MAIN_BYTES + ks * 2 * LBO) >> 4), bd, idesc, 1u);
+                }
+                if (!Q6 && s == 0) mma_f16(d_min, dn + ((aa + MAIN_BYTES) >> 4), dn + ((bb + TN * 2 * KS) >> 4), idesc, 0u);
+                tc_commit(&S->a_empty[slot]);              // operand slots free once these MMAs have read them
+                tc_commit(&S->b_empty[bslot]);
+                if (s == SPS - 1) tc_commit(&S->acc_full[pr]);   // the super-block's integers are complete
+                }
+                __syncwarp();
+                TPROF(0, 4 * g + 3);
+                if (++slot == na) { slot = 0; use++; }
+                if (++bslot == nb) { bslot = 0; buse++; }
+            }
+        }
+    } else if (warp < 2 + N_EXP) {
+        // ------------------------------------------------------------ expanders: stage raw GGUF blocks (cp.async), write operand tiles
+        const int et = threadIdx.x - 64, r = et & (TM - 1), h = et >> 7;
+        const uint8_t *const Wt = p.W + (size_t)row0 * p.rb + (size_t)sb0 * BLK;
+        // staging: a thread owns chunks c = et + 256 i of a super-block's TM x CPR 16-byte chunks (consecutive lanes = consecutive chunks of
+        // a row piece: whole sectors).  Row pointers and slot offsets are fixed for the launch; only the block offset moves.
+        constexpr int NCP = (TM * CPR + N_EXP * 32 - 1) / (N_EXP * 32);
+        const uint8_t *cp_row[NCP];
+        uint32_t cp_dst[NCP], cp_ch[NCP];
+#pragma unroll
+        for (int i = 0; i < NCP; i++) {
+            const int c = et + i * N_EXP * 32, rr = c / CPR, ch = c % CPR;
+            cp_row[i] = Wt + (size_t)(rr < TM ? rr : 0) * p.rb;
+            cp_ch[i] = (uint32_t)ch * 16u;
+            cp_dst[i] = (uint32_t)rr * p.rstride + (uint32_t)ch * 16u;
+        }
+        int i_slot = 0, i_use = 0;                     // raw ring position of the next super-block to stage
+        auto issue_raw = [&](int b) {
+            if (p.dbg & 16) return;
+            if (i_use > 0) tc_wait(&S->raw_empty[i_slot], (i_use - 1) & 1);
+            const uint32_t slotp = smem_u32(raw) + (uint32_t)i_slot * (TM * p.rstride);
+#pragma unroll
+            for (int i = 0; i < NCP; i++) {
+                if ((i + 1) * N_EXP * 32 <= TM * CPR || et + i * N_EXP * 32 < TM * CPR) {
+                    const uint8_t *src = cp_row[i] + (size_t)b * BLK;
+                    if (Q6) src -= (uintptr_t)src & 15;    // the piece keeps its 16-byte phase inside the slot row (Q4_K / Q5_K blocks are 16-byte aligned)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slotp + cp_dst[i]), "l"(src + cp_ch[i]) : "memory");
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&S->raw_full[i_slot])) : "memory");
+            if (++i_slot == rs) { i_slot = 0; i_use++; }
+        };
+        for (int b = 0; b < rs - 1 && b < nsb; b++) issue_raw(b);
+        const uint8_t *const myrow = Wt + (size_t)r * p.rb;
+        int r_slot = 0, r_use = 0, slot = 0, use = 0;  // raw ring position of super-block b, operand ring position of stage 4 b + s
+        for (int b = 0; b < nsb; b++) {
+            if (b + rs - 1 < nsb) issue_raw(b + rs - 1);
+            if (!(p.dbg & 16)) tc_wait(&S->raw_full[r_slot], r_use & 1);
+            const uint8_t *blk = raw + ((size_t)r_slot * TM + r) * p.rstride + (Q6 ? (uint32_t)((uintptr_t)(myrow + (size_t)b * BLK) & 15) : 0u);
+            KHeader kh = {};
+            uint32_t qh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (!Q6) {
+                kh = read_kheader(blk);
+                if (Q5) {
+                    const uint4 h0 = *(const uint4 *)(blk + 16), h1 = *(const uint4 *)(blk + 32);
+                    qh[0] = h0.x; qh[1] = h0.y; qh[2] = h0.z; qh[3] = h0.w; qh[4] = h1.x; qh[5] = h1.y; qh[6] = h1.z; qh[7] = h1.w;
+                }
+            }
+#pragma unroll 1
+            for (int s = 0; s < SPS; s++) {
+                if (warp == 2) TPROF(1, 4 * (SPS * b + s));
+                if (use > 0) tc_wait(&S->a_empty[slot], (use - 1) & 1);
+                if (warp == 2) TPROF(1, 4 * (SPS * b + s) + 1);
+                uint8_t *as = a_ring + (size_t)slot * p.a_slot;
+                if (p.dbg & 1) {}
+                else if (Q6) expand_q6k(blk, s, h, r, as, as + MAIN_BYTES);
+                else expand_k45<Q5>(blk, kh, qh, s, h, r, as);
+                if (s == 0 && h == 0 && !(p.dbg & 128)) {
+                    if (Q6) meta[(b & 3) * TM + r] = make_float2(half_bits_to_float(*(const unsigned short *)(blk + 208)), 0.0f);
+                    else { write_min_row(kh, r, as + MAIN_BYTES); meta[(b & 3) * TM + r] = make_float2(kh.d, kh.dmin); }
+                }
+                if (!(p.dbg & 8)) fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S->a_full[slot]);
+                if (warp == 2) TPROF(1, 4 * (SPS * b + s) + 2);
+                if (++slot == na) { slot = 0; use++; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->raw_empty[r_slot]);
+            if (++r_slot == rs) { r_slot = 0; r_use++; }
+        }
+    } else {
+        // ------------------------------------------------------------ drain: TMEM -> registers, fold the block scales
+        const int q = warp & 3, chalf = (warp - 2 - N_EXP) >> 2;          // TMEM lane quarter (fixed by the warp id), column half
+        const int r = q * 32 + lane, c_base = chalf * CH;
+        float out[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) out[c] = 0.0f;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        for (int b = 0; b < nsb; b++) {
+            const int pr = b & 1;
+            if (warp == 2 + N_EXP) TPROF(2, 4 * b);
+            tc_wait(&S->acc_full[pr], (b >> 1) & 1);
+            if (warp == 2 + N_EXP) TPROF(2, 4 * b + 1);
+            tc_fence_after();
+            const float2 mt = meta[(b & 3) * TM + r];
+            const float4 *da4 = (const float4 *)(p.Bd + (size_t)(sb0 + b) * p.Mpad + tok0 + c_base);
+            const uint32_t t_main = tmem + lane_addr + (uint32_t)pr * (2 * TN) + (uint32_t)c_base;
+#pragma unroll
+            for (int c0 = 0; c0 < CH; c0 += 8) {
+                uint32_t P[8], Mn[8];
+                if (!(p.dbg & 64)) {
+                    tmem_ld8(t_main + c0, P);
+                    if (!Q6) tmem_ld8(t_main + TN + c0, Mn);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) P[j] = Mn[j] = 0;
+                }
+                if (c0 == CH - 8) {                        // every accumulator column of this warp is in registers: the tensor core may overwrite the buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S->acc_empty[pr]);
+                    if (warp == 2 + N_EXP) TPROF(2, 4 * b + 2);
+                }
+                if (p.dbg & 4) continue;
+                const float4 d0 = __ldg(da4 + (c0 >> 2)), d1 = __ldg(da4 + (c0 >> 2) + 1);
+                const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float u = mt.x * __uint_as_float(P[j]);
+                    if (!Q6) u = fmaf(-mt.y, __uint_as_float(Mn[j]), u);
+                    out[c0 + j] = fmaf(da[j], u, out[c0 + j]);
+                }
+            }
+        }
+        if (warp == 2 + N_EXP) TPROF(2, 255);
+        float *const dstv = gridDim.z > 1 ? p.part + (size_t)blockIdx.z * p.M * p.N : p.dst;
+        const size_t stride = gridDim.z > 1 ? (size_t)p.N : p.dst_stride;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int tok = tok0 + c_base + c;
+            if (tok < p.M) dstv[(size_t)tok * stride + row0 + r] = out[c];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// dst[tok][n] = sum over the K slices in slice order (deterministic)
+__global__ void __launch_bounds__(256) b200_gemm_tc_reduce_kernel(const float *__restrict__ part, int ksplit, int N, int M, float *__restrict__ dst, size_t dst_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * N) return;
+    const int tok = (int)(i / N), n = (int)(i % N);
+    float a = part[i];
+    for (int z = 1; z < ksplit; z++) a += part[(size_t)z * M * N + i];
+    dst[(size_t)tok * dst_stride + n] = a;
+}
+
+template <int TYPE, int TN>
+int launch_tc_t(b200_ctx *ctx, const TcParams &p, dim3 grid, size_t smem) {
+    auto kern = b200_gemm_tc_kernel<TYPE, TN>;
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        attr_set[ctx->device & 15] = true;
+    }
+    kern<<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+template <int TYPE>
+int launch_tc(b200_ctx *ctx, const TcParams &p, int tn, dim3 grid, size_t smem) {
+    return tn == 32 ? launch_tc_t<TYPE, 32>(ctx, p, grid, smem) : tn == 64 ? launch_tc_t<TYPE, 64>(ctx, p, grid, smem) : launch_tc_t<TYPE, 128>(ctx, p, grid, smem);
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int type, int64_t N, int64_t K, int64_t M) {
+    if (type != B200_TYPE_Q4_K && type != B200_TYPE_Q5_K && type != B200_TYPE_Q6_K) return false;
+    static const bool off = getenv("GGML_B200_NO_GEMM_TC") != nullptr;
+    return !off && N % TM == 0 && K % 256 == 0 && M >= 1;
+}
+
+// dst[tok * dst_stride + n] = sum_k W[n, k] * x[k, tok]; x f32 with column stride x_stride bytes
+int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, int64_t M,
+                float *dst, size_t dst_stride) {
+    if (!gemm_tc_supported(type, N, K, M) || (type != B200_TYPE_Q6_K && (((uintptr_t)W | rb) & 15)) || ((uintptr_t)W & 1)) {
+        b200_set_error("gemm_tc: unsupported shape");
+        return B200_ERR_UNSUPPORTED;
+    }
+    const int tn = M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    const int ntile = (int)((M + tn - 1) / tn), Mpad = ntile * tn, nsb = (int)(K / 256);
+    const size_t sz_img = (size_t)ntile * nsb * img_bytes(tn);
+    uint8_t *scr = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, sz_img + (size_t)nsb * Mpad * 4);
+    if (!scr) return B200_ERR_ALLOC;
+    TcParams p = {};
+    p.W = W; p.rb = (uint32_t)rb; p.N = (int)N; p.K = (int)K; p.M = (int)M; p.Mpad = Mpad; p.nsb = nsb;
+    p.img = scr; p.Bd = (const float *)(scr + sz_img); p.dst = dst; p.dst_stride = dst_stride;
+    {
+        const int64_t warps = (int64_t)Mpad * nsb;
+        b200_gemm_tc_pack_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(x, x_stride, (int)K, (int)M, Mpad, nsb, tn, stage_k(type == B200_TYPE_Q6_K), scr, (float *)p.Bd);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    const bool q6 = type == B200_TYPE_Q6_K;
+    const int ks = stage_k(q6);
+    p.a_slot = q6 ? 2 * main_bytes(ks) : main_bytes(ks) + MIN_BYTES;
+    p.b_slot = (uint32_t)tn * (2u * (uint32_t)ks + (q6 ? 0u : 32u));
+    p.rstride = type == B200_TYPE_Q4_K ? 144u : type == B200_TYPE_Q5_K ? 176u : 240u;        // odd multiples of 16: conflict-free 16-byte row reads
+    // shared memory: the weight-operand ring is fed on chip (2-3 stages cover the expander -> MMA hand-off), the raw ring covers HBM latency
+    // for 18-30 KB per super-block; everything else goes to the activation ring -- a 16-20 KB bulk copy out of L2 takes ~1.5 us and the
+    // stages in flight bound the kernel (profiles/r2_gemm_tc.md)
+    const size_t fixed = 4 * TM * sizeof(float2) + sizeof(TcBars) + 1024;
+    static const int env_na = getenv("GGML_B200_TC_STAGES") ? atoi(getenv("GGML_B200_TC_STAGES")) : 0;
+    static const int env_rs = getenv("GGML_B200_TC_RAW") ? atoi(getenv("GGML_B200_TC_RAW")) : 0;
+    static const int env_dbg = getenv("GGML_B200_TC_DBG") ? atoi(getenv("GGML_B200_TC_DBG")) : 0;
+    p.dbg = env_dbg;
+    const size_t raw_sb = (size_t)TM * p.rstride;
+    p.na = env_na >= 2 && env_na <= 4 ? env_na : 2;
+    p.rs = env_rs >= 2 && env_rs <= 8 ? env_rs : (tn <= 32 ? 4 : tn <= 64 ? 3 : 2);
+    const size_t left = ctx->smem_optin - fixed - (size_t)p.na * p.a_slot - (size_t)p.rs * raw_sb;
+    p.nb = (int)(left / p.b_slot);
+    if (p.nb > 16) p.nb = 16;
+    if (p.nb < 2) { b200_set_error("gemm_tc: shared memory"); return B200_ERR_FAILED; }
+    const size_t smem = (size_t)p.na * p.a_slot + (size_t)p.nb * p.b_slot + (size_t)p.rs * raw_sb + 4 * TM * sizeof(float2) + sizeof(TcBars);
+    // split K when the (row tile x token tile) grid leaves most of the machine idle; slices of >= min_sb super-blocks, partials reduced in slice order
+    static const int max_split = getenv("GGML_B200_TC_KSPLIT") ? atoi(getenv("GGML_B200_TC_KSPLIT")) : 8;
+    const int min_sb = tn <= 32 ? 2 : 4;
+    const int64_t ctas = (N / TM) * ntile;
+    int ksplit = 1;
+    while (ksplit < max_split && ctas * ksplit * 2 <= ctx->sm_count && nsb / (ksplit * 2) >= min_sb) ksplit *= 2;
+    p.sb_per_split = (nsb + ksplit - 1) / ksplit;
+    ksplit = (nsb + p.sb_per_split - 1) / p.sb_per_split;
+    if (ksplit > 1) {
+        p.part = (float *)ctx->get_scratch(SCRATCH_MISC, (size_t)ksplit * M * N * 4);
+        if (!p.part) return B200_ERR_ALLOC;
+    }
+    const dim3 grid((unsigned)(N / TM), (unsigned)ntile, (unsigned)ksplit);
+    static const int env_prof = getenv("GGML_B200_TC_PROF") ? atoi(getenv("GGML_B200_TC_PROF")) : 0;
+    static unsigned long long *prof_buf = nullptr;
+    static int prof_left = 2;
+    if (env_prof && prof_left > 0) {
+        if (!prof_buf) cudaMalloc(&prof_buf, 3 * 256 * 8);
+        cudaMemsetAsync(prof_buf, 0, 3 * 256 * 8, ctx->stream);
+        p.prof = prof_buf;
+    }
+    int rc;
+    switch (type) {
+        case B200_TYPE_Q4_K: rc = launch_tc<B200_TYPE_Q4_K>(ctx, p, tn, grid, smem); break;
+        case B200_TYPE_Q5_K: rc = launch_tc<B200_TYPE_Q5_K>(ctx, p, tn, grid, smem); break;
+        default:             rc = launch_tc<B200_TYPE_Q6_K>(ctx, p, tn, grid, smem); break;
+    }
+    if (p.prof) {
+        static unsigned long long hp[3 * 256];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hp, prof_buf, sizeof(hp), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 3 * 256; i++) if (hp[i] && hp[i] < t0) t0 = hp[i];
+        fprintf(stderr, "gemm_tc timeline (clk after first stamp) type %d N %d K %d M %d tn %d na %d nb %d rs %d ksplit %d\n", type, (int)N, (int)K, (int)M, tn, p.na, p.nb, p.rs, ksplit);
+        for (int g = 0; g < 64 && hp[4 * g]; g++) {
+            fprintf(stderr, " g%2d mma: top %6lld a_full %6lld b_full %6lld issued %6lld | exp: top %6lld a_empty %6lld arrived %6lld", g, (long long)(hp[4 * g] - t0),
+                    (long long)(hp[4 * g + 1] - t0), (long long)(hp[4 * g + 2] - t0), (long long)(hp[4 * g + 3] - t0), (long long)(hp[256 + 4 * g] - t0),
+                    (long long)(hp[256 + 4 * g + 1] - t0), (long long)(hp[256 + 4 * g + 2] - t0));
+            const int sps = 256 / ks;
+            if (g % sps == sps - 1) {
+                const int sb = g / sps;
+                fprintf(stderr, " | drain sb%d: top %6lld acc_full %6lld loaded %6lld", sb, (long long)(hp[512 + 4 * sb] - t0), (long long)(hp[512 + 4 * sb + 1] - t0), (long long)(hp[512 + 4 * sb + 2] - t0));
+            }
+            fprintf(stderr, "\n");
+        }
+        fprintf(stderr, " drain done %lld\n", (long long)(hp[512 + 255] - t0));
+        prof_left--;
+    }
+    if (rc || ksplit == 1) return rc;
+    const int64_t total = M * N;
+    b200_gemm_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p.part, ksplit, (int)N, (int)M, dst, dst_stride);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}

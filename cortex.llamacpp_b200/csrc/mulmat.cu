@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cuda_bf16.h>
 #include "gemm_i8.h"
+#include "gemm_tc.h"
 
 int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);
 int launch_gemv_f32(b200_ctx *ctx, int type, const uint8_t *W, size_t row_bytes, int64_t N, int64_t K, const float *x, size_t x_stride_bytes,
@@ -261,6 +262,20 @@ int op_mul_mat(b200_ctx *ctx, const b200_op *op) {
     // prompt batches: the mma.sync tile GEMM (gemm_mma.cu, all five formats); GGML_B200_PREFER_TCGEN05=1 sends K-quants to the tcgen05
     // GEMM instead (gemm_i8.cu: correct, but its CUDA-core stages keep it below the mma.sync kernel -- DESIGN.md 8)
     static const int prefer_tc = getenv("GGML_B200_PREFER_TCGEN05") ? atoi(getenv("GGML_B200_PREFER_TCGEN05")) : 0;
+    // K-quants from tc_min_m token columns up: the tcgen05 kind::f16 GEMM (gemm_tc.cu: exact-integer f16 operands, min term on the tensor core)
+    static const int64_t tc_min_m = getenv("GGML_B200_TC_MIN_M") ? atoi(getenv("GGML_B200_TC_MIN_M")) : 33;
+    if (M >= tc_min_m && !prefer_tc && x.nb[0] == 4 && gemm_tc_supported(w.type, N, K, M) && !((uintptr_t)w.data & 15) && !(w.nb[2] & 15) && !(w.nb[3] & 15)) {
+        for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
+                const int64_t w2 = i2 / (x.ne[2] / w.ne[2]), w3 = i3 / (x.ne[3] / w.ne[3]);
+                const uint8_t *wp = (const uint8_t *)w.data + w2 * w.nb[2] + w3 * w.nb[3];
+                const float *xp = (const float *)((const char *)x.data + i2 * x.nb[2] + i3 * x.nb[3]);
+                float *dp = (float *)((char *)d.data + i2 * d.nb[2] + i3 * d.nb[3]);
+                int rc = gemm_tc_run(ctx, w.type, wp, rb, N, K, xp, x.nb[1], M, dp, d.nb[1] / 4);
+                if (rc) return rc;
+            }
+        return B200_OK;
+    }
     if (M > mma_max_m && gemm_mma_supported(w.type, N, K, M) && !(prefer_tc && gemm_i8_supported(w.type, N, K, M))) {
         for (int64_t i3 = 0; i3 < x.ne[3]; i3++)
             for (int64_t i2 = 0; i2 < x.ne[2]; i2++) {
