@@ -38,9 +38,9 @@ constexpr uint32_t MIN_BYTES = TM * 16 * 2;             // the min-term tile of 
 constexpr uint32_t LBO = 128, SBO_MIN = 2 * 128;
 __host__ __device__ constexpr uint32_t sbo_main(int ks) { return (uint32_t)(ks / 8) * 128u; }
 
-// activation image of one (token tile, super-block): [stage 0: tn x 2 ks B][min tile: tn x 32 B][stage 1]..[stage 256 / ks - 1]
-__host__ __device__ inline uint32_t img_bytes(int tn) { return (uint32_t)tn * 544u; }
-__host__ __device__ inline uint32_t img_stage_off(int tn, int s, int ks) { return s == 0 ? 0u : (uint32_t)tn * (32u + 2u * (uint32_t)ks * (uint32_t)s); }
+// activation image of one (token tile, super-block): [stage 0: tn x 2 ks B][min tiles u1, u2: 2 x tn x 32 B][stage 1]..[stage 256 / ks - 1]
+__host__ __device__ inline uint32_t img_bytes(int tn) { return (uint32_t)tn * 576u; }
+__host__ __device__ inline uint32_t img_stage_off(int tn, int s, int ks) { return s == 0 ? 0u : (uint32_t)tn * (64u + 2u * (uint32_t)ks * (uint32_t)s); }
 
 struct TcParams {
     const uint8_t *W; uint32_t rb; int N, K, M, Mpad, nsb;
@@ -50,6 +50,7 @@ struct TcParams {
     int sb_per_split; float *part;      // split-K: blockIdx.z covers super-blocks [z * sb_per_split, ...), partials [z][M][N]
     int na, nb, rs;                     // weight-operand ring depth, activation-operand ring depth (64-k stages), raw ring depth (super-blocks)
     uint32_t a_slot, b_slot, rstride;
+    int nbm;                            // activation-side min-tile ring depth (super-blocks)
     unsigned long long *prof;           // optional in-kernel timeline of CTA 0 (GGML_B200_TC_PROF=1): [3 roles][256] clock64 stamps
     int dbg;                            // timing experiments (GGML_B200_TC_DBG): 1 skip expansion, 2 skip MMAs, 4 skip drain math, 8 skip the proxy fence
 };
@@ -99,9 +100,16 @@ __global__ void __launch_bounds__(256) b200_gemm_tc_pack_kernel(const float *__r
 #pragma unroll
     for (int j = 0; j < 4; j++) h[j] = __halves2half2(__int2half_rn(q[2 * j]), __int2half_rn(q[2 * j + 1]));
     *(uint4 *)(im + img_stage_off(tn, s, ks) + (uint32_t)(n >> 3) * sbo_main(ks) + (uint32_t)c * LBO + (uint32_t)(n & 7) * 16) = *(const uint4 *)h;
-    if ((lane & 1) == 0) {
-        const int i = lane >> 1;                       // 16-group of the super-block = K column of the min tile
-        *(__half *)(im + (uint32_t)tn * 2u * (uint32_t)ks + (uint32_t)(n >> 3) * SBO_MIN + (uint32_t)(i >> 3) * LBO + (uint32_t)(n & 7) * 16 + (uint32_t)(i & 7) * 2) = __int2half_rn(pair);
+    // min-term operand: u_j = d * bsum_j (per-32 sums) split into two tf32 parts whose product with the weight side stays exact
+    const int s32 = pair + __shfl_down_sync(0xffffffffu, pair, 2);      // lanes 0, 4, 8, ..: sum of the 32-group lane / 4
+    if ((lane & 3) == 0) {
+        const int j = lane >> 2;
+        const float u = __fmul_rn(d, (float)s32);
+        const float u1 = __uint_as_float(__float_as_uint(u) & 0xffffe000u);
+        const float u2 = __uint_as_float(__float_as_uint(__fsub_rn(u, u1)) & 0xffffe000u);
+        uint8_t *mp = im + (uint32_t)tn * 2u * (uint32_t)ks + (uint32_t)(n >> 3) * SBO_MIN + (uint32_t)(j >> 2) * LBO + (uint32_t)(n & 7) * 16 + (uint32_t)(j & 3) * 4;
+        *(float *)mp = u1;
+        *(float *)(mp + (uint32_t)tn * 32u) = u2;
     }
     if (lane == 0) Bd[(size_t)b * Mpad + tok] = d;
 }
@@ -134,18 +142,21 @@ __device__ __forceinline__ KHeader read_kheader(const uint8_t *blk) {
     return k;
 }
 
-// min-term operand row: columns i = 0..15 hold m_{i / 2} (the activation side holds the per-16 quant sums)
-__device__ __forceinline__ void write_min_row(const KHeader &k, int r, uint8_t *a_min) {
-    const __half2 off = __floats2half2_rn(-1024.0f, -1024.0f);
-    uint32_t o[8];
+// min-term operand row: v_j = dmin * m_j (exact in f32: 11 x 6 bits) as two tf32 parts hi + lo (8 k-columns of 4 bytes each); the activation
+// side holds u_j = d_a * bsum_j as u1 + u2: the tensor core accumulates hi*u1 + hi*u2 + lo*u1 (every product exact, 2^-21 of the term dropped)
+__device__ __forceinline__ void write_min_row(const KHeader &k, int r, uint8_t *a_hi, uint8_t *a_lo) {
+    uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const uint32_t src = j < 4 ? k.m_lo : k.m_hi;
-        o[j] = h2_u32(__hadd2(u32_h2(__byte_perm(src, 0x64646464u, 0x4040 | (j & 3) | ((j & 3) << 8))), off));
+        const float v = __fmul_rn(k.dmin, (float)(((j < 4 ? k.m_lo : k.m_hi) >> (8 * (j & 3))) & 0xffu));
+        hi[j] = __float_as_uint(v) & 0xffffe000u;
+        lo[j] = __float_as_uint(__fsub_rn(v, __uint_as_float(hi[j])));
     }
-    uint8_t *p = a_min + (uint32_t)(r >> 3) * SBO_MIN + (uint32_t)(r & 7) * 16;
-    *(uint4 *)p = make_uint4(o[0], o[1], o[2], o[3]);
-    *(uint4 *)(p + LBO) = make_uint4(o[4], o[5], o[6], o[7]);
+    const uint32_t off = (uint32_t)(r >> 3) * SBO_MIN + (uint32_t)(r & 7) * 16;
+    *(uint4 *)(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *(uint4 *)(a_hi + off + LBO) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *(uint4 *)(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *(uint4 *)(a_lo + off + LBO) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
 }
 
 // Q4_K / Q5_K, 128-k stages: thread (row r, half h) expands the 32-byte quant group 2 s + h of stage s = sub-blocks j = 2 (2 s + h) (low
@@ -213,7 +224,9 @@ __device__ __forceinline__ void expand_q6k(const uint8_t *blk, int s, int h, int
 
 // ---------------------------------------------------------------------------------------------------------------- the GEMM
 struct TcBars {
-    uint64_t raw_full[8], raw_empty[8], a_full[4], a_empty[4], b_full[16], b_empty[16], acc_full[2], acc_empty[2];
+    // operand stage g uses full[g & 15] / empty[g & 15] (phase (g >> 4) & 1) whatever the two operand rings' depths are: the expanders (8
+    // arrivals) and the activation producer (1 arrival + the copies' bytes) complete `full`, ONE tcgen05.commit completes `empty`
+    uint64_t raw_full[8], raw_empty[8], full[16], empty[16], acc_full[2], acc_empty[2];
     uint32_t tmem_base, pad[3];
 };
 
@@ -229,7 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
     uint8_t *a_ring = tsm;
     uint8_t *b_ring = a_ring + (size_t)p.na * p.a_slot;
     uint8_t *raw = b_ring + (size_t)p.nb * p.b_slot;
-    float2 *meta = (float2 *)(raw + (size_t)p.rs * TM * p.rstride);       // [4][TM]: (d, dmin) of the row's super-block
+    uint8_t *amin = raw + (size_t)p.rs * TM * p.rstride;                  // [hi | lo] tf32 tiles of the current super-block's mins (2 x 4 KB)
+    uint8_t *bmin = amin + (Q6 ? 0 : 2 * MIN_BYTES);                      // [nbm][u1 | u2] (2 x TN x 32 B)
+    float2 *meta = (float2 *)(bmin + (Q6 ? 0 : (size_t)p.nbm * TN * 64));       // [4][TM]: (d, dmin) of the row's super-block
     TcBars *S = (TcBars *)(meta + 4 * TM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,8 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; i++) { mbar_init(&S->raw_full[i], N_EXP * 32); mbar_init(&S->raw_empty[i], N_EXP); }
-        for (int i = 0; i < 4; i++) { mbar_init(&S->a_full[i], N_EXP); mbar_init(&S->a_empty[i], 1); }
-        for (int i = 0; i < 16; i++) { mbar_init(&S->b_full[i], 1); mbar_init(&S->b_empty[i], 1); }
+        for (int i = 0; i < 16; i++) { mbar_init(&S->full[i], N_EXP + 1); mbar_init(&S->empty[i], 1); }
         for (int i = 0; i < 2; i++) { mbar_init(&S->acc_full[i], 1); mbar_init(&S->acc_empty[i], N_DRAIN); }
         mbar_fence_init();
     }
@@ -256,53 +270,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
         // ------------------------------------------------------------ activation producer: one bulk copy per operand stage
         {
             const uint8_t *src = p.img + ((size_t)blockIdx.y * p.nsb + sb0) * img_bytes(TN);
-            int slot = 0, use = 0;                     // ring position of stage g: slot = g % nb, use = g / nb (kept incrementally: nb is a run-time value)
+            int slot = 0, mslot = 0;                   // activation ring slot g % nb, min-tile ring slot b % nbm (kept incrementally: run-time depths)
             for (int g = 0; g < SPS * nsb; g++) {
                 const int b = g >> LG_SPS, s = g & (SPS - 1);
                 if (p.dbg & 32) break;
-                if (use > 0) tc_wait(&S->b_empty[slot], (use - 1) & 1);
-                const uint32_t bytes = (uint32_t)TN * (2u * KS + ((s == 0 && !Q6) ? 32u : 0u));
+                if (g >= nb) tc_wait(&S->empty[(g - nb) & 15], ((g - nb) >> 4) & 1);
+                const bool with_min = s == 0 && !Q6;
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&S->b_full[slot], bytes);
-                    bulk_g2s(b_ring + (size_t)slot * p.b_slot, src + (size_t)b * img_bytes(TN) + img_stage_off(TN, s, KS), bytes, &S->b_full[slot]);
+                    uint64_t *bar = &S->full[g & 15];
+                    mbar_arrive_expect_tx(bar, (uint32_t)TN * (2u * KS + (with_min ? 64u : 0u)));
+                    const uint8_t *sp = src + (size_t)b * img_bytes(TN) + img_stage_off(TN, s, KS);
+                    bulk_g2s(b_ring + (size_t)slot * p.b_slot, sp, (uint32_t)TN * 2u * KS, bar);
+                    if (with_min) bulk_g2s(bmin + (size_t)mslot * TN * 64, sp + (size_t)TN * 2 * KS, (uint32_t)TN * 64u, bar);
                 }
                 __syncwarp();
-                if (++slot == nb) { slot = 0; use++; }
+                if (with_min && ++mslot == p.nbm) mslot = 0;
+                if (++slot == nb) slot = 0;
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
         {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);      // f16 x f16 -> f32, K-major A and B
-            int slot = 0, use = 0, bslot = 0, buse = 0;
             const uint64_t dm = make_desc(0, LBO, SBO_MAIN), dn = make_desc(0, LBO, SBO_MIN);      // descriptors = these + (address >> 4)
-            for (int g = 0; g < SPS * nsb; g++) {
+            const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);      // tf32 x tf32 -> f32
+            const uint32_t am = smem_u32(amin);
+            int slot = 0, bslot = 0, mslot = 0;
+            const int G = SPS * nsb;
+            for (int g = 0; g < G; g++) {
                 const int b = g >> LG_SPS, s = g & (SPS - 1), pr = b & 1;
-                if (s == 0 && b >= 2) tc_wait(&S->acc_empty[pr], ((b >> 1) - 1) & 1);
                 TPROF(0, 4 * g);
-                tc_wait(&S->a_full[slot], use & 1);
+                if (s == 0 && b >= 2) tc_wait(&S->acc_empty[pr], ((b >> 1) - 1) & 1);
+                if (!(p.dbg & 32)) tc_wait(&S->full[g & 15], (g >> 4) & 1);
                 TPROF(0, 4 * g + 1);
-                if (!(p.dbg & 32)) tc_wait(&S->b_full[bslot], buse & 1);
-                TPROF(0, 4 * g + 2);
                 tc_fence_after();
-                if (elect_one()) {
                 const uint32_t aa = smem_u32(a_ring + (size_t)slot * p.a_slot), bb = smem_u32(b_ring + (size_t)bslot * p.b_slot);
-                const uint32_t d_main = tmem + (uint32_t)pr * (2 * TN), d_min = d_main + TN;
+                const uint32_t d_main = tmem + (uint32_t)pr * TN, d_min = tmem + 2 * TN;
+                constexpr int NK = KS / 16, NK0 = NK;
+                if (elect_one() && !(p.dbg & 2)) {
 #pragma unroll
-                for (int ks = 0; ks < KS / 16 && !(p.dbg & 2); ks++) {
-                    const uint64_t bd = dm + ((bb + ks * 2 * LBO) >> 4);
-                    mma_f16(d_main, dm + ((aa + ks * 2 * LBO) >> 4), bd, idesc, (s | ks) ? 1u : 0u);
-                    if (Q6) mma_f16(d_main, dm + ((aa + MAIN_BYTES + ks * 2 * LBO) >> 4), bd, idesc, 1u);
-                }
-                if (!Q6 && s == 0) mma_f16(d_min, dn + ((aa + MAIN_BYTES) >> 4), dn + ((bb + TN * 2 * KS) >> 4), idesc, 0u);
-                tc_commit(&S->a_empty[slot]);              // operand slots free once these MMAs have read them
-                tc_commit(&S->b_empty[bslot]);
-                if (s == SPS - 1) tc_commit(&S->acc_full[pr]);   // the super-block's integers are complete
+                    for (int ks = 0; ks < NK0; ks++) {
+                        const uint64_t bd = dm + ((bb + ks * 2 * LBO) >> 4);
+                        mma_f16(d_main, dm + ((aa + ks * 2 * LBO) >> 4), bd, idesc, (s | ks) ? 1u : 0u);
+                        if (Q6) mma_f16(d_main, dm + ((aa + MAIN_BYTES + ks * 2 * LBO) >> 4), bd, idesc, 1u);
+                    }
                 }
                 __syncwarp();
+                TPROF(0, 4 * g + 2);
+                if (elect_one()) {
+                    if (!(p.dbg & 2)) {
+#pragma unroll
+                        for (int ks = NK0; ks < NK; ks++) {
+                            const uint64_t bd = dm + ((bb + ks * 2 * LBO) >> 4);
+                            mma_f16(d_main, dm + ((aa + ks * 2 * LBO) >> 4), bd, idesc, (s | ks) ? 1u : 0u);
+                            if (Q6) mma_f16(d_main, dm + ((aa + MAIN_BYTES + ks * 2 * LBO) >> 4), bd, idesc, 1u);
+                        }
+                        if (!Q6 && s == 0) {                   // min term, accumulated over ALL super-blocks: hi*u1 + hi*u2 + lo*u1
+                            const uint32_t bm = smem_u32(bmin + (size_t)mslot * TN * 64);
+                            mma_tf32(d_min, dn + (am >> 4), dn + (bm >> 4), idesc32, b ? 1u : 0u);
+                            mma_tf32(d_min, dn + (am >> 4), dn + ((bm + TN * 32) >> 4), idesc32, 1u);
+                            mma_tf32(d_min, dn + ((am + MIN_BYTES) >> 4), dn + (bm >> 4), idesc32, 1u);
+                        }
+                    }
+                    tc_commit(&S->empty[g & 15]);              // operand slots free once these MMAs have read them
+                    if (s == SPS - 1) tc_commit(&S->acc_full[pr]);   // the super-block's integers are complete
+                }
+                __syncwarp();
+                if (!Q6 && s == 0 && ++mslot == p.nbm) mslot = 0;
                 TPROF(0, 4 * g + 3);
-                if (++slot == na) { slot = 0; use++; }
-                if (++bslot == nb) { bslot = 0; buse++; }
+                if (++slot == na) slot = 0;
+                if (++bslot == nb) bslot = 0;
             }
         }
     } else if (warp < 2 + N_EXP) {
@@ -339,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
         };
         for (int b = 0; b < rs - 1 && b < nsb; b++) issue_raw(b);
         const uint8_t *const myrow = Wt + (size_t)r * p.rb;
-        int r_slot = 0, r_use = 0, slot = 0, use = 0;  // raw ring position of super-block b, operand ring position of stage 4 b + s
+        int r_slot = 0, r_use = 0, slot = 0, g = 0;    // raw ring position of super-block b, weight-operand slot of stage g = SPS b + s
         for (int b = 0; b < nsb; b++) {
             if (b + rs - 1 < nsb) issue_raw(b + rs - 1);
             if (!(p.dbg & 16)) tc_wait(&S->raw_full[r_slot], r_use & 1);
@@ -356,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
 #pragma unroll 1
             for (int s = 0; s < SPS; s++) {
                 if (warp == 2) TPROF(1, 4 * (SPS * b + s));
-                if (use > 0) tc_wait(&S->a_empty[slot], (use - 1) & 1);
+                if (g >= na) tc_wait(&S->empty[(g - na) & 15], ((g - na) >> 4) & 1);
                 if (warp == 2) TPROF(1, 4 * (SPS * b + s) + 1);
                 uint8_t *as = a_ring + (size_t)slot * p.a_slot;
                 if (p.dbg & 1) {}
@@ -364,13 +401,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
                 else expand_k45<Q5>(blk, kh, qh, s, h, r, as);
                 if (s == 0 && h == 0 && !(p.dbg & 128)) {
                     if (Q6) meta[(b & 3) * TM + r] = make_float2(half_bits_to_float(*(const unsigned short *)(blk + 208)), 0.0f);
-                    else { write_min_row(kh, r, as + MAIN_BYTES); meta[(b & 3) * TM + r] = make_float2(kh.d, kh.dmin); }
+                    else { write_min_row(kh, r, amin, amin + MIN_BYTES); meta[(b & 3) * TM + r] = make_float2(kh.d, kh.dmin); }
                 }
                 if (!(p.dbg & 8)) fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S->a_full[slot]);
+                if (lane == 0) mbar_arrive(&S->full[g & 15]);
                 if (warp == 2) TPROF(1, 4 * (SPS * b + s) + 2);
-                if (++slot == na) { slot = 0; use++; }
+                if (++slot == na) slot = 0;
+                g++;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->raw_empty[r_slot]);
@@ -392,33 +430,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
             tc_fence_after();
             const float2 mt = meta[(b & 3) * TM + r];
             const float4 *da4 = (const float4 *)(p.Bd + (size_t)(sb0 + b) * p.Mpad + tok0 + c_base);
-            const uint32_t t_main = tmem + lane_addr + (uint32_t)pr * (2 * TN) + (uint32_t)c_base;
+            const uint32_t t_main = tmem + lane_addr + (uint32_t)pr * TN + (uint32_t)c_base;
 #pragma unroll
-            for (int c0 = 0; c0 < CH; c0 += 8) {
-                uint32_t P[8], Mn[8];
+            for (int c0 = 0; c0 < CH; c0 += 16) {
+                uint32_t P[16];
                 if (!(p.dbg & 64)) {
-                    tmem_ld8(t_main + c0, P);
-                    if (!Q6) tmem_ld8(t_main + TN + c0, Mn);
+                    tmem_ld16(t_main + c0, P);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) P[j] = Mn[j] = 0;
+                    for (int j = 0; j < 16; j++) P[j] = 0;
                 }
-                if (c0 == CH - 8) {                        // every accumulator column of this warp is in registers: the tensor core may overwrite the buffer
+                if (c0 == CH - 16) {                       // every accumulator column of this warp is in registers: the tensor core may overwrite the buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S->acc_empty[pr]);
                     if (warp == 2 + N_EXP) TPROF(2, 4 * b + 2);
                 }
                 if (p.dbg & 4) continue;
-                const float4 d0 = __ldg(da4 + (c0 >> 2)), d1 = __ldg(da4 + (c0 >> 2) + 1);
-                const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    float u = mt.x * __uint_as_float(P[j]);
-                    if (!Q6) u = fmaf(-mt.y, __uint_as_float(Mn[j]), u);
-                    out[c0 + j] = fmaf(da[j], u, out[c0 + j]);
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 d4 = __ldg(da4 + (c0 >> 2) + j4);
+                    const float da[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) out[c0 + 4 * j4 + j] = fmaf(da[j] * mt.x, __uint_as_float(P[4 * j4 + j]), out[c0 + 4 * j4 + j]);
                 }
+            }
+        }
+        if (!Q6 && !(p.dbg & 64)) {
+            // the min term of all super-blocks sits in its own accumulator (the last acc_full covers its MMAs too)
+            const uint32_t t_min = tmem + lane_addr + 2 * TN + (uint32_t)c_base;
+#pragma unroll
+            for (int c0 = 0; c0 < CH; c0 += 16) {
+                uint32_t Mn[16];
+                tmem_ld16(t_min + c0, Mn);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) out[c0 + j] -= __uint_as_float(Mn[j]);
             }
         }
         if (warp == 2 + N_EXP) TPROF(2, 255);
@@ -494,8 +542,8 @@ int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N,
     }
     const bool q6 = type == B200_TYPE_Q6_K;
     const int ks = stage_k(q6);
-    p.a_slot = q6 ? 2 * main_bytes(ks) : main_bytes(ks) + MIN_BYTES;
-    p.b_slot = (uint32_t)tn * (2u * (uint32_t)ks + (q6 ? 0u : 32u));
+    p.a_slot = q6 ? 2 * main_bytes(ks) : main_bytes(ks);
+    p.b_slot = (uint32_t)tn * 2u * (uint32_t)ks;
     p.rstride = type == B200_TYPE_Q4_K ? 144u : type == B200_TYPE_Q5_K ? 176u : 240u;        // odd multiples of 16: conflict-free 16-byte row reads
     // shared memory: the weight-operand ring is fed on chip (2-3 stages cover the expander -> MMA hand-off), the raw ring covers HBM latency
     // for 18-30 KB per super-block; everything else goes to the activation ring -- a 16-20 KB bulk copy out of L2 takes ~1.5 us and the
@@ -508,11 +556,19 @@ int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N,
     const size_t raw_sb = (size_t)TM * p.rstride;
     p.na = env_na >= 2 && env_na <= 4 ? env_na : 2;
     p.rs = env_rs >= 2 && env_rs <= 8 ? env_rs : (tn <= 32 ? 4 : tn <= 64 ? 3 : 2);
-    const size_t left = ctx->smem_optin - fixed - (size_t)p.na * p.a_slot - (size_t)p.rs * raw_sb;
-    p.nb = (int)(left / p.b_slot);
-    if (p.nb > 16) p.nb = 16;
+    // min-term tiles (Q4_K / Q5_K): one weight-side buffer (the operand ring is one super-block deep: na == stages per super-block) and a ring
+    // of activation-side tiles as deep as the activation ring reaches in super-blocks
+    const int sps = 256 / ks;
+    if (!q6) p.na = sps;
+    size_t left = ctx->smem_optin - fixed - (size_t)p.na * p.a_slot - (size_t)p.rs * raw_sb - (q6 ? 0 : 2 * MIN_BYTES);
+    p.nb = 0; p.nbm = 0;
+    for (int nb = 16; nb >= 2; nb--) {
+        const int nbm = q6 ? 0 : (nb + sps - 1) / sps;
+        if ((size_t)nb * p.b_slot + (size_t)nbm * tn * 64 <= left) { p.nb = nb; p.nbm = nbm; break; }
+    }
     if (p.nb < 2) { b200_set_error("gemm_tc: shared memory"); return B200_ERR_FAILED; }
-    const size_t smem = (size_t)p.na * p.a_slot + (size_t)p.nb * p.b_slot + (size_t)p.rs * raw_sb + 4 * TM * sizeof(float2) + sizeof(TcBars);
+    const size_t smem = (size_t)p.na * p.a_slot + (size_t)p.nb * p.b_slot + (size_t)p.rs * raw_sb + (q6 ? 0 : 2 * MIN_BYTES + (size_t)p.nbm * tn * 64) +
+                        4 * TM * sizeof(float2) + sizeof(TcBars);
     // split K when the (row tile x token tile) grid leaves most of the machine idle; slices of >= min_sb super-blocks, partials reduced in slice order
     static const int max_split = getenv("GGML_B200_TC_KSPLIT") ? atoi(getenv("GGML_B200_TC_KSPLIT")) : 8;
     const int min_sb = tn <= 32 ? 2 : 4;
