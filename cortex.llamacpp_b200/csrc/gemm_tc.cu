@@ -51,9 +51,21 @@ struct TcParams {
     int na, nb, rs;                     // weight-operand ring depth, activation-operand ring depth (64-k stages), raw ring depth (super-blocks)
     uint32_t a_slot, b_slot, rstride;
     int nbm;                            // activation-side min-tile ring depth (super-blocks)
+    // grouped mode (MUL_MAT_ID prompt batches): token tile = chunk of <= 128 (token, slot) pairs of one expert; g_E = 0: dense
+    const int32_t *g_off, *g_pairs; int g_E, g_n_used, g_b_ne1; size_t g_expert_stride, g_d_nb1, g_d_nb2;
     unsigned long long *prof;           // optional in-kernel timeline of CTA 0 (GGML_B200_TC_PROF=1): [3 roles][256] clock64 stamps
     int dbg;                            // timing experiments (GGML_B200_TC_DBG): 1 skip expansion, 2 skip MMAs, 4 skip drain math, 8 skip the proxy fence
 };
+
+// grouped mode: chunk -> (expert, first pair, pairs in the chunk); cnt = 0: the chunk does not exist (fewer pairs than the upper bound)
+__device__ __forceinline__ void tc_g_lookup(const TcParams &p, int chunk, int &e, int &first, int &cnt) {
+    cnt = 0; first = 0;
+    for (e = 0; e < p.g_E; e++) {
+        const int o0 = p.g_off[e], n = p.g_off[e + 1] - o0, nch = (n + 127) / 128;
+        if (chunk < nch) { first = o0 + chunk * 128; cnt = min(128, n - chunk * 128); return; }
+        chunk -= nch;
+    }
+}
 
 // a hang on the GPU box costs a whole lease: every wait in this kernel gives up (trap -> launch failure) after ~1 s.  No printf: a
 // kernel that can print pays for the FIFO set-up at every launch.
@@ -77,14 +89,22 @@ __device__ __forceinline__ bool elect_one() {
 // ---------------------------------------------------------------------------------------------------------------- activation pack
 // one warp per (token, super-block); lane owns 8 consecutive elements
 __global__ void __launch_bounds__(256) b200_gemm_tc_pack_kernel(const float *__restrict__ x, size_t x_stride, int K, int M, int Mpad, int nsb, int tn, int ks,
-                                                                uint8_t *__restrict__ img, float *__restrict__ Bd) {
+                                                                uint8_t *__restrict__ img, float *__restrict__ Bd, const TcParams g) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (gw >= (int64_t)Mpad * nsb) return;
     const int b = (int)(gw % nsb), tok = (int)(gw / nsb), tile = tok / tn, n = tok % tn;
     float v[8];
-    if (tok < M) {
-        const float *xp = (const float *)((const char *)x + (size_t)tok * x_stride) + b * 256 + lane * 8;
+    int64_t col = tok;                                 // source column of this token slot (dense: itself)
+    bool live = tok < M;
+    if (g.g_E) {                                       // grouped: slot n of chunk `tile` = a (token, slot) pair of the chunk's expert
+        int e, first, cnt;
+        tc_g_lookup(g, tile, e, first, cnt);
+        live = n < cnt;
+        if (live) { const int pair = g.g_pairs[first + n]; col = g.g_b_ne1 == 1 ? pair / g.g_n_used : pair; }
+    }
+    if (live) {
+        const float *xp = (const float *)((const char *)x + (size_t)col * x_stride) + b * 256 + lane * 8;
         const float4 a = *(const float4 *)xp, c = *(const float4 *)(xp + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
     } else {
@@ -249,6 +269,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TM, tok0 = blockIdx.y * TN;
+    int g_e = 0, g_first = 0, g_cnt = TN;
+    if (p.g_E) {                                       // grouped: this token tile is a chunk of one expert's pairs (or does not exist)
+        tc_g_lookup(p, blockIdx.y, g_e, g_first, g_cnt);
+        if (g_cnt == 0) return;
+    }
     const int sb0 = (int)blockIdx.z * p.sb_per_split;
     const int nsb = min(p.sb_per_split, p.nsb - sb0);
     const int na = p.na, nb = p.nb, rs = p.rs;
@@ -345,7 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
     } else if (warp < 2 + N_EXP) {
         // ------------------------------------------------------------ expanders: stage raw GGUF blocks (cp.async), write operand tiles
         const int et = threadIdx.x - 64, r = et & (TM - 1), h = et >> 7;
-        const uint8_t *const Wt = p.W + (size_t)row0 * p.rb + (size_t)sb0 * BLK;
+        const uint8_t *const Wt = p.W + (size_t)g_e * p.g_expert_stride + (size_t)row0 * p.rb + (size_t)sb0 * BLK;
         // staging: a thread owns chunks c = et + 256 i of a super-block's TM x CPR 16-byte chunks (consecutive lanes = consecutive chunks of
         // a row piece: whole sectors).  Row pointers and slot offsets are fixed for the launch; only the block offset moves.
         constexpr int NCP = (TM * CPR + N_EXP * 32 - 1) / (N_EXP * 32);
@@ -472,10 +497,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) b200_gemm_tc_kernel(const TcPar
         if (warp == 2 + N_EXP) TPROF(2, 255);
         float *const dstv = gridDim.z > 1 ? p.part + (size_t)blockIdx.z * p.M * p.N : p.dst;
         const size_t stride = gridDim.z > 1 ? (size_t)p.N : p.dst_stride;
+        if (p.g_E) {
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const int tok = tok0 + c_base + c;
-            if (tok < p.M) dstv[(size_t)tok * stride + row0 + r] = out[c];
+            for (int c = 0; c < CH; c++) {
+                const int tl = c_base + c;
+                if (tl < g_cnt) {
+                    const int pair = p.g_pairs[g_first + tl];
+                    p.dst[(size_t)(pair % p.g_n_used) * p.g_d_nb1 + (size_t)(pair / p.g_n_used) * p.g_d_nb2 + row0 + r] = out[c];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int tok = tok0 + c_base + c;
+                if (tok < p.M) dstv[(size_t)tok * stride + row0 + r] = out[c];
+            }
         }
     }
     tc_fence_before();
@@ -519,24 +555,17 @@ bool gemm_tc_supported(int type, int64_t N, int64_t K, int64_t M) {
     return !off && N % TM == 0 && K % 256 == 0 && M >= 1;
 }
 
-// dst[tok * dst_stride + n] = sum_k W[n, k] * x[k, tok]; x f32 with column stride x_stride bytes
-int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, int64_t M,
-                float *dst, size_t dst_stride) {
-    if (!gemm_tc_supported(type, N, K, M) || (type != B200_TYPE_Q6_K && (((uintptr_t)W | rb) & 15)) || ((uintptr_t)W & 1)) {
-        b200_set_error("gemm_tc: unsupported shape");
-        return B200_ERR_UNSUPPORTED;
-    }
-    const int tn = M <= 32 ? 32 : M <= 64 ? 64 : 128;
-    const int ntile = (int)((M + tn - 1) / tn), Mpad = ntile * tn, nsb = (int)(K / 256);
+// common host side: activation pack, shared-memory geometry, split-K, launch.  p: W, rb, N, K, M (dense) or the group fields (grouped; M = 0).
+static int tc_go(b200_ctx *ctx, int type, TcParams &p, const float *x, size_t x_stride, int tn, int ntile, bool allow_split) {
+    const int64_t N = p.N, K = p.K, M = p.M;
+    const int Mpad = ntile * tn, nsb = (int)(K / 256);
     const size_t sz_img = (size_t)ntile * nsb * img_bytes(tn);
     uint8_t *scr = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, sz_img + (size_t)nsb * Mpad * 4);
     if (!scr) return B200_ERR_ALLOC;
-    TcParams p = {};
-    p.W = W; p.rb = (uint32_t)rb; p.N = (int)N; p.K = (int)K; p.M = (int)M; p.Mpad = Mpad; p.nsb = nsb;
-    p.img = scr; p.Bd = (const float *)(scr + sz_img); p.dst = dst; p.dst_stride = dst_stride;
+    p.Mpad = Mpad; p.nsb = nsb; p.img = scr; p.Bd = (const float *)(scr + sz_img);
     {
         const int64_t warps = (int64_t)Mpad * nsb;
-        b200_gemm_tc_pack_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(x, x_stride, (int)K, (int)M, Mpad, nsb, tn, stage_k(type == B200_TYPE_Q6_K), scr, (float *)p.Bd);
+        b200_gemm_tc_pack_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(x, x_stride, (int)K, (int)M, Mpad, nsb, tn, stage_k(type == B200_TYPE_Q6_K), scr, (float *)p.Bd, p);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -574,7 +603,7 @@ int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N,
     const int min_sb = tn <= 32 ? 2 : 4;
     const int64_t ctas = (N / TM) * ntile;
     int ksplit = 1;
-    while (ksplit < max_split && ctas * ksplit * 2 <= ctx->sm_count && nsb / (ksplit * 2) >= min_sb) ksplit *= 2;
+    while (allow_split && ksplit < max_split && ctas * ksplit * 2 <= ctx->sm_count && nsb / (ksplit * 2) >= min_sb) ksplit *= 2;
     p.sb_per_split = (nsb + ksplit - 1) / ksplit;
     ksplit = (nsb + p.sb_per_split - 1) / p.sb_per_split;
     if (ksplit > 1) {
@@ -619,8 +648,35 @@ int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N,
     }
     if (rc || ksplit == 1) return rc;
     const int64_t total = M * N;
-    b200_gemm_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p.part, ksplit, (int)N, (int)M, dst, dst_stride);
+    b200_gemm_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p.part, ksplit, (int)N, (int)M, p.dst, p.dst_stride);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
+}
+
+// dst[tok * dst_stride + n] = sum_k W[n, k] * x[k, tok]; x f32 with column stride x_stride bytes
+int gemm_tc_run(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, int64_t M,
+                float *dst, size_t dst_stride) {
+    if (!gemm_tc_supported(type, N, K, M) || (type != B200_TYPE_Q6_K && (((uintptr_t)W | rb) & 15)) || ((uintptr_t)W & 1)) {
+        b200_set_error("gemm_tc: unsupported shape");
+        return B200_ERR_UNSUPPORTED;
+    }
+    const int tn = M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    TcParams p = {};
+    p.W = W; p.rb = (uint32_t)rb; p.N = (int)N; p.K = (int)K; p.M = (int)M; p.dst = dst; p.dst_stride = dst_stride;
+    return tc_go(ctx, type, p, x, x_stride, tn, (int)((M + tn - 1) / tn), true);
+}
+
+// MUL_MAT_ID for prompt batches: the (token, slot) pairs counting-sorted by expert on the device (mulmat.cu) become token tiles of <= 128 pairs
+// per expert; every tile runs the same GEMM against its expert's matrix.  g.max_chunks: upper bound of sum_e ceil(count_e / 128).
+int gemm_tc_run_grouped(b200_ctx *ctx, int type, const uint8_t *W, size_t rb, int64_t N, int64_t K, const float *x, size_t x_stride, const MmGroupDesc &g, float *dst) {
+    if (!gemm_tc_supported(type, N, K, 128) || (type != B200_TYPE_Q6_K && (((uintptr_t)W | rb | g.expert_stride) & 15)) || (((uintptr_t)W | g.expert_stride) & 1)) {
+        b200_set_error("gemm_tc: unsupported shape");
+        return B200_ERR_UNSUPPORTED;
+    }
+    TcParams p = {};
+    p.W = W; p.rb = (uint32_t)rb; p.N = (int)N; p.K = (int)K; p.M = 0; p.dst = dst;
+    p.g_off = g.off; p.g_pairs = g.pairs; p.g_E = g.E; p.g_n_used = g.n_used; p.g_b_ne1 = g.b_ne1;
+    p.g_expert_stride = g.expert_stride; p.g_d_nb1 = g.d_nb1; p.g_d_nb2 = g.d_nb2;
+    return tc_go(ctx, type, p, x, x_stride, 128, g.max_chunks, false);
 }

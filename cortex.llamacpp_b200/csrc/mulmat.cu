@@ -429,6 +429,10 @@ int op_mul_mat_id(b200_ctx *ctx, const b200_op *op) {
         // prompt batches (>= 32 pairs per expert on average): token tiles of 128 pairs per expert through the tile GEMM (gemm_mma.cu)
         if (npairs >= 32 * E && gemm_mma_supported(as.type, N, K, 128)) {
             g.max_chunks = (int)std::min<int64_t>(npairs, npairs / 128 + E);
+            // K-quants: the tcgen05 kind::f16 GEMM in grouped mode (gemm_tc.cu); Q4_0 / Q8_0: the mma.sync tile GEMM
+            static const int prefer_i8 = getenv("GGML_B200_PREFER_TCGEN05") ? atoi(getenv("GGML_B200_PREFER_TCGEN05")) : 0;
+            if (!prefer_i8 && gemm_tc_supported(as.type, N, K, 128) && !(((uintptr_t)as.data | as.nb[2]) & 15))
+                return gemm_tc_run_grouped(ctx, as.type, (const uint8_t *)as.data, rb, N, K, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], g, (float *)d.data);
             return gemm_mma_run_grouped(ctx, as.type, (const uint8_t *)as.data, rb, N, K, (const float *)b.data, b.ne[1] == 1 ? b.nb[2] : b.nb[1], g, (float *)d.data);
         }
         uint8_t *act = (uint8_t *)ctx->get_scratch(SCRATCH_ACT, L.col_bytes * (size_t)acols);

@@ -250,8 +250,9 @@ def test_mul_mat_id_grouped_by_expert_on_device(b200, ctx, t, b_ne1, n_tok, K):
 @pytest.mark.parametrize("t", [R.Q4_K, R.Q6_K, R.Q5_K, R.Q4_0, R.Q8_0])
 @pytest.mark.parametrize("b_ne1,n_tok,K", [(1, 200, 1024), (2, 160, 2304)])
 def test_mul_mat_id_prompt_batch_grouped_gemm(b200, ctx, t, b_ne1, n_tok, K):
-    """MoE prompt batches (>= 32 pairs per expert on average): the pairs of an expert form token tiles of 128 for the mma.sync tile GEMM
-    (gemm_mma.cu grouped mode); unbalanced routing -> one expert with several tiles, experts with a ragged or no tile"""
+    """MoE prompt batches (>= 32 pairs per expert on average): the pairs of an expert form token tiles of 128 for the tile GEMMs in grouped
+    mode (K-quants: gemm_tc.cu on tcgen05, Q4_0 / Q8_0: gemm_mma.cu); unbalanced routing -> one expert with several tiles, experts with a
+    ragged or no tile"""
     rng = np.random.default_rng(31 + t + b_ne1 + n_tok)
     n_expert, n_used, N = 8, 2, 256
     As = rand_quant_rows(t, n_expert * N, K, rng)
