@@ -19,6 +19,7 @@
 // skipped before any K/V byte is requested (unified multi-slot KV cache).  Splits are merged by a small
 // combine kernel (log-sum-exp).  A tcgen05 variant for long prefill is future work.
 #include "common.cuh"
+#include "fattn_tc.h"
 
 namespace {
 
@@ -1249,6 +1250,17 @@ int op_flash_attn_ext(b200_ctx *ctx, const b200_op *op) {
         else CUDA_TRY(cudaLaunchKernelEx(&cfg, b200_fattn_f16acc_kernel<64, KV_F16>, p));
         ctx->launches++;
         return B200_OK;
+    }
+    // prompt-sized query blocks at head size 128: the tcgen05 kernel (fattn_tc.cu: 128 query rows of one head per CTA, S and the per-tile
+    // P V in TMEM).  Soft-capping and ALiBi slopes stay on the mma.sync kernel below.
+    static const int use_tc = getenv("GGML_B200_FA_TC") ? atoi(getenv("GGML_B200_FA_TC")) : 1;
+    static const int tc_min_q = getenv("GGML_B200_FA_TC_MIN_Q") ? atoi(getenv("GGML_B200_FA_TC_MIN_Q")) : 64;
+    if (use_tc && D == 128 && p.n_q >= tc_min_q && kv_kind(k.type) == kv_kind(v.type) && kv_kind(k.type) >= 0 && p.softcap == 0.0f && p.max_bias == 0.0f &&
+        p.n_kv % 64 == 0 && !(((uintptr_t)q.data | q.nb[1] | q.nb[2] | (uintptr_t)d.data) & 15) && (!has_mask || !(((uintptr_t)m.data | m.nb[1]) & 15))) {
+        FaTcArgs a = {};
+        a.q = p.q; a.q_nb1 = p.q_nb1; a.q_nb2 = p.q_nb2; a.k = p.k; a.k_nb1 = p.k_nb1; a.k_nb2 = p.k_nb2; a.v = p.v; a.v_nb1 = p.v_nb1; a.v_nb2 = p.v_nb2;
+        a.mask = p.mask; a.m_nb1 = p.m_nb1; a.dst = p.dst; a.n_q = p.n_q; a.n_kv = p.n_kv; a.H = p.H; a.gq = p.gq; a.scale = p.scale;
+        return fattn_tc_launch(ctx, a, kv_kind(k.type));
     }
     // single-token decode over an f16 cache: the vector kernel (one warp per 32 positions, all heads of the group).  Parity green,
     // but measured SLOWER than the mma tile kernel in round 1 (10.5 + 9.2 us with 24 splits to merge vs 9.5 + 5.1 us; 499 vs

@@ -91,7 +91,8 @@ CASES = [
     # D, H, Hkv, n_q, n_kv
     (128, 32, 8, 1, 256), (128, 32, 8, 1, 4096), (128, 32, 32, 1, 512), (128, 64, 8, 1, 1024), (64, 32, 4, 1, 512),
     (128, 32, 8, 3, 512), (128, 32, 8, 32, 1024), (128, 8, 8, 35, 512), (64, 32, 4, 7, 256), (128, 16, 1, 2, 512),
-    (128, 8, 2, 128, 256), (128, 8, 2, 512, 640), (64, 8, 2, 250, 512),        # prompt-sized query blocks (causal mask: the live-tile map path)
+    (128, 8, 2, 128, 256), (128, 8, 2, 512, 640), (64, 8, 2, 250, 512),        # prompt-sized query blocks (causal mask: the live-tile map path;
+    (128, 8, 2, 100, 512), (128, 32, 8, 300, 1024), (128, 4, 4, 2048, 2304),   #  D = 128 from 64 query columns up: the tcgen05 kernel, fattn_tc.cu)
 ]
 
 
@@ -196,3 +197,26 @@ def test_flash_attn_cpu_exact_f16_accumulator_mode(b200, ctx, D, H, Hkv, n_q, n_
     print("fa_exact: bit-identical elements %.4f, max rel err %.3g (fast mode %.3g)" % (same, err, err_fast))
     # softmax weights go through a correctly rounded exp on both sides: every fp16 rounding of the accumulator agrees
     assert same >= 0.999 and err <= 1e-6, (same, err)
+
+
+@pytest.mark.parametrize("tk", [R.F16, R.Q8_0, R.Q4_0])
+def test_flash_attn_tcgen05_prompt_kernel_is_the_one_that_runs(b200, ctx, tk):
+    """D = 128, >= 64 query columns, no soft-cap / ALiBi: ONE launch of fattn_tc.cu (no live-tile map, no KV splits, no combine kernel);
+    a multi-slot prompt batch (every 64 query rows attend to their own slot's cells) exercises the per-tile liveness test: whole tiles dead
+    for a CTA, rows that are fully masked inside a live tile, rows whose first live tile comes late"""
+    rng = np.random.default_rng(77 + tk)
+    D, H, Hkv, n_q, n_kv, slots = 128, 8, 2, 256, 1024, 4
+    q, kb, vb, mask = make_case(rng, D, H, Hkv, n_q, n_kv, tk)
+    cells = n_kv // slots
+    mask[:] = -np.inf
+    for i in range(n_q):
+        s = i // 64
+        mask[i, s * cells: s * cells + 1 + (i * 37) % cells] = 0
+    scale = 1.0 / np.sqrt(D)
+    l0 = ctx.launches()
+    got = run_fa(b200, ctx, q, kb, vb, mask, D, n_kv, Hkv, tk, scale)
+    assert ctx.launches() - l0 == 1, "the tcgen05 prompt kernel is a single launch"
+    exact = exact_attention(q, kb, vb, mask, D, n_kv, Hkv, tk, scale)
+    assert np.isfinite(got).all() and nmse(got, exact) <= 1e-10, nmse(got, exact)
+    want = R.orc_flash_attn(q, kb, vb, mask, D, n_kv, Hkv, tk, tk, scale)
+    assert nmse(got, want) <= (5e-4 if tk == R.F16 else 1e-10)
