@@ -28,9 +28,13 @@ struct GemvActDesc {
     float          eps;
 };
 
+// L2 look-ahead: constant weight ranges of the launches that follow this one (graph.cu fills them in)
+constexpr int GEMV_MAX_PF = 4;
+struct GemvPf { const void *ptr; size_t bytes; };
+
 int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, int ncols, bool w_const,
-                const void *pf_ptr, size_t pf_bytes);
+                const GemvPf *pf, int npf);
 // batch-1 K-quant kernel (gemv_bs1.cu): 1 = launched, 0 = not eligible, < 0 = error
 int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, bool w_const,
-                        const void *pf_ptr, size_t pf_bytes, int l2pf);
+                        const GemvPf *pf, int npf, int l2pf);
 int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);

@@ -52,8 +52,9 @@ struct Bs1Params {
     int            w_const, use_pdl, ncw;      // ncw: consumer warps (blockDim / 32 - 1)
     int            cs;                         // thread-block cluster size sharing the activation prologue (1 = none)
     uint32_t       off_aq64, off_aq128, off_ad, off_s32, off_s16, off_ring;   // 0 = layout not needed (aq*, s*)
-    const uint8_t *pf_ptr;
-    unsigned long long pf_bytes;
+    const uint8_t *pf_ptr[GEMV_MAX_PF];     // L2 look-ahead: weight ranges of the launches that follow (gemv.h)
+    unsigned long long pf_bytes[GEMV_MAX_PF];
+    int            npf, pf_late;               // pf_late: issue after this launch's own copies (HBM idles through tail, boundary and prologue)
     unsigned long long *prof;           // optional [grid][32] globaltimer stamps (tools/bs1_prof.py)
 };
 
@@ -193,6 +194,20 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
     }
 }
 
+// the weights of the launches that follow: ask the L2 to start fetching this CTA's 1/G of every range (fire and forget)
+__device__ __forceinline__ void bs1_l2_lookahead(const Bs1Params &p, int G, int c, int lane) {
+    constexpr unsigned long long PIECE = 8192;
+    for (int r = 0; r < p.npf; r++) {
+        const unsigned long long per = ((p.pf_bytes[r] / G) + 15ull) & ~15ull;
+        const unsigned long long b0 = per * c, lim = p.pf_bytes[r] & ~15ull;
+        const unsigned long long b1 = b0 + per < lim ? b0 + per : lim;
+        for (unsigned long long o = b0 + (unsigned long long)lane * PIECE; o < b1; o += 32 * PIECE) {
+            const uint32_t n = (uint32_t)(b1 - o < PIECE ? b1 - o : PIECE);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr[r] + o), "r"(n) : "memory");
+        }
+    }
+}
+
 template <int TYPES>
 __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const Bs1Params p) {
     const int BS1_NCW = p.ncw, BS1_THREADS = (p.ncw + 1) * 32;
@@ -259,20 +274,11 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
             if (first_pass) {
                 first_pass = false;
                 PROF(2);
-                // the NEXT matmul's weights: ask the L2 to start fetching this CTA's 1/G of them now
-                if (p.pf_bytes) {
-                    const unsigned long long per = ((p.pf_bytes / G) + 15ull) & ~15ull;
-                    const unsigned long long b0 = per * c, lim = p.pf_bytes & ~15ull;
-                    const unsigned long long b1 = b0 + per < lim ? b0 + per : lim;
-                    constexpr unsigned long long PIECE = 8192;
-                    for (unsigned long long o = b0 + (unsigned long long)lane * PIECE; o < b1; o += 32 * PIECE) {
-                        const uint32_t n = (uint32_t)(b1 - o < PIECE ? b1 - o : PIECE);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + o), "r"(n) : "memory");
-                    }
-                }
+                if (p.npf && !p.pf_late) bs1_l2_lookahead(p, G, c, lane);
             }
         }
         PROF(3);
+        if (p.npf && p.pf_late) bs1_l2_lookahead(p, G, c, lane);
         if (p.use_pdl && !waited) pdl_wait();
         return;
     }
@@ -423,7 +429,7 @@ int bs1_max_clusters(b200_ctx *ctx, int cs, int threads, size_t smem_bytes) {
 
 // 1 = launched, 0 = not eligible (caller falls through to the general kernel), < 0 = error
 int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, bool w_const,
-                        const void *pf_ptr, size_t pf_bytes, int l2pf) {
+                        const GemvPf *pf, int npf, int l2pf) {
     if (!g_bs1_env) {
         if (const char *e = getenv("GGML_B200_BS1_CTAS")) g_bs1_ctas = atoi(e);          // CTAs per SM (1 or 2; default 2)
         if (const char *e = getenv("GGML_B200_BS1_SMEM_KB")) g_bs1_smem_kb = atoi(e);    // shared memory per CTA
@@ -488,11 +494,21 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     if (ns < 2) return 0;
     p.nstages = ns; p.stage_bytes = stage;
     const size_t smem_bytes = off + (size_t)ns * stage;
-    if (l2pf && pf_ptr && pf_bytes) {
-        p.pf_ptr = (const uint8_t *)pf_ptr;
-        p.pf_bytes = pf_bytes < ((size_t)48 << 20) ? pf_bytes : ((size_t)48 << 20);
-        const uintptr_t mis = (uintptr_t)p.pf_ptr & 15;
-        if (mis) { p.pf_ptr += 16 - mis; p.pf_bytes = p.pf_bytes > 16 ? p.pf_bytes - 16 : 0; }
+    if (l2pf && pf) {
+        // l2pf 1: the next launch's first matrix, issued with this launch's first copies (round 1: measured neutral);
+        // l2pf 2: every range the graph handed down, issued AFTER this launch's own copies
+        static const size_t cap_mb = getenv("GGML_B200_L2PF_MB") ? (size_t)atoi(getenv("GGML_B200_L2PF_MB")) : 96;
+        size_t budget_pf = l2pf == 1 ? ((size_t)48 << 20) : (cap_mb << 20);
+        p.pf_late = l2pf >= 2;
+        for (int r = 0; r < npf && r < (l2pf == 1 ? 1 : GEMV_MAX_PF) && budget_pf > 0; r++) {
+            if (!pf[r].ptr || pf[r].bytes < 64) continue;
+            const uint8_t *q = (const uint8_t *)pf[r].ptr;
+            size_t nb = pf[r].bytes < budget_pf ? pf[r].bytes : budget_pf;
+            const uintptr_t mis = (uintptr_t)q & 15;
+            if (mis) { q += 16 - mis; nb -= 16; }
+            p.pf_ptr[p.npf] = q; p.pf_bytes[p.npf] = nb; p.npf++;
+            budget_pf -= nb < budget_pf ? nb : budget_pf;
+        }
     }
     if (ctx->prof_buf) {                 // rotating per-launch slots so consecutive launches can be laid on one timeline
         p.prof = (unsigned long long *)ctx->prof_buf + (size_t)(ctx->prof_launch % 8) * 296 * 32;

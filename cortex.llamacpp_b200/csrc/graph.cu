@@ -93,7 +93,7 @@ struct ExecNode {
     b200_op op;                                  // EX_OP
     GemvSegDesc seg[GEMV_MAX_SEG]; int nseg = 0; // EX_GEMV
     int64_t K = 0; GemvActDesc act; int ncols = 0; bool w_const = false;
-    const void *pf_ptr = nullptr; size_t pf_bytes = 0;
+    GemvPf pf[GEMV_MAX_PF] = {}; int npf = 0;    // L2 look-ahead ranges (weights of the launches that follow)
     RopeStoreDesc rs;                            // EX_ROPE_STORE
     int kv_slot = -1;                            // index of this node's K destination in the KV pointer table (V = +1)
     std::shared_ptr<std::vector<DsNode>> ds;     // EX_DSTEP: the run of nodes one persistent decode-step launch executes (dstep.cu)
@@ -476,16 +476,35 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
         out.push_back(e);
         i++;
     }
-    // weight look-ahead: every fused GEMV asks the L2 to start fetching the weights of the next GEMV-like node
-    const ExecNode *next = nullptr;
-    for (int i = (int)out.size() - 1; i >= 0; i--) {
-        ExecNode &e = out[i];
-        const bool mm_op = e.kind == EX_OP && e.op.op == B200_OP_MUL_MAT && b200_type_is_quant(e.op.src[0].type) && (e.op.src[0].flags & B200_TENSOR_FLAG_WEIGHT);
-        if (e.kind == EX_GEMV && next) {
-            if (next->kind == EX_GEMV) { e.pf_ptr = next->seg[0].W; e.pf_bytes = (size_t)next->seg[0].N * next->seg[0].rb; }
-            else { e.pf_ptr = next->op.src[0].data; e.pf_bytes = (size_t)next->op.src[0].ne[1] * b200_row_bytes(next->op.src[0].type, next->op.src[0].ne[0]); }
+    // weight look-ahead: a fused GEMV asks the L2 to start fetching the constant weights of the GEMV-like nodes that follow.
+    // Adjacent successor: its matrices.  When attention sits in between (rope+store, flash_attn, combine move ~3 MB per layer and
+    // leave HBM idle for ~15 us), the matrices of the next TWO nodes (wo, then gate|up): they stream into the L2 under the
+    // attention kernels; the node in between then skips its own look-ahead (already on its way).
+    auto gemv_like = [](const ExecNode &e) {
+        return e.kind == EX_GEMV || (e.kind == EX_OP && e.op.op == B200_OP_MUL_MAT && b200_type_is_quant(e.op.src[0].type) && (e.op.src[0].flags & B200_TENSOR_FLAG_WEIGHT));
+    };
+    auto add_ranges = [](ExecNode &e, const ExecNode &nx) {
+        if (nx.kind == EX_GEMV) {
+            if (!nx.w_const) return;
+            for (int s = 0; s < nx.nseg && e.npf < GEMV_MAX_PF; s++) {
+                if (nx.seg[s].expert_id) continue;           // the expert is only known on the device
+                e.pf[e.npf].ptr = nx.seg[s].W; e.pf[e.npf].bytes = (size_t)nx.seg[s].N * nx.seg[s].rb; e.npf++;
+            }
+        } else if (e.npf < GEMV_MAX_PF) {
+            e.pf[e.npf].ptr = nx.op.src[0].data; e.pf[e.npf].bytes = (size_t)nx.op.src[0].ne[1] * b200_row_bytes(nx.op.src[0].type, nx.op.src[0].ne[0]); e.npf++;
         }
-        if (e.kind == EX_GEMV || mm_op) next = &e;
+    };
+    std::vector<char> covered(out.size(), 0);
+    for (size_t i = 0; i < out.size(); i++) {
+        ExecNode &e = out[i];
+        if (e.kind != EX_GEMV) continue;
+        size_t j = i + 1;
+        while (j < out.size() && !gemv_like(out[j])) j++;
+        if (j >= out.size()) continue;
+        if (j == i + 1) { if (!covered[j]) add_ranges(e, out[j]); continue; }
+        add_ranges(e, out[j]); covered[j] = 1;
+        size_t k = j + 1;
+        if (k < out.size() && gemv_like(out[k])) { add_ranges(e, out[k]); covered[k] = 1; }
     }
     if (layer_fusion && ctx->opt_dstep) pack_dstep(ctx, out);
     return B200_OK;
@@ -508,7 +527,7 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
             rc = dstep_prepare(ctx, *e.ds, &prog);           // cached by content: a hit (no upload) once prepare_dstep() has seen this list
             if (!rc) rc = dstep_launch(ctx, prog);
         }
-        else if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf_ptr, e.pf_bytes);
+        else if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf, e.npf);
         else if (e.kind == EX_ROPE_STORE) rc = launch_rope_store(ctx, e.rs);
         else rc = dispatch(ctx, &e.op);
         if (rc) return rc;
