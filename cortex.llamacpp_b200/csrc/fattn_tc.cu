@@ -41,6 +41,7 @@ __device__ __forceinline__ void ft_wait(uint64_t *bar, uint32_t parity) {
         if (++spins > (1u << 24)) __trap();        // a hang on the GPU box costs a whole lease
     }
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ bool ft_elect() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -98,6 +99,23 @@ __device__ __forceinline__ void load_row32(const char *row, int qd, float (&v)[3
     }
 }
 
+// bytes of one head's row in the cache: 128 f16 / 4 q8_0 blocks / 4 q4_0 blocks
+__host__ __device__ constexpr int raw_row_bytes(int kt) { return kt == KV_F16 ? HD * 2 : kt == KV_Q8_0 ? (HD / 32) * 34 : (HD / 32) * 18; }
+
+// the 64 cache rows of KV tile t (one head) -> raw[cell][raw_row_bytes], by asynchronous copies from the 256 worker threads: the tile
+// is on its way while the tensor core and the softmax work on the previous one.  f16 rows are 16-byte aligned, quantised rows 8-byte.
+template <int KT>
+__device__ __forceinline__ void fetch_tile(uint8_t *raw, const char *base, uint64_t nb1, int t, int wt) {
+    constexpr int RB = raw_row_bytes(KT), PB = KT == KV_F16 ? 16 : 8, PC = RB / PB;      // pieces per row: 16 / 17 / 9
+    const char *g = base + (uint64_t)t * TC * nb1;
+    const uint32_t sb = smem_u32(raw);
+    for (int i = wt; i < TC * PC; i += 256) {
+        const int c = i / PC, pc = i - c * PC;
+        if (KT == KV_F16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + (uint32_t)(c * RB + pc * PB)), "l"(g + (uint64_t)c * nb1 + pc * PB) : "memory");
+        else              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sb + (uint32_t)(c * RB + pc * PB)), "l"(g + (uint64_t)c * nb1 + pc * PB) : "memory");
+    }
+}
+
 template <int KT>
 __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTcArgs p) {
     constexpr bool QUANT = KT != KV_F16;
@@ -106,7 +124,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
     uint8_t *k_hi = q_lo + (QUANT ? Q_BYTES : 0), *k_lo = k_hi + KV_BYTES;
     uint8_t *v_hi = k_lo + (QUANT ? KV_BYTES : 0), *v_lo = v_hi + KV_BYTES;
     uint8_t *p_hi = v_lo + (QUANT ? KV_BYTES : 0), *p_lo = p_hi + P_BYTES;
-    FtShared *S = (FtShared *)(p_lo + P_BYTES);
+    uint8_t *raw_k = p_lo + P_BYTES, *raw_v = raw_k + TC * raw_row_bytes(KT);          // the NEXT tile's cache rows, as stored (cp.async)
+    FtShared *S = (FtShared *)(raw_v + TC * raw_row_bytes(KT));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = (int)gridDim.x - 1 - (int)blockIdx.x;       // late query blocks (most live tiles under a causal mask) first
@@ -167,48 +186,70 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
     const uint64_t dd = make_desc(0, LBO, SBO_D), dc = make_desc(0, LBO, SBO_C);
     int live_tiles = 0;
     const int n_tiles = p.n_kv / TC;
+    const char *kbase = p.k + (size_t)hkv * p.k_nb2, *vbase = p.v + (size_t)hkv * p.v_nb2;
+    // mask values of (my row, my 32 cells of tile t); rows past n_q read as -inf
+    uint4 mk[4];
+    auto load_mask = [&](int t) {
+        if (q_idx < p.n_q) {
+            if (p.mask) {
+                const uint4 *mp = (const uint4 *)(p.mask + (size_t)q_idx * p.m_nb1 + (size_t)(t * TC + hf * 32) * 2);
+#pragma unroll
+                for (int j = 0; j < 4; j++) mk[j] = mp[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) mk[j] = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) mk[j] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+        }
+    };
+    // software pipeline: tile t + 1's cache rows (cp.async -> raw_k / raw_v) and mask words (registers) are requested while tile t
+    // is in the tensor core / softmax; ncu of the first version: long_scoreboard 6.1 stall cycles per issue, tensor pipe 8.5 % active
+    if (warp > 0 && n_tiles > 0) {
+        fetch_tile<KT>(raw_k, kbase, p.k_nb1, 0, wt);
+        fetch_tile<KT>(raw_v, vbase, p.v_nb1, 0, wt);
+        load_mask(0);
+    }
     for (int t = 0; t < n_tiles; t++) {
-        // ---- mask values of (my row, my 32 cells) + liveness of the whole tile ----
-        uint4 mk[4];
+        // ---- liveness of the whole tile (anything but -inf in any row) ----
         int live = 0;
         if (warp > 0) {
             if (q_idx < p.n_q) {
                 if (p.mask) {
-                    const uint4 *mp = (const uint4 *)(p.mask + (size_t)q_idx * p.m_nb1 + (size_t)(t * TC + hf * 32) * 2);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        mk[j] = mp[j];
                         const uint32_t w[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) live |= ((w[e] & 0xffffu) != 0xfc00u) | ((w[e] >> 16) != 0xfc00u);      // anything but -inf
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) mk[j] = make_uint4(0, 0, 0, 0);
-                    live = 1;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) mk[j] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                } else live = 1;
             }
+            cp_async_wait_all();                                // my pieces of tile t's rows have landed; the barrier below publishes them
         }
-        if (!__syncthreads_or(live)) continue;
+        if (!__syncthreads_or(live)) {                          // fully masked: nobody reads the raw rows; move on to the next tile
+            if (warp > 0 && t + 1 < n_tiles) {
+                fetch_tile<KT>(raw_k, kbase, p.k_nb1, t + 1, wt);
+                fetch_tile<KT>(raw_v, vbase, p.v_nb1, t + 1, wt);
+                load_mask(t + 1);
+            }
+            continue;
+        }
         const uint32_t par = (uint32_t)(live_tiles & 1);
         live_tiles++;
 
         if (warp > 0) {
             // ---- stage K (K-major) and V (MN-major): thread = (cell, quarter of the dims) ----
             const int c = wt & (TC - 1), qd = wt >> 6;
-            const size_t cell = (size_t)t * TC + c;
             float v[32];
-            load_row32<KT>(p.k + cell * p.k_nb1 + (size_t)hkv * p.k_nb2, qd, v);
+            load_row32<KT>((const char *)raw_k + c * raw_row_bytes(KT), qd, v);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float w[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
                 const uint32_t off = (uint32_t)(c >> 3) * SBO_D + (uint32_t)(qd * 4 + j) * LBO + (uint32_t)(c & 7) * 16;
                 store_chunk<QUANT>(w, k_hi + off, k_lo + off);
             }
-            load_row32<KT>(p.v + cell * p.v_nb1 + (size_t)hkv * p.v_nb2, qd, v);
+            load_row32<KT>((const char *)raw_v + c * raw_row_bytes(KT), qd, v);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float w[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
@@ -218,6 +259,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
             fence_proxy_async();
         }
         __syncthreads();
+        if (warp > 0 && t + 1 < n_tiles) {                      // every thread has converted its part: the raw buffers are free again
+            fetch_tile<KT>(raw_k, kbase, p.k_nb1, t + 1, wt);
+            fetch_tile<KT>(raw_v, vbase, p.v_nb1, t + 1, wt);
+        }
 
         if (warp == 0) {
             // ---- S = Q K^T (+ Q K_lo^T + Q_lo K^T for quantised operands) ----
@@ -262,6 +307,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
                     mx = fmaxf(mx, fmaxf(s[i], s[i + 1]));
                 }
             }
+            if (t + 1 < n_tiles) load_mask(t + 1);              // mk is consumed: the next tile's words travel during the rest of this one
             S->xmax[hf][r] = mx;
             named_bar_sync(1, 256);
             const float m_new = fmaxf(m_run, fmaxf(mx, S->xmax[hf ^ 1][r]));
@@ -341,7 +387,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
 template <int KT>
 int launch_ft(b200_ctx *ctx, const FaTcArgs &p) {
     constexpr bool QUANT = KT != KV_F16;
-    const size_t smem = (size_t)Q_BYTES * (QUANT ? 2 : 1) + (size_t)KV_BYTES * (QUANT ? 4 : 2) + 2 * P_BYTES + sizeof(FtShared);
+    const size_t smem = (size_t)Q_BYTES * (QUANT ? 2 : 1) + (size_t)KV_BYTES * (QUANT ? 4 : 2) + 2 * P_BYTES + 2 * (size_t)TC * raw_row_bytes(KT) + sizeof(FtShared);
     auto kern = b200_fattn_tc_kernel<KT>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {

@@ -54,6 +54,7 @@ struct Bs1Params {
     uint32_t       off_aq64, off_aq128, off_ad, off_s32, off_s16, off_ring;   // 0 = layout not needed (aq*, s*)
     const uint8_t *pf_ptr[GEMV_MAX_PF];     // L2 look-ahead: weight ranges of the launches that follow (gemv.h)
     unsigned long long pf_bytes[GEMV_MAX_PF];
+    int            window;                     // first-fill window in stages (0 = the whole ring at once)
     int            npf, pf_late;               // pf_late: issue after this launch's own copies (HBM idles through tail, boundary and prologue)
     unsigned long long *prof;           // optional [grid][32] globaltimer stamps (tools/bs1_prof.py)
 };
@@ -152,6 +153,7 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
             }
         }
         float norm_scale = 1.0f;
+        if (p.prof) { asm volatile("" : "+f"(xa[0][0].x)); PROFQ(26); }
         if (p.act_mode == ACT_F32_NORM) {
             double s = 0.0;
 #pragma unroll
@@ -160,7 +162,9 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
 #pragma unroll
                 for (int j = 0; j < 8; j++) s += (double)__fmul_rn(v[j], v[j]);
             }
+            if (p.prof) { asm volatile("" : "+d"(s)); PROFQ(27); }
             norm_scale = bs1_norm_scale(p, s_red, s, warp, lane);
+            if (p.prof) { asm volatile("" : "+f"(norm_scale)); PROFQ(28); }
         }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -254,9 +258,15 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
         const uint64_t pol = l2_policy_evict_first();
         int i = lane, use = 0;
         bool first_pass = true;
+        const int win = p.window > 0 ? p.window : BS1_MAX_STAGES;
         PROF(1);
         while (__any_sync(0xffffffffu, lane < ns && i < nchunks)) {
-            if (lane < ns && i < nchunks && (use == 0 || mbar_test_wait(&empty[lane], (use - 1) & 1))) {
+            // first fill: a sliding window of `win` stages in flight per SM (stage l is issued when stage l - win has landed) instead of the
+            // whole ring at once -- 32 MB queued chip-wide would put 3-5 us of DRAM queueing in front of the first stage AND of the
+            // activation loads; 8-12 stages cover the bandwidth-delay product.  Afterwards a stage is re-armed the moment it is released.
+            bool go = lane < ns && i < nchunks;
+            if (go) go = use == 0 ? (lane < win || mbar_test_wait(&full[lane - win], 0)) : mbar_test_wait(&empty[lane], (use - 1) & 1);
+            if (go) {
                 int s = 0, lo_s = lo[0], hi_s = hi[0], c0 = 0;
 #pragma unroll
                 for (int t = 1; t < GEMV_MAX_SEG; t++) if (t < p.nseg && i >= ch0[t]) { s = t; lo_s = lo[t]; hi_s = hi[t]; c0 = ch0[t]; }
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
 #undef PROF
 }
 
-int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0, g_bs1_warps = 0, g_bs1_cluster = 4, g_bs1_lpr32 = 1;
+int g_bs1_ctas = 0, g_bs1_smem_kb = 0, g_bs1_off = 0, g_bs1_warps = 0, g_bs1_cluster = 4, g_bs1_lpr32 = 1, g_bs1_window = 64;     // window: measured best at 48-64 KB per SM (+1.5 % on the decode step)
 bool g_bs1_env = false;
 
 template <int TYPES>
@@ -437,6 +447,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         if (const char *e = getenv("GGML_B200_BS1_CLUSTER")) g_bs1_cluster = atoi(e);   // 1 = off, 2 or 4 CTAs share the prologue of long vectors
         if (const char *e = getenv("GGML_B200_BS1_LPR32")) g_bs1_lpr32 = atoi(e);
         if (const char *e = getenv("GGML_B200_BS1_WARPS")) g_bs1_warps = atoi(e);       // 16 or 32 warps per CTA (default 32)
+        if (const char *e = getenv("GGML_B200_BS1_WINDOW")) g_bs1_window = atoi(e);     // first-fill window in KB per SM (0 = whole ring at once)
         g_bs1_env = true;
     }
     if (g_bs1_off || nseg < 1 || nseg > GEMV_MAX_SEG || K <= 0 || (K & 255) || K > 65536) return 0;
@@ -493,6 +504,9 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     if (ns >= ncw) ns = ns / ncw * ncw;                  // every consumer warp owns the same number of stages
     if (ns < 2) return 0;
     p.nstages = ns; p.stage_bytes = stage;
+    // window in bytes, not stages: GGML_B200_BS1_WINDOW is in KB per SM
+    p.window = g_bs1_window > 0 ? (int)(((size_t)g_bs1_window * 1024 + stage - 1) / stage) : 0;
+    if (p.window >= ns) p.window = 0;
     const size_t smem_bytes = off + (size_t)ns * stage;
     if (l2pf && pf) {
         // l2pf 1: the next launch's first matrix, issued with this launch's first copies (round 1: measured neutral);

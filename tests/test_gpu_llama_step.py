@@ -167,6 +167,32 @@ def test_llama_decode_cuda_graph_replay(b200, ctx):
     ctx.set_option("cuda_graphs", 0)
 
 
+def test_l2_lookahead_modes_do_not_change_results(b200, ctx):
+    """option l2_prefetch (0 off, 1 next matmul with the first copies, 2 following launches' ranges after the launch's own copies, across
+    the attention chain): a pure L2 hint -- logits bit-identical in every mode (gemv_bs1.cu bs1_l2_lookahead, graph.cu look-ahead pass)"""
+    import torch
+    from __graft_entry__ import load_llama_graph
+    lg = load_llama_graph()
+    g = lg.LlamaGraph(b200, model="mid-d128", ftype="q4_k_m", kv="f16", n_ctx=256, max_tokens=1)
+    rng = np.random.default_rng(5)
+    emb, pos, mask = g.set_inputs_host(1, 9, 256, rng)
+    g.inp_embd[:g.E] = torch.from_numpy(emb.reshape(-1)).cuda()
+    g.pos[:1] = torch.from_numpy(pos).cuda()
+    g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    ops = g.build(1, 9, 256)
+    ctx.set_option("fusion", 2); ctx.set_option("pdl", 1); ctx.set_option("cuda_graphs", 0)
+    outs = []
+    for mode in (0, 1, 2):
+        ctx.set_option("l2_prefetch", mode)
+        g.logits.zero_(); torch.cuda.synchronize()
+        ctx.compute(ops); ctx.sync()
+        outs.append(g.logits[:g.V].cpu().numpy().copy())
+    ctx.set_option("l2_prefetch", 0); ctx.set_option("pdl", 0)
+    assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 @pytest.mark.parametrize("kv", ["f16", "q8_0"])
 def test_llama_decode_graph_replay_follows_kv_head(b200, ctx, kv):
     """a real decode loop: every step stores its K/V rows one cell further (the only thing that changes in llama.cpp's

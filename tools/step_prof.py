@@ -23,7 +23,8 @@ n_gemv = 4 * layers + 1
 ctx.compute(ops); ctx.sync()
 p = prof.cpu().numpy().reshape(8, 296, 32).astype(np.int64)
 names = {0: "cta start", 1: "producer ready", 2: "first copies issued", 3: "all copies issued", 4: "past pdl_wait", 5: "prologue done",
-         6: "first stage landed", 7: "first chunk done", 24: "x landed (w0)", 25: "quantised (w0)"}
+         6: "first stage landed", 7: "first chunk done", 24: "x landed (w0)", 25: "quantised (w0)", 2: "first copies issued", 26: "x in regs (w0)",
+         27: "sumsq done (w0)", 28: "norm scale (w0)"}
 kinds = ["qkv(norm)", "wo(+res)", "gate|up(norm)", "down(swiglu+res)"]
 order = sorted(range(8), key=lambda s: p[s][:, 0][p[s][:, 0] > 0].min() if (p[s][:, 0] > 0).any() else 1 << 62)
 first_idx = n_gemv - 8
@@ -36,7 +37,7 @@ for j, sidx in enumerate(order):
     t0 = q[:, 0][q[:, 0] > 0].min()
     w = q[:, 8:8 + 16]; end = w[w > 0].max()
     line = "launch %2d %-18s gap-from-prev-end %6s | " % (li, kind, "-" if prev_end is None else str(t0 - prev_end))
-    for i in (4, 24, 25, 5, 6, 7, 3):
+    for i in (2, 4, 26, 27, 28, 24, 25, 5, 6, 7, 3):
         v = q[:, i][q[:, i] > 0] - t0
         if len(v): line += "%s %d | " % (names[i], int(np.median(v)))
     line += "last warp done %d" % (end - t0)
