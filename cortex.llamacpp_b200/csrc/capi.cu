@@ -140,7 +140,8 @@ int b200_synchronize(b200_ctx *ctx) {
 int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     std::string k(key);
     int *slot = k == "fusion" ? &ctx->opt_fusion : k == "pdl" ? &ctx->opt_pdl : k == "l2_prefetch" ? &ctx->opt_l2_prefetch :
-                k == "debug_skip" ? &ctx->opt_debug_skip : (k == "fa_exact" || k == "cpu_exact") ? &ctx->opt_cpu_exact : k == "dstep" ? &ctx->opt_dstep : nullptr;
+                k == "debug_skip" ? &ctx->opt_debug_skip : (k == "fa_exact" || k == "cpu_exact") ? &ctx->opt_cpu_exact : k == "dstep" ? &ctx->opt_dstep :
+                k == "ffn_pair" ? &ctx->opt_ffn_pair : nullptr;
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
     else if (slot) {
         if (*slot != value) {                 // captured graphs bake these options in: drop them

@@ -128,6 +128,7 @@ struct b200_ctx {
     int           opt_cuda_graphs = 0;
     int           opt_fusion      = 2;      // 0 off, 1 two-op fusions, 2 + llama layer fusions for decode ubatches
     int           opt_pdl         = 0;
+    int           opt_ffn_pair    = 1;      // FFN decode fusion: the gate|up GEMV writes silu(gate) * up itself (gemv_bs1.cu pair mode); 0 = swiglu in the down GEMV's prologue
     int           opt_l2_prefetch = 0;      // L2 look-ahead of the next matmul's weights: measured neutral on B200 (profiles/r1_gemv_diag.md), off
     int           opt_cpu_exact   = 0;      // parity mode (exact.cu, fattn.cu): every float sum in the order of the reference's AVX2 CPU build, the fp16
                                             // V accumulator of f16-cache attention, correctly rounded exp/sin/cos.  Slow; proves summation order is the only difference

@@ -539,7 +539,8 @@ int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K) {
 
 // General entry: up to GEMV_MAX_SEG weight matrices that share K and the activation columns.
 int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, int ncols, bool w_const,
-                const GemvPf *pf, int npf) {
+                const GemvPf *pf, int npf, bool *pair) {
+    if (pair && ncols != 1) { *pair = false; pair = nullptr; }
     const void *pf_ptr = pf && npf > 0 ? pf[0].ptr : nullptr;
     const size_t pf_bytes = pf && npf > 0 ? pf[0].bytes : 0;
     if (nseg <= 0 || nseg > GEMV_MAX_SEG || ncols <= 0) return B200_OK;
@@ -581,8 +582,9 @@ int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, con
     if (ncols == 1) {
         // batch-1 decode over K-quants: the compact half-SM kernel (gemv_bs1.cu); anything it does not take falls through
         const int l2pf = g_gemv_l2pf >= 0 ? g_gemv_l2pf : ctx->opt_l2_prefetch;
-        const int rc = gemv_bs1_try_launch(ctx, segs, nseg, K, ga, w_const, pf, npf, l2pf);
+        const int rc = gemv_bs1_try_launch(ctx, segs, nseg, K, ga, w_const, pf, npf, l2pf, pair);
         if (rc != 0) return rc < 0 ? rc : B200_OK;
+        if (pair) *pair = false;
     }
     const ActLayout L = ActLayout::make(q8k, K);
     constexpr int MAXW = GEMV_THREADS / 32 - 1;

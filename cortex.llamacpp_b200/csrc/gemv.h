@@ -33,8 +33,10 @@ constexpr int GEMV_MAX_PF = 4;
 struct GemvPf { const void *ptr; size_t bytes; };
 
 int gemv_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, int ncols, bool w_const,
-                const GemvPf *pf, int npf);
+                const GemvPf *pf, int npf, bool *pair = nullptr);
+// `pair` (FFN gate|up launch, 2 segments): request the paired epilogue -- h = silu(seg0 row) * seg1 row written to seg[0].dst and NOTHING
+// else; *pair tells the caller whether the launch did it (only the batch-1 kernel can), so that the down projection reads h directly
 // batch-1 K-quant kernel (gemv_bs1.cu): 1 = launched, 0 = not eligible, < 0 = error
 int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, bool w_const,
-                        const GemvPf *pf, int npf, int l2pf);
+                        const GemvPf *pf, int npf, int l2pf, bool *pair = nullptr);
 int gemv_max_cols(const b200_ctx *ctx, int type, size_t rb, int64_t K);

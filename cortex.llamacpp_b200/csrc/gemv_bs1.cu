@@ -55,6 +55,8 @@ struct Bs1Params {
     const uint8_t *pf_ptr[GEMV_MAX_PF];     // L2 look-ahead: weight ranges of the launches that follow (gemv.h)
     unsigned long long pf_bytes[GEMV_MAX_PF];
     int            window;                     // first-fill window in stages (0 = the whole ring at once)
+    int            pair;                       // 1: seg 0 = gate, seg 1 = up (same rows): the epilogue writes silu(gate) * up into seg[0].dst, nothing else
+    uint32_t       off_gval, off_gflag;        // pair mode: this CTA's gate row results + "ready" words
     int            npf, pf_late;               // pf_late: issue after this launch's own copies (HBM idles through tail, boundary and prologue)
     unsigned long long *prof;           // optional [grid][32] globaltimer stamps (tools/bs1_prof.py)
 };
@@ -198,6 +200,29 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
     }
 }
 
+// Row result -> destination.  Pair mode (the FFN's gate|up launch): the gate row's value is parked in shared memory; the warp that
+// finishes the UP row of the same index (chunks of seg 1 follow all chunks of seg 0: ~3 ring passes later, usually another warp)
+// picks it up and stores h = silu(gate) * up, computed exactly like the swiglu activation prologue does (ggml_silu_lane, then one
+// rounded multiply).  The down projection then reads ONE f32 vector and needs no expf in its prologue.  A warp never waits while it
+// holds a ring stage (the stage is released before the row reduction), so the gate rows always make progress.
+__device__ __forceinline__ void bs1_store_row(const Bs1Params &p, const Bs1Seg &sg, int s, int o, int ol, float acc, float *gval, volatile uint32_t *gflag) {
+    if (p.pair) {
+        if (s == 0) {
+            gval[ol] = acc;
+            __threadfence_block();
+            gflag[ol] = 1u;
+        } else {
+            while (gflag[ol] == 0u) { }
+            __threadfence_block();
+            const float g = ((volatile float *)gval)[ol];
+            p.seg[0].dst[o] = __fmul_rn(ggml_silu_lane(g), acc);
+        }
+        return;
+    }
+    if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
+    sg.dst[o] = acc;
+}
+
 // the weights of the launches that follow: ask the L2 to start fetching this CTA's 1/G of every range (fire and forget)
 __device__ __forceinline__ void bs1_l2_lookahead(const Bs1Params &p, int G, int c, int lane) {
     constexpr unsigned long long PIECE = 8192;
@@ -294,6 +319,9 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
     }
 
     // ---------------------------------------------------------------------- consumers: prologue
+    float *gval = (float *)(smem + p.off_gval);
+    volatile uint32_t *gflag = (volatile uint32_t *)(smem + p.off_gflag);
+    if (p.pair) for (int i = threadIdx.x; i < hi[0] - lo[0]; i += BS1_NCW * 32) gflag[i] = 0u;      // published by the prologue's CTA barrier
     if (p.use_pdl) pdl_wait();          // the activations belong to the previous kernels
     if (warp == 0) PROF(4);
     bs1_prologue(p, smem, s_red, warp, lane);
@@ -353,11 +381,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
                     if (lpr == 32) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (bl == 0 && mine) {
-                        const int o = row0 + r + sub;
-                        if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
-                        sg.dst[o] = acc;
-                    }
+                    if (bl == 0 && mine) bs1_store_row(p, sg, s, row0 + r + sub, row0 + r + sub - lo_s, acc, gval, gflag);
                 }
             } else if (TYPES & TB_Q6_K) {
 #pragma unroll 1
@@ -370,11 +394,7 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
                         if (lane == 0) mbar_arrive(&empty[st]);
                     }
                     acc = warp_reduce_sum(acc);
-                    if (lane == 0) {
-                        const int o = row0 + r;
-                        if (sg.residual) acc = __fadd_rn(acc, sg.residual[o]);
-                        sg.dst[o] = acc;
-                    }
+                    if (lane == 0) bs1_store_row(p, sg, s, row0 + r, row0 + r - lo_s, acc, gval, gflag);
                 }
             }
             if (i == 0) PROF(7);
@@ -439,7 +459,9 @@ int bs1_max_clusters(b200_ctx *ctx, int cs, int threads, size_t smem_bytes) {
 
 // 1 = launched, 0 = not eligible (caller falls through to the general kernel), < 0 = error
 int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_t K, const GemvActDesc &ga, bool w_const,
-                        const GemvPf *pf, int npf, int l2pf) {
+                        const GemvPf *pf, int npf, int l2pf, bool *pair) {
+    const bool want_pair = pair != nullptr;
+    if (pair) *pair = false;
     if (!g_bs1_env) {
         if (const char *e = getenv("GGML_B200_BS1_CTAS")) g_bs1_ctas = atoi(e);          // CTAs per SM (1 or 2; default 2)
         if (const char *e = getenv("GGML_B200_BS1_SMEM_KB")) g_bs1_smem_kb = atoi(e);    // shared memory per CTA
@@ -472,6 +494,14 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     p.off_ad = off; off += (uint32_t)(K / 256) * 4; off = (off + 15) & ~15u;
     if (need64)  { p.off_s32 = off; off += (uint32_t)(K / 32) * 2; off = (off + 15) & ~15u; }
     if (need128) { p.off_s16 = off; off += (uint32_t)(K / 16) * 2; off = (off + 15) & ~15u; }
+    static const int pair_off = getenv("GGML_B200_BS1_PAIR") ? !atoi(getenv("GGML_B200_BS1_PAIR")) : 0;
+    if (want_pair && !pair_off && nseg == 2 && segs[0].N == segs[1].N && segs[0].N / ctx->sm_count + 1 <= 2048 && !segs[0].residual && !segs[1].residual &&
+        !segs[0].expert_id && !segs[1].expert_id) {
+        const uint32_t rows = (uint32_t)(segs[0].N / ctx->sm_count + 1);
+        p.pair = 1;
+        p.off_gval = off; off += rows * 4; off = (off + 15) & ~15u;
+        p.off_gflag = off; off += rows * 4; off = (off + 15) & ~15u;
+    }
     off = (off + 127) & ~127u;
     p.off_ring = off;
     const int cps = g_bs1_ctas == 2 ? 2 : 1;
@@ -534,7 +564,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     if (grid > min_rows) grid = min_rows;                // every CTA gets at least one row of every segment
     // long activation vectors (a warp would quantise two blocks, every CTA would re-read 50+ KB): share the prologue in a cluster
     p.cs = 1;
-    if (g_bs1_cluster > 1 && ga.mode != ACT_F32_NORM && (K >> 8) > ncw && grid >= ctx->sm_count / 2) {
+    if (g_bs1_cluster > 1 && !p.pair && ga.mode != ACT_F32_NORM && (K >> 8) > ncw && grid >= ctx->sm_count / 2) {
         const int cs = g_bs1_cluster >= 4 ? 4 : 2;
         static int max_cl[5] = {0, 0, -1, 0, -1};
         if (max_cl[cs] < 0) {
@@ -548,6 +578,8 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
         if (max_cl[cs] > 0 && gcl >= ctx->sm_count * 3 / 4) { p.cs = cs; grid = gcl; }
     }
     for (int s = 0; s < nseg; s++) { p.seg[s].q = (int)(segs[s].N / grid); p.seg[s].rem = (int)(segs[s].N % grid); }
+    if (p.pair && (p.cs > 1 || (segs[0].N + grid - 1) / grid > segs[0].N / ctx->sm_count + 1)) { b200_set_error("gemv_bs1: pair-mode row table too small"); return B200_ERR_FAILED; }
+    if (pair) *pair = p.pair != 0;
     int rc;
     switch (mask) {
         case TB_Q4_K: rc = bs1_launch_t<TB_Q4_K>(ctx, p, (int)grid, smem_bytes); break;

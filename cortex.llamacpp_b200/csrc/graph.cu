@@ -94,6 +94,7 @@ struct ExecNode {
     GemvSegDesc seg[GEMV_MAX_SEG]; int nseg = 0; // EX_GEMV
     int64_t K = 0; GemvActDesc act; int ncols = 0; bool w_const = false;
     GemvPf pf[GEMV_MAX_PF] = {}; int npf = 0;    // L2 look-ahead ranges (weights of the launches that follow)
+    int pair = 0;                                // FFN: 1 = gate|up launch (may write silu(gate)*up itself), 2 = the down launch that follows it
     RopeStoreDesc rs;                            // EX_ROPE_STORE
     int kv_slot = -1;                            // index of this node's K destination in the KV pointer table (V = +1)
     std::shared_ptr<std::vector<DsNode>> ds;     // EX_DSTEP: the run of nodes one persistent decode-step launch executes (dstep.cu)
@@ -313,8 +314,10 @@ static int match_ffn(const b200_op *ops, int n, int i, const FuseScratch &fs, st
     g.seg[1] = seg_of(*up, fs.u, (size_t)FF, nullptr);
     g.act = GemvActDesc{};
     g.act.mode = ACT_F32_NORM; g.act.x = (const float *)xin->data; g.act.x_stride = xin->nb[1]; g.act.x2 = nw; g.act.eps = eps;
+    g.pair = 1;
     out.push_back(g);
     ExecNode d;
+    d.pair = 2;
     d.kind = EX_GEMV; d.nseg = 1; d.K = FF; d.ncols = (int)T; d.w_const = true;
     d.seg[0] = tp ? seg_of(*down, (float *)down->dst.data, (size_t)E, nullptr) : seg_of(*down, (float *)add.dst.data, (size_t)E, (const float *)resid->data);
     d.act = GemvActDesc{};
@@ -514,6 +517,7 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
     // timing experiments only (results are then wrong): option "debug_skip" / GGML_B200_DEBUG_SKIP bit 0 flash_attn, 1 rope+store, 2 GEMV, 3 all-reduce
     static const int env_skip = getenv("GGML_B200_DEBUG_SKIP") ? atoi(getenv("GGML_B200_DEBUG_SKIP")) : 0;
     const int dbg_skip = env_skip | ctx->opt_debug_skip;
+    bool pair_done = false;
     for (const ExecNode &e : list) {
         int rc;
         if (dbg_skip) {
@@ -527,7 +531,15 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
             rc = dstep_prepare(ctx, *e.ds, &prog);           // cached by content: a hit (no upload) once prepare_dstep() has seen this list
             if (!rc) rc = dstep_launch(ctx, prog);
         }
-        else if (e.kind == EX_GEMV) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf, e.npf);
+        else if (e.kind == EX_GEMV) {
+            if (e.pair == 1 && ctx->opt_ffn_pair) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf, e.npf, &pair_done);
+            else if (e.pair == 2 && pair_done) {          // the gate|up launch left h = silu(gate) * up in the gate scratch: plain f32 activations
+                GemvActDesc a = e.act; a.mode = ACT_F32; a.x2 = nullptr;
+                rc = gemv_launch(ctx, e.seg, e.nseg, e.K, a, e.ncols, e.w_const, e.pf, e.npf);
+                pair_done = false;
+            }
+            else rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf, e.npf);
+        }
         else if (e.kind == EX_ROPE_STORE) rc = launch_rope_store(ctx, e.rs);
         else rc = dispatch(ctx, &e.op);
         if (rc) return rc;

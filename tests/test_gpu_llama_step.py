@@ -167,6 +167,40 @@ def test_llama_decode_cuda_graph_replay(b200, ctx):
     ctx.set_option("cuda_graphs", 0)
 
 
+@pytest.mark.parametrize("model,ftype", [("mid-d128", "q4_k_m"), ("tiny-d128", "q5_k_m"), ("tiny-d128", "q4_k_m")])
+def test_ffn_pair_epilogue_bit_identical(b200, ctx, model, ftype):
+    """option ffn_pair: the fused gate|up GEMV writes h = silu(gate) * up itself (gemv_bs1.cu pair mode: gate row parked in shared
+    memory, picked up by the warp that finishes the up row) and the down GEMV reads h as plain f32 activations, instead of
+    silu(gate) * up in the down GEMV's prologue -- same arithmetic (ggml_silu_lane, one rounded multiply): logits bit-identical,
+    eager and under CUDA-graph replay"""
+    import torch
+    from __graft_entry__ import load_llama_graph
+    lg = load_llama_graph()
+    g = lg.LlamaGraph(b200, model=model, ftype=ftype, kv="f16", n_ctx=256, max_tokens=1)
+    rng = np.random.default_rng(11)
+    emb, pos, mask = g.set_inputs_host(1, 5, 256, rng)
+    g.inp_embd[:g.E] = torch.from_numpy(emb.reshape(-1)).cuda()
+    g.pos[:1] = torch.from_numpy(pos).cuda()
+    g.mask_f32[:mask.size] = torch.from_numpy(mask.reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    ops = g.build(1, 5, 256)
+    ctx.set_option("fusion", 2); ctx.set_option("pdl", 1)
+    outs = {}
+    for graphs in (0, 1):
+        ctx.set_option("cuda_graphs", graphs)
+        for pair in (0, 1):
+            ctx.set_option("ffn_pair", pair)
+            for _ in range(3):
+                g.logits.zero_(); torch.cuda.synchronize()
+                ctx.compute(ops); ctx.sync()
+            outs[(graphs, pair)] = g.logits[:g.V].cpu().numpy().copy()
+    ctx.set_option("ffn_pair", 1); ctx.set_option("pdl", 0); ctx.set_option("cuda_graphs", 0)
+    ref = outs[(0, 0)]
+    assert np.isfinite(ref).all() and np.abs(ref).max() > 0
+    for k, v in outs.items():
+        assert np.array_equal(ref, v), k
+
+
 def test_l2_lookahead_modes_do_not_change_results(b200, ctx):
     """option l2_prefetch (0 off, 1 next matmul with the first copies, 2 following launches' ranges after the launch's own copies, across
     the attention chain): a pure L2 hint -- logits bit-identical in every mode (gemv_bs1.cu bs1_l2_lookahead, graph.cu look-ahead pass)"""

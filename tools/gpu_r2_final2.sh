@@ -1,6 +1,7 @@
 #!/bin/bash
-# round-2 closing evidence (re-entry session): both bench arms, smoke, configs #1/#2/#4 through the C ABI; the GPU suite runs in gpu_r2_h.sh
+# round-2 closing evidence (re-entry session): GPU suite, both bench arms, smoke, configs #1/#2/#4 through the C ABI
 mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/r2f_pytest_gpu.log; tail -2 gpurun_out/r2f_pytest_gpu.log
 timeout 900 python bench.py --impl reference > gpurun_out/r2f_bench_reference.json 2> gpurun_out/r2f_bench_reference.err; tail -c 600 gpurun_out/r2f_bench_reference.json
 timeout 1500 python bench.py > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err; tail -c 2500 gpurun_out/r2f_bench.json
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
