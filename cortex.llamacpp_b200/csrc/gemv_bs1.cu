@@ -564,7 +564,11 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     if (grid > min_rows) grid = min_rows;                // every CTA gets at least one row of every segment
     // long activation vectors (a warp would quantise two blocks, every CTA would re-read 50+ KB): share the prologue in a cluster
     p.cs = 1;
-    if (g_bs1_cluster > 1 && !p.pair && ga.mode != ACT_F32_NORM && (K >> 8) > ncw && grid >= ctx->sm_count / 2) {
+    // Only the swiglu prologue (two vectors + expf per element) is worth the cluster barrier, which waits for the LAST member to
+    // start (CTAs replace the previous kernel's CTAs one by one: 2 us of skew in a real step); plain f32 vectors -- the down projection
+    // after a pair-mode gate|up launch -- are loaded and quantised by every CTA itself: 557 vs 546 tok/s (GGML_B200_BS1_CLUSTER_F32=1 restores)
+    static const int cluster_f32 = getenv("GGML_B200_BS1_CLUSTER_F32") ? atoi(getenv("GGML_B200_BS1_CLUSTER_F32")) : 0;
+    if (g_bs1_cluster > 1 && !p.pair && (ga.mode == ACT_F32_SWIGLU || (ga.mode == ACT_F32 && cluster_f32)) && (K >> 8) > ncw && grid >= ctx->sm_count / 2) {
         const int cs = g_bs1_cluster >= 4 ? 4 : 2;
         static int max_cl[5] = {0, 0, -1, 0, -1};
         if (max_cl[cs] < 0) {
