@@ -99,6 +99,65 @@ __device__ __forceinline__ void load_row32(const char *row, int qd, float (&v)[3
     }
 }
 
+// ---- operand conversion without the f32 round trip -------------------------------------------------------------------------------
+// The 32 head dims [32 qd, 32 qd + 32) of one raw cache row (shared memory, as stored) -> four 16-byte operand chunks of f16 `hi`
+// and, for quantised caches, of the remainders `lo`.  Quantised: the value is d * q with d an f16 and q a small integer, so
+//   hi = rn_f16(d * q) = HMUL2(d, q),   lo = rn_f16(d * q - hi) = HFMA2(d, q, -hi)   (the residual of a product is formed exactly)
+// are bit for bit what split_h(d * (float)q) gives, at ~1 instruction per value instead of ~8.  Integers reach f16 through the
+// 0x6400 magic number (PRMT a byte under the exponent of 1024, subtract 1024 + bias).  Blocks are 2-byte aligned: words are fetched
+// aligned and funnel-shifted.
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *(const uint32_t *)&h; }
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *(const __half2 *)&u; }
+template <int KT>
+__device__ __forceinline__ void convert_row32(const uint8_t *row, int qd, uint4 (&hi)[4], uint4 (&lo)[4]) {
+    if (KT == KV_F16) {
+        const uint4 *p = (const uint4 *)(row + qd * 64);
+#pragma unroll
+        for (int j = 0; j < 4; j++) hi[j] = p[j];
+        return;
+    }
+    constexpr int BB = KT == KV_Q8_0 ? 34 : 18, NW = KT == KV_Q8_0 ? 9 : 5;
+    const uint8_t *b = row + qd * BB;
+    const uint32_t mis = (uint32_t)(uintptr_t)b & 2u;                    // the block's 2-byte phase inside its first aligned word
+    const uint32_t *wp = (const uint32_t *)(b - mis);
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = wp[i];
+    w[NW] = 0;
+    // q[i]: the quant words (bytes 2.. of the block); d: the block scale
+    const uint32_t sh = mis ? 0u : 16u;                                  // mis == 2: d is the high half of w[0], the quants start at w[1]
+    const uint32_t dbits = mis ? (w[0] >> 16) : (w[0] & 0xffffu);
+    const __half2 d2 = u2h(dbits | (dbits << 16));
+    constexpr int NQ = KT == KV_Q8_0 ? 8 : 4;
+    uint32_t q[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; i++) q[i] = mis ? w[i + 1] : __funnelshift_r(w[i], w[i + 1], sh);
+    auto emit = [&](uint32_t bytes4, __half2 bias, uint32_t &h0, uint32_t &h1, uint32_t &l0, uint32_t &l1) {
+        // 4 unsigned bytes -> 4 integers (byte - bias) -> d * q as hi + lo
+        const __half2 a = __hsub2(u2h(__byte_perm(bytes4, 0x64646464u, 0x4140)), bias), c = __hsub2(u2h(__byte_perm(bytes4, 0x64646464u, 0x4342)), bias);
+        const __half2 ha = __hmul2(d2, a), hc = __hmul2(d2, c);
+        h0 = h2u(ha); h1 = h2u(hc);
+        l0 = h2u(__hfma2(d2, a, __hneg2(ha))); l1 = h2u(__hfma2(d2, c, __hneg2(hc)));
+    };
+    if (KT == KV_Q8_0) {
+        const __half2 bias = __float2half2_rn(1024.0f + 128.0f);         // int8 + 128 = unsigned byte
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            emit(q[2 * j] ^ 0x80808080u, bias, hi[j].x, hi[j].y, lo[j].x, lo[j].y);
+            emit(q[2 * j + 1] ^ 0x80808080u, bias, hi[j].z, hi[j].w, lo[j].z, lo[j].w);
+        }
+    } else {
+        const __half2 bias = __float2half2_rn(1024.0f + 8.0f);           // block_q4_0: element i = low nibble of byte i, i + 16 = high nibble, minus 8
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            emit(q[2 * j] & 0x0f0f0f0fu, bias, hi[j].x, hi[j].y, lo[j].x, lo[j].y);
+            emit(q[2 * j + 1] & 0x0f0f0f0fu, bias, hi[j].z, hi[j].w, lo[j].z, lo[j].w);
+            emit((q[2 * j] >> 4) & 0x0f0f0f0fu, bias, hi[2 + j].x, hi[2 + j].y, lo[2 + j].x, lo[2 + j].y);
+            emit((q[2 * j + 1] >> 4) & 0x0f0f0f0fu, bias, hi[2 + j].z, hi[2 + j].w, lo[2 + j].z, lo[2 + j].w);
+        }
+    }
+}
+
 // bytes of one head's row in the cache: 128 f16 / 4 q8_0 blocks / 4 q4_0 blocks
 __host__ __device__ constexpr int raw_row_bytes(int kt) { return kt == KV_F16 ? HD * 2 : kt == KV_Q8_0 ? (HD / 32) * 34 : (HD / 32) * 18; }
 
@@ -237,24 +296,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
         }
         const uint32_t par = (uint32_t)(live_tiles & 1);
         live_tiles++;
+        float alpha_t = 1.0f;
 
         if (warp > 0) {
             // ---- stage K (K-major) and V (MN-major): thread = (cell, quarter of the dims) ----
             const int c = wt & (TC - 1), qd = wt >> 6;
-            float v[32];
-            load_row32<KT>((const char *)raw_k + c * raw_row_bytes(KT), qd, v);
+            uint4 ch[4], cl[4];
+            convert_row32<KT>(raw_k + c * raw_row_bytes(KT), qd, ch, cl);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float w[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
                 const uint32_t off = (uint32_t)(c >> 3) * SBO_D + (uint32_t)(qd * 4 + j) * LBO + (uint32_t)(c & 7) * 16;
-                store_chunk<QUANT>(w, k_hi + off, k_lo + off);
+                *(uint4 *)(k_hi + off) = ch[j];
+                if (QUANT) *(uint4 *)(k_lo + off) = cl[j];
             }
-            load_row32<KT>((const char *)raw_v + c * raw_row_bytes(KT), qd, v);
+            convert_row32<KT>(raw_v + c * raw_row_bytes(KT), qd, ch, cl);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float w[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
                 const uint32_t off = (uint32_t)(qd * 4 + j) * SBO_C + (uint32_t)(c >> 3) * LBO + (uint32_t)(c & 7) * 16;
-                store_chunk<QUANT>(w, v_hi + off, v_lo + off);
+                *(uint4 *)(v_hi + off) = ch[j];
+                if (QUANT) *(uint4 *)(v_lo + off) = cl[j];
             }
             fence_proxy_async();
         }
@@ -328,9 +388,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
                 const uint32_t off = (uint32_t)(r >> 3) * SBO_C + (uint32_t)(hf * 4 + j) * LBO + (uint32_t)(r & 7) * 16;
                 store_chunk<true>(w, p_hi + off, p_lo + off);
             }
-            // the rescale of the running output is applied when the tile's product arrives
-#pragma unroll
-            for (int i = 0; i < HD / 2; i++) out[i] *= alpha;
+            alpha_t = alpha;                                    // the rescale of the running output is folded into the accumulate below (one FFMA per element)
             fence_proxy_async();
             tc_fence_before();
         }
@@ -362,7 +420,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) b200_fattn_tc_kernel(const FaTc
                 tmem_ld16(ta + c0, o);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j++) out[c0 + j] += __uint_as_float(o[j]);
+                for (int j = 0; j < 16; j++) out[c0 + j] = fmaf(out[c0 + j], alpha_t, __uint_as_float(o[j]));
             }
             tc_fence_before();
         }
