@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 closing evidence (re-entry session): GPU suite, both bench arms, smoke, configs #1/#2/#4 through the C ABI
+# closing evidence on one B200: GPU suite, both bench arms, smoke, configs #1/#2/#4 through the C ABI (outputs copied to profiles/r2_*)
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/r2f_pytest_gpu.log; tail -2 gpurun_out/r2f_pytest_gpu.log
 timeout 900 python bench.py --impl reference > gpurun_out/r2f_bench_reference.json 2> gpurun_out/r2f_bench_reference.err; tail -c 600 gpurun_out/r2f_bench_reference.json
