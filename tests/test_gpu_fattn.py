@@ -93,6 +93,7 @@ CASES = [
     (128, 32, 8, 3, 512), (128, 32, 8, 32, 1024), (128, 8, 8, 35, 512), (64, 32, 4, 7, 256), (128, 16, 1, 2, 512),
     (128, 8, 2, 128, 256), (128, 8, 2, 512, 640), (64, 8, 2, 250, 512),        # prompt-sized query blocks (causal mask: the live-tile map path;
     (128, 8, 2, 100, 512), (128, 32, 8, 300, 1024), (128, 4, 4, 2048, 2304),   #  D = 128 from 64 query columns up: the tcgen05 kernel, fattn_tc.cu)
+    (128, 8, 2, 128, 4608),                                                    # a ubatch appended at depth ~4.5k (config #3's 4k context): 72 KV tiles through the cp.async pipeline
 ]
 
 
