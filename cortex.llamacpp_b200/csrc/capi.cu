@@ -102,6 +102,8 @@ b200_ctx *b200_ctx_create(int device) {
     if (const char *e = getenv("GGML_B200_GRAPHS")) ctx->opt_cuda_graphs = atoi(e);
     if (const char *e = getenv("GGML_B200_FUSION")) ctx->opt_fusion = atoi(e);
     if (const char *e = getenv("GGML_B200_PDL")) ctx->opt_pdl = atoi(e);
+    if (const char *e = getenv("GGML_B200_FA_MERGE")) ctx->opt_fa_merge_in_wo = atoi(e);      // 1: the output projection's GEMV merges the flash-attention KV splits (opt-in, measured slower)
+    if (const char *e = getenv("GGML_B200_FFN_PAIR")) ctx->opt_ffn_pair = atoi(e);
     if (const char *e = getenv("GGML_B200_FA_EXACT")) ctx->opt_cpu_exact = atoi(e);
     if (const char *e = getenv("GGML_B200_CPU_EXACT")) ctx->opt_cpu_exact = atoi(e);
     if (const char *e = getenv("GGML_B200_DSTEP")) ctx->opt_dstep = atoi(e);
@@ -141,7 +143,7 @@ int b200_set_option(b200_ctx *ctx, const char *key, int value) {
     std::string k(key);
     int *slot = k == "fusion" ? &ctx->opt_fusion : k == "pdl" ? &ctx->opt_pdl : k == "l2_prefetch" ? &ctx->opt_l2_prefetch :
                 k == "debug_skip" ? &ctx->opt_debug_skip : (k == "fa_exact" || k == "cpu_exact") ? &ctx->opt_cpu_exact : k == "dstep" ? &ctx->opt_dstep :
-                k == "ffn_pair" ? &ctx->opt_ffn_pair : nullptr;
+                k == "ffn_pair" ? &ctx->opt_ffn_pair : k == "fa_merge_in_wo" ? &ctx->opt_fa_merge_in_wo : nullptr;
     if (k == "cuda_graphs") ctx->opt_cuda_graphs = value;
     else if (slot) {
         if (*slot != value) {                 // captured graphs bake these options in: drop them

@@ -140,6 +140,13 @@ struct b200_ctx {
                                                // slower than the per-launch path on B200 (2.66 vs 1.88 ms/step, profiles/r2_dstep_timeline.md)
     // live-tile map of the attention mask (fattn.cu): built by the first FLASH_ATTN_EXT of a graph that uses a given mask, reused by
     // the other layers; dropped at every graph_compute / compute_op entry and when an op writes into the mask
+    // decode fusion "split merge in the consumer": graph.cu asks the flash-attention launch to leave its KV-split partials unmerged
+    // (fa_skip_combine) when the batch-1 GEMV of the attention output projection will merge them in its activation prologue; the launch
+    // answers with where the partials are (fa_part_ns = 0: it merged them itself, dst is valid)
+    bool          fa_skip_combine = false;
+    const float * fa_part = nullptr;
+    int           fa_part_ns = 0, fa_part_gq = 0;
+    int           opt_fa_merge_in_wo = 0;       // measured slower (532 vs 555 tok/s): 148 CTAs re-reading the same ~100 KB of partials is an L2 hot spot (5 us); opt-in
     bool          fa_map_valid = false;
     uintptr_t     fa_map_mask = 0, fa_map_mask_end = 0;
     int64_t       fa_map_key[4] = {0, 0, 0, 0};        // m_nb1, n_kv, n_q, QC

@@ -1152,6 +1152,12 @@ int launch_fa(b200_ctx *ctx, const FaParams &p, int n_tiles) {
     if (p.cluster) return B200_OK;
     cfg.numAttrs = p.use_pdl ? 1 : 0;
     if (p.n_splits > 1 && !p.counters) {
+        if (ROWS8 && D == 128 && ctx->fa_skip_combine && p.n_q == 1 && p.n_splits <= 16) {
+            // batch-1 decode: the output projection's GEMV merges the splits in its activation prologue (gemv_bs1.cu bs1_load_fa_partials,
+            // same arithmetic in the same order as b200_fattn_combine_kernel): one launch less on the token's critical path
+            ctx->fa_part = p.part; ctx->fa_part_ns = p.n_splits; ctx->fa_part_gq = p.gq;
+            return B200_OK;
+        }
         cfg.gridDim = dim3((unsigned)((n_tiles * 16 + 3) / 4));
         cfg.blockDim = dim3(128);
         cfg.dynamicSmemBytes = 0;

@@ -94,6 +94,7 @@ struct ExecNode {
     GemvSegDesc seg[GEMV_MAX_SEG]; int nseg = 0; // EX_GEMV
     int64_t K = 0; GemvActDesc act; int ncols = 0; bool w_const = false;
     GemvPf pf[GEMV_MAX_PF] = {}; int npf = 0;    // L2 look-ahead ranges (weights of the launches that follow)
+    int fa_merge = 0;                            // 1 = FLASH_ATTN op whose KV-split merge the next node (2 = that batch-1 GEMV) can do in its prologue
     int pair = 0;                                // FFN: 1 = gate|up launch (may write silu(gate)*up itself), 2 = the down launch that follows it
     RopeStoreDesc rs;                            // EX_ROPE_STORE
     int kv_slot = -1;                            // index of this node's K destination in the KV pointer table (V = +1)
@@ -509,6 +510,44 @@ static int fuse(b200_ctx *ctx, const b200_op *ops, int n, std::vector<ExecNode> 
         size_t k = j + 1;
         if (k < out.size() && gemv_like(out[k])) { add_ranges(e, out[k]); covered[k] = 1; }
     }
+    // split merge in the consumer: a batch-1 FLASH_ATTN node directly followed by the fused output-projection GEMV that reads its
+    // result as plain f32 activations.  The attention output must be dead afterwards: scanning the nodes that follow, the first touch of
+    // its range has to be a full overwrite (ggml-alloc reuses the buffer), not a read.
+    if (layer_fusion) {
+        auto rng = [](const void *ptr, size_t bytes, uintptr_t &lo, uintptr_t &hi) { lo = (uintptr_t)ptr; hi = lo + bytes; };
+        for (size_t i = 0; i + 1 < out.size(); i++) {
+            ExecNode &fa = out[i], &mm = out[i + 1];
+            if (fa.kind != EX_OP || fa.op.op != B200_OP_FLASH_ATTN_EXT || mm.kind != EX_GEMV) continue;
+            const b200_tensor &q = fa.op.src[0], &d = fa.op.dst;
+            if (q.ne[1] != 1 || q.ne[0] != 128 || mm.ncols != 1 || mm.nseg != 1 || mm.act.mode != ACT_F32 || mm.act.x != (const float *)d.data ||
+                mm.K != q.ne[0] * q.ne[2] || mm.seg[0].expert_id) continue;
+            uintptr_t lo, hi;
+            rng(d.data, (size_t)mm.K * 4, lo, hi);
+            auto touches = [&](const void *ptr, size_t bytes) { uintptr_t a, b; rng(ptr, bytes, a, b); return ptr && a < hi && lo < b; };
+            auto covers = [&](const void *ptr, size_t bytes) { uintptr_t a, b; rng(ptr, bytes, a, b); return ptr && a <= lo && hi <= b; };
+            if (touches(mm.seg[0].residual, (size_t)mm.seg[0].N * 4)) continue;
+            bool dead = false, live = false;
+            for (size_t j = i + 2; j < out.size() && !dead && !live; j++) {
+                const ExecNode &e = out[j];
+                if (e.kind == EX_OP) {
+                    for (int t = 0; t < e.op.n_src && !live; t++) { uintptr_t a, b; tensor_range(e.op.src[t], a, b); live = e.op.src[t].data && a < hi && lo < b; }
+                    if (!live) { uintptr_t a, b; tensor_range(e.op.dst, a, b); if (a <= lo && hi <= b) dead = true; else if (a < hi && lo < b) live = true; }
+                } else if (e.kind == EX_GEMV) {
+                    const size_t xb = (size_t)e.K * 4;
+                    live = touches(e.act.x, xb) || (e.act.mode != ACT_F32 && touches(e.act.x2, xb));
+                    for (int t = 0; t < e.nseg && !live; t++) live = touches(e.seg[t].residual, (size_t)e.seg[t].N * 4);
+                    for (int t = 0; t < e.nseg && !live && !dead; t++) { if (covers(e.seg[t].dst, (size_t)e.seg[t].N * 4)) dead = true; else if (touches(e.seg[t].dst, (size_t)e.seg[t].N * 4)) live = true; }
+                } else if (e.kind == EX_ROPE_STORE) {    // reads q, k, v of the ubatch; writes the roped q (a write that does not cover the whole range counts as a touch)
+                    const RopeStoreDesc &r = e.rs;
+                    const size_t qb = (size_t)r.T * r.H * r.D * 4, kb = (size_t)r.T * r.Hkv * r.D * 4;
+                    live = touches(r.q, qb) || touches(r.k, kb) || touches(r.v, kb);
+                    if (!live) { if (covers(r.q_out, qb)) dead = true; else if (touches(r.q_out, qb)) live = true; }
+                } else live = true;                      // decode-step nodes: not analysed, keep the merged output
+            }
+            if (live) continue;                          // (never touched again also counts as dead)
+            fa.fa_merge = 1; mm.fa_merge = 2;
+        }
+    }
     if (layer_fusion && ctx->opt_dstep) pack_dstep(ctx, out);
     return B200_OK;
 }
@@ -530,6 +569,21 @@ static int run_list(b200_ctx *ctx, const std::vector<ExecNode> &list) {
             DsProgram *prog = nullptr;
             rc = dstep_prepare(ctx, *e.ds, &prog);           // cached by content: a hit (no upload) once prepare_dstep() has seen this list
             if (!rc) rc = dstep_launch(ctx, prog);
+        }
+        else if (e.kind == EX_OP && e.fa_merge == 1 && ctx->opt_fa_merge_in_wo && (&e + 1) < list.data() + list.size() && (&e + 1)->fa_merge == 2 && !dbg_skip) {
+            // would the batch-1 GEMV take the output projection with the split merge in its prologue?  (dry run: no launch)
+            const ExecNode &mm = *(&e + 1);
+            GemvActDesc a = mm.act; a.mode = ACT_FA_PART;
+            const bool can = gemv_bs1_try_launch(ctx, mm.seg, mm.nseg, mm.K, a, mm.w_const, nullptr, 0, 0, nullptr, true) == 1;
+            ctx->fa_part_ns = 0; ctx->fa_part = nullptr;
+            ctx->fa_skip_combine = can;
+            rc = dispatch(ctx, &e.op);
+            ctx->fa_skip_combine = false;
+        }
+        else if (e.kind == EX_GEMV && e.fa_merge == 2 && ctx->fa_part_ns > 1) {
+            GemvActDesc a = e.act; a.mode = ACT_FA_PART; a.fa_part = ctx->fa_part; a.fa_ns = ctx->fa_part_ns; a.fa_gq = ctx->fa_part_gq;
+            ctx->fa_part_ns = 0;
+            rc = gemv_launch(ctx, e.seg, e.nseg, e.K, a, e.ncols, e.w_const, e.pf, e.npf);
         }
         else if (e.kind == EX_GEMV) {
             if (e.pair == 1 && ctx->opt_ffn_pair) rc = gemv_launch(ctx, e.seg, e.nseg, e.K, e.act, e.ncols, e.w_const, e.pf, e.npf, &pair_done);
