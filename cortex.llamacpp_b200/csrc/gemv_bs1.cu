@@ -47,6 +47,7 @@ struct Bs1Params {
     int            nseg, K, act_mode;
     const float *  x, *x2;
     float          eps;
+    double         inv_K;                      // 1 / K when K is a power of two (exact), else 0
     const float *  fa_part; int fa_ns, fa_gq;  // ACT_FA_PART: unmerged flash-attention KV-split partials (see bs1_load_fa_partials)
     int            nstages;
     uint32_t       stage_bytes;
@@ -180,16 +181,19 @@ __device__ __forceinline__ void bs1_load_fa_partials(const Bs1Params &p, int b, 
 }
 
 // sum over the consumer warps of per-warp partial sums of squares -> 1/rms (rms_norm like glue.cu / the CPU oracle: sum in double)
-__device__ __forceinline__ float bs1_norm_scale(const Bs1Params &p, double *s_red, double s, int warp, int lane) {
+// `nact` warps (0 .. nact - 1) hold blocks of the vector: only they meet at the barrier and need the result (the others would add exact zeros)
+__device__ __forceinline__ float bs1_norm_scale(const Bs1Params &p, double *s_red, double s, int warp, int lane, int nact) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) s_red[warp] = s;
-    named_bar_sync(2, p.ncw * 32);
+    named_bar_sync(2, nact * 32);
     // every warp adds the <= 31 partial sums with the same shuffle tree (fixed order => identical on all warps and CTAs)
-    double t = lane < p.ncw ? s_red[lane] : 0.0;
+    double t = lane < nact ? s_red[lane] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)p.K), p.eps)));
+    // K a power of two (4096, 8192 ...): the division is an exact scaling, done as one multiply
+    const double mean = p.inv_K != 0.0 ? t * p.inv_K : t / (double)p.K;
+    return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)mean, p.eps)));
 }
 // f32 activations (optionally rms_norm(x)*w or silu(g)*u) -> q8_K in shared memory, bit-exact vs quantize_row_q8_K_ref.
 // K <= 2 * 256 * ncw (every llama shape at batch 1): each warp holds its <= 2 blocks in registers, so x is read ONCE even
@@ -222,7 +226,8 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
         }
         float norm_scale = 1.0f;
         if (p.prof) { asm volatile("" : "+f"(xa[0][0].x)); PROFQ(26); }
-        if (p.act_mode == ACT_F32_NORM) {
+        const int nact = min(ncw, nchunk);           // norm mode never runs in clusters: warp w holds blocks w and w + ncw
+        if (p.act_mode == ACT_F32_NORM && warp < nact) {
             double s = 0.0;
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -231,7 +236,7 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
                 for (int j = 0; j < 8; j++) s += (double)__fmul_rn(v[j], v[j]);
             }
             if (p.prof) { asm volatile("" : "+d"(s)); PROFQ(27); }
-            norm_scale = bs1_norm_scale(p, s_red, s, warp, lane);
+            norm_scale = bs1_norm_scale(p, s_red, s, warp, lane, nact);
             if (p.prof) { asm volatile("" : "+f"(norm_scale)); PROFQ(28); }
         }
 #pragma unroll
@@ -252,7 +257,7 @@ __device__ __forceinline__ void bs1_prologue(const Bs1Params &p, uint8_t *smem, 
     if (p.act_mode == ACT_F32_NORM) {
         double s = 0.0;
         for (int i = threadIdx.x; i < p.K; i += ncw * 32) { const float v = p.x[i]; s += (double)__fmul_rn(v, v); }
-        norm_scale = bs1_norm_scale(p, s_red, s, warp, lane);
+        norm_scale = bs1_norm_scale(p, s_red, s, warp, lane, ncw);
     }
 #pragma unroll 1
     for (int b = warp; b < nchunk; b += ncw) {
@@ -557,6 +562,7 @@ int gemv_bs1_try_launch(b200_ctx *ctx, const GemvSegDesc *segs, int nseg, int64_
     Bs1Params p = {};
     p.nseg = nseg; p.K = (int)K; p.act_mode = ga.mode; p.x = ga.x; p.x2 = ga.x2; p.eps = ga.eps;
     p.fa_part = ga.fa_part; p.fa_ns = ga.fa_ns; p.fa_gq = ga.fa_gq;
+    p.inv_K = (K & (K - 1)) == 0 ? 1.0 / (double)K : 0.0;
     p.w_const = w_const ? 1 : 0; p.use_pdl = ctx->opt_pdl;
     // shared memory: barriers | s_red | aq64 | aq128 | d | s32 | s16 | ring
     uint32_t off = 2 * BS1_MAX_STAGES * 8 + 32 * 8;
