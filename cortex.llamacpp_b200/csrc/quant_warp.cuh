@@ -16,13 +16,15 @@ __device__ __forceinline__ void warp_quant_q8k(const float (&v)[8], int lane, ui
         const float a = fabsf(v[j]);
         if (a > amax) { amax = a; mx = v[j]; }
     }
-    int src = lane;   // first-occurrence tie break: equal |x| -> lower index wins (the reference scans in order)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int   os = __shfl_xor_sync(0xffffffffu, src, o);
-        if (oa > amax || (oa == amax && os < src)) { amax = oa; mx = om; src = os; }
+    // block maximum of |x| with the reference's first-occurrence tie break (equal |x| -> lower index wins: the reference scans in order).
+    // Non-negative floats order like their bit patterns, so one integer REDUX finds the maximum, a ballot finds the lanes that hold it and
+    // the lowest of them supplies the signed value (was: a 5-step tree of 3 shuffles each).  NaN never occurs in activations that matter;
+    // a NaN |x| compares false in `a > amax` above exactly as before and is ignored by both versions.
+    {
+        const unsigned top = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+        const unsigned holders = __ballot_sync(0xffffffffu, __float_as_uint(amax) == top);
+        mx = __shfl_sync(0xffffffffu, mx, __ffs(holders) - 1);
+        amax = __uint_as_float(top);
     }
     int8_t q[8];
     int lsum = 0;
