@@ -626,18 +626,23 @@ __global__ void __launch_bounds__(NWARP * 32, 2) b200_fattn_rows8_kernel(const F
     }
     for (int it = it_begin + warp; it < it_end; it += NWARP) {
         const int kv0 = (mp ? mp[1 + it] : it) * BK;
-        if (mrowp && !mp) {                       // skip a tile that is fully masked for this column
-            const __half mv = *(const __half *)(mrowp + (uint64_t)(kv0 + lane) * 2);
-            if (!__any_sync(0xffffffffu, !(__hisinf(mv) && __half2float(mv) < 0.0f))) continue;
-        }
+        // no live-tile map (a decode step): the tile's cache rows are requested BEFORE the mask says whether the tile is live -- the mask
+        // words and the rows then travel together (one L2 round trip instead of two on the token's critical path; a dead tile costs a
+        // few KB of L2 traffic, and its copies are drained before the buffers are reused)
         __syncwarp();
         if (!(PREFETCH && mp)) {
             if (KQ) fetch_raw<D, KT>(rawK, kbase, p.k_nb1, kv0, lane);
             if (VQ) fetch_raw<D, VT>(rawV, vbase, p.v_nb1, kv0, lane);
         }
+        if (KT == KV_F16) stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane, rawK, 1.0f);
+        if (VT == KV_F16) stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane, rawV, PV_SCALE);
+        if (mrowp && !mp) {                       // skip a tile that is fully masked for this column
+            const __half mv = *(const __half *)(mrowp + (uint64_t)(kv0 + lane) * 2);
+            if (!__any_sync(0xffffffffu, !(__hisinf(mv) && __half2float(mv) < 0.0f))) { cp_async_wait_all(); continue; }
+        }
         if (KQ || VQ) { cp_async_wait_all(); __syncwarp(); }
-        stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane, rawK, 1.0f);
-        stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane, rawV, PV_SCALE);
+        if (KT != KV_F16) stage_tile<D, KT, true>(sK, sKs, kbase, p.k_nb1, kv0, lane, rawK, 1.0f);
+        if (VT != KV_F16) stage_tile<D, VT, true>(sV, sVs, vbase, p.v_nb1, kv0, lane, rawV, PV_SCALE);
         if (KT == KV_F16 || VT == KV_F16) cp_async_wait_all();
         __syncwarp();
         if (PREFETCH && mp && it + NWARP < it_end) {
@@ -938,26 +943,56 @@ __global__ void __launch_bounds__(128) b200_fattn_combine_kernel(const FaParams 
     if (!((r / p.HG) < p.QC && col < p.n_q && hin < p.gq)) return;
     const float *base = p.part + ((uint64_t)tile_id * p.n_splits * 16 + r) * (D + 2);
     const uint64_t sstride = (uint64_t)16 * (D + 2);
-    float M = -INFINITY;
-    for (int s = lane; s < p.n_splits; s += 32) M = fmaxf(M, base[s * sstride + D]);
-    M = warp_reduce_max(M);
-    float L = 0.0f;
-    for (int s = lane; s < p.n_splits; s += 32) {
-        const float ms = base[s * sstride + D];
-        L += ms == -INFINITY ? 0.0f : base[s * sstride + D + 1] * expf(ms - M);
-    }
-    // fixed-order sum over lanes (xor tree is order-independent of scheduling)
-    L = warp_reduce_sum(L);
     constexpr int PER = D / 32;
     float acc[PER];
 #pragma unroll
     for (int j = 0; j < PER; j++) acc[j] = 0.0f;
-    for (int s = 0; s < p.n_splits; s++) {
-        const float *pp = base + s * sstride;
-        const float ms = pp[D];
-        const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+    float M = -INFINITY, L = 0.0f;
+    if (p.n_splits <= 32) {
+        // Same arithmetic in the same order as the general path below, but every load of a group of 8 splits is in flight before anything
+        // is consumed: the merge costs ~2 L2 round trips instead of n_splits + 2 (a decode step runs this kernel once per layer, on the
+        // token's critical path).  Lane s holds (m_s, l_s); the per-split factors come from shuffles instead of reloads.
+        const float ms_l = lane < p.n_splits ? base[lane * sstride + D] : -INFINITY;
+        const float ls_l = lane < p.n_splits ? base[lane * sstride + D + 1] : 0.0f;
+        float v[8][PER];
+        auto fetch = [&](int s0) {
 #pragma unroll
-        for (int j = 0; j < PER; j++) acc[j] += pp[lane + 32 * j] * f;
+            for (int u = 0; u < 8; u++)
+                if (s0 + u < p.n_splits) {
+#pragma unroll
+                    for (int j = 0; j < PER; j++) v[u][j] = base[(s0 + u) * sstride + lane + 32 * j];
+                }
+        };
+        fetch(0);
+        M = warp_reduce_max(ms_l);
+        L = warp_reduce_sum(ms_l == -INFINITY ? 0.0f : ls_l * expf(ms_l - M));
+        for (int s0 = 0; s0 < p.n_splits; s0 += 8) {
+            if (s0) fetch(s0);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (s0 + u < p.n_splits) {
+                    const float ms = __shfl_sync(0xffffffffu, ms_l, s0 + u);
+                    const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+#pragma unroll
+                    for (int j = 0; j < PER; j++) acc[j] += v[u][j] * f;
+                }
+        }
+    } else {
+        for (int s = lane; s < p.n_splits; s += 32) M = fmaxf(M, base[s * sstride + D]);
+        M = warp_reduce_max(M);
+        for (int s = lane; s < p.n_splits; s += 32) {
+            const float ms = base[s * sstride + D];
+            L += ms == -INFINITY ? 0.0f : base[s * sstride + D + 1] * expf(ms - M);
+        }
+        // fixed-order sum over lanes (xor tree is order-independent of scheduling)
+        L = warp_reduce_sum(L);
+        for (int s = 0; s < p.n_splits; s++) {
+            const float *pp = base + s * sstride;
+            const float ms = pp[D];
+            const float f = ms == -INFINITY ? 0.0f : expf(ms - M);
+#pragma unroll
+            for (int j = 0; j < PER; j++) acc[j] += pp[lane + 32 * j] * f;
+        }
     }
     float *o = p.dst + ((uint64_t)col * p.H + hk * p.gq + hin) * D;
 #pragma unroll
