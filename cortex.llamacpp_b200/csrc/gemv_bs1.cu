@@ -360,8 +360,12 @@ __global__ void __launch_bounds__(BS1_MAX_THREADS, 1) b200_gemv_bs1_kernel(const
             // first fill: a sliding window of `win` stages in flight per SM (stage l is issued when stage l - win has landed) instead of the
             // whole ring at once -- 32 MB queued chip-wide would put 3-5 us of DRAM queueing in front of the first stage AND of the
             // activation loads; 8-12 stages cover the bandwidth-delay product.  Afterwards a stage is re-armed the moment it is released.
+            // "stage l - win has landed" = its `full` barrier is past phase 0, OR its lane has already re-armed it (use >= 2: a re-arm needs
+            // the consumer's release, which needs the landing).  The second clause is monotonic: the 1-bit phase test alone would read
+            // false again after an even number of landings, should this warp ever be held off for a whole consume + refill period.
+            const int use_behind = __shfl_sync(0xffffffffu, use, lane >= win ? lane - win : lane);
             bool go = lane < ns && i < nchunks;
-            if (go) go = use == 0 ? (lane < win || mbar_test_wait(&full[lane - win], 0)) : mbar_test_wait(&empty[lane], (use - 1) & 1);
+            if (go) go = use == 0 ? (lane < win || use_behind >= 2 || mbar_test_wait(&full[lane - win], 0)) : mbar_test_wait(&empty[lane], (use - 1) & 1);
             if (go) {
                 int s = 0, lo_s = lo[0], hi_s = hi[0], c0 = 0;
 #pragma unroll
