@@ -153,7 +153,11 @@ B200_API int         b200_supports_op(int device, const b200_op *op); /* 1 / 0 *
 B200_API int         b200_graph_compute(b200_ctx *ctx, const b200_op *ops, int n_ops);
 B200_API int         b200_op_compute(b200_ctx *ctx, const b200_op *op);   /* single op, no fusion */
 B200_API int64_t     b200_kernel_launches(const b200_ctx *ctx);       /* kernels launched by this ctx so far (bench: gpu_launches) */
-B200_API int         b200_set_option(b200_ctx *ctx, const char *key, int value); /* "cuda_graphs", "fusion", "pdl" */
+/* keys: "cuda_graphs", "fusion" (0 off, 1 two-op, 2 + llama layer fusions), "pdl", "cpu_exact" (parity mode: the reference CPU
+ * backend's summation order), "l2_prefetch" (0 off / 1 / 2), "ffn_pair" (gate|up GEMV writes silu(gate)*up; default 1),
+ * "fa_merge_in_wo" (output projection merges the flash-attention KV splits; default 0), "dstep" (persistent decode-step kernel;
+ * default 0), "debug_skip" (timing experiments only).  Changing one drops the captured CUDA graphs. */
+B200_API int         b200_set_option(b200_ctx *ctx, const char *key, int value);
 
 /* ---- tensor parallelism: one process (and one b200_ctx) per GPU ------------------------------
  * Replaces the split-buffer matmul driver ggml_cuda_op_mul_mat + ggml_backend_cuda_split_buffer_type
